@@ -1,0 +1,81 @@
+"""ctypes binding of ``libfastvim_b200.so`` (the C ABI declared in include/fastvim_b200.h).
+
+PyTorch is plumbing here: it owns device memory and streams; every hot-path op goes through
+the ``fv_*`` entry points below.  There is no CPU or PyTorch fallback: if the library is not
+built, ``lib()`` raises, and every op in this package fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libfastvim_b200.so")
+
+FV_F32, FV_BF16 = 0, 1
+FV_POOL_MEAN, FV_POOL_MAX = 0, 1
+
+
+class fv_geom(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("dim", C.c_int32), ("outer", C.c_int32), ("pool", C.c_int32),
+                ("inner", C.c_int32), ("tok_stride_outer", C.c_int64), ("tok_stride_pool", C.c_int64),
+                ("tok_stride_inner", C.c_int64)]
+
+
+_P, _I, _L, _F = C.c_void_p, C.c_int, C.c_int64, C.c_float
+_G = C.POINTER(fv_geom)
+
+# name -> argtypes; every symbol declared in include/fastvim_b200.h must be listed here
+# (tests/test_abi.py cross-checks this table against the header).
+SIGNATURES = {
+    "fv_conv_pool_fwd": [_G, _I, _P, _L, _L, _P, _P, _F, _I, _P, _P],
+    "fv_scan_fwd": [_G, _I, _P, _P, _L, _I, _I, _P, _P, _P, _I, _P, _P],
+    "fv_gate_fwd": [_G, _I, _P, _P, _L, _L, _P, _P, _P, _P, _P, _P, _F, _P, _L, _L, _P, _P],
+    "fv_norm_gate_apply": [_G, _I, _I, _P, _L, _L, _P, _L, _L, _P, _P, _P, _F, _P],
+    "fv_add_norm_fwd": [_I, _L, _I, _P, _L, _P, _P, _P, _F, _I, _P, _L, _P, _P, _P, _P],
+    "fv_selective_scan_fwd": [_I, _I, _I, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P],
+}
+
+_lib = None
+
+
+class FastVimLibraryError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded C-ABI library.  Raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FastVimLibraryError(
+            f"{LIB_PATH} not found: build it with `python -m fastvim_b200.build` "
+            "(fastvim_b200 has no CPU/PyTorch fallback for its CUDA kernels)")
+    l = C.CDLL(LIB_PATH)
+    l.fv_last_error.restype = C.c_char_p
+    l.fv_last_error.argtypes = []
+    l.fv_version.restype = C.c_int
+    l.fv_launch_count.restype = C.c_int64
+    l.fv_reset_launch_count.restype = None
+    for name, args in SIGNATURES.items():
+        fn = getattr(l, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    _lib = l
+    return l
+
+
+def call(name: str, *args) -> None:
+    l = lib()
+    rc = getattr(l, name)(*args)
+    if rc != 0:
+        raise FastVimLibraryError(f"{name} failed (rc={rc}): {l.fv_last_error().decode()}")
+
+
+def launch_count() -> int:
+    return int(lib().fv_launch_count())
+
+
+def reset_launch_count() -> None:
+    lib().fv_reset_launch_count()

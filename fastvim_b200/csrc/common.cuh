@@ -1,0 +1,154 @@
+// fastvim_b200 -- shared device/host helpers (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <type_traits>
+
+#include "fastvim_b200.h"
+
+namespace fv {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- host side -------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int finish_launch(const char* what);  // counts the launch, maps cudaGetLastError to rc
+int fail(const char* fmt, ...);       // set_error + return 1
+
+#define FV_REQUIRE(cond, ...)                      \
+    do {                                           \
+        if (!(cond)) return ::fv::fail(__VA_ARGS__); \
+    } while (0)
+
+static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- geometry --------------------------------------------------------------------
+struct Geom {
+    int B, D, outer, pool, inner, Lp, L;
+    int64_t so, sp, si;
+};
+static inline Geom make_geom(const fv_geom* g) {
+    Geom r;
+    r.B = g->batch; r.D = g->dim; r.outer = g->outer; r.pool = g->pool; r.inner = g->inner;
+    r.Lp = g->outer * g->inner; r.L = g->outer * g->pool * g->inner;
+    r.so = g->tok_stride_outer; r.sp = g->tok_stride_pool; r.si = g->tok_stride_inner;
+    return r;
+}
+// sequence position t in [0, L) -> memory token row of the image
+__device__ __forceinline__ int64_t seq_to_row(const Geom& g, int t) {
+    if (g.inner == 1) {
+        int o = t / g.pool, p = t - o * g.pool;
+        return o * g.so + p * g.sp;
+    }
+    int q = t / g.inner, i = t - q * g.inner;
+    int o = q / g.pool, p = q - o * g.pool;
+    return o * g.so + p * g.sp + i * g.si;
+}
+// pooled position j, slot p -> sequence position
+__device__ __forceinline__ int pooled_to_seq(const Geom& g, int j, int p) {
+    if (g.inner == 1) return j * g.pool + p;
+    int o = j / g.inner, i = j - o * g.inner;
+    return (o * g.pool + p) * g.inner + i;
+}
+
+// ---- 4-wide vector access (V = 4 channels per thread) -----------------------------
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 ld4(const bf16* p) {
+    uint2 r = *reinterpret_cast<const uint2*>(p);
+    __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&r.x);
+    __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&r.y);
+    float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+    return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ void st4(bf16* p, float4 v) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+    uint2 r;
+    r.x = *reinterpret_cast<uint32_t*>(&a);
+    r.y = *reinterpret_cast<uint32_t*>(&b);
+    *reinterpret_cast<uint2*>(p) = r;
+}
+__device__ __forceinline__ float ld1(const float* p) { return *p; }
+__device__ __forceinline__ float ld1(const bf16* p) { return __bfloat162float(*p); }
+__device__ __forceinline__ void st1(float* p, float v) { *p = v; }
+__device__ __forceinline__ void st1(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+// ---- transcendental helpers --------------------------------------------------------
+// The non-GEMM half of the block is co-limited by the MUFU pipe (16 ops/clk/SM) and HBM:
+// per full-resolution element the path needs 5 SiLUs (2 conv directions in K1, the same 2
+// recomputed in K2b, and the z gate).  exp+rcp costs 2 MUFU per SiLU.  For bf16 I/O we use
+// silu(x) = h + h*tanh(h), h = x/2, with tanh.approx.f16x2: ONE MUFU op per TWO elements
+// (abs error ~2^-11, four times below the bf16 rounding the result receives anyway).
+// fp32 I/O keeps the exact form.
+__device__ __forceinline__ float silu_exact(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+__device__ __forceinline__ void silu_pair_fast(float& a, float& b) {
+    float ha = 0.5f * a, hb = 0.5f * b;
+    __half2 h = __floats2half2_rn(ha, hb);
+    uint32_t hi = *reinterpret_cast<uint32_t*>(&h), ho;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(ho) : "r"(hi));
+    float2 t = __half22float2(*reinterpret_cast<__half2*>(&ho));
+    a = fmaf(ha, t.x, ha);
+    b = fmaf(hb, t.y, hb);
+}
+template <bool FAST>
+__device__ __forceinline__ float4 silu4(float4 v) {
+    if (FAST) {
+        silu_pair_fast(v.x, v.y);
+        silu_pair_fast(v.z, v.w);
+    } else {
+        v.x = silu_exact(v.x); v.y = silu_exact(v.y); v.z = silu_exact(v.z); v.w = silu_exact(v.w);
+    }
+    return v;
+}
+// d silu(x)/dx = s + x*s*(1-s), s = sigmoid(x)
+__device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float dsilu(float x) {
+    float s = sigmoidf_(x);
+    return s * fmaf(x, 1.f - s, 1.f);
+}
+// softplus with the reference threshold (selective_scan_fwd_kernel.cuh:153-156)
+__device__ __forceinline__ float softplus20(float x) { return x <= 20.f ? log1pf(__expf(x)) : x; }
+
+template <typename T> struct is_fast : std::false_type {};
+template <> struct is_fast<bf16> : std::true_type {};
+
+__device__ __forceinline__ float4 operator+(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float4 fma4(float4 a, float4 b, float4 c) {
+    return make_float4(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y), fmaf(a.z, b.z, c.z), fmaf(a.w, b.w, c.w));
+}
+__device__ __forceinline__ float4 max4(float4 a, float4 b) {
+    return make_float4(fmaxf(a.x, b.x), fmaxf(a.y, b.y), fmaxf(a.z, b.z), fmaxf(a.w, b.w));
+}
+__device__ __forceinline__ float4 scale4(float4 a, float s) { return make_float4(a.x * s, a.y * s, a.z * s, a.w * s); }
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Depthwise conv taps of 4 consecutive channels, transposed to one float4 per tap.
+// conv_w is (dim, 4): out[t] = bias + sum_k w[k] * x[t-3+k]  (causal) -- oracle/fastvim_oracle.py
+// causal_conv1d_oracle; the b-direction applies the same taps to the time-reversed sequence:
+// out_b[t] = bias_b + sum_k w_b[k] * x[t+3-k].
+struct Taps {
+    float4 w[4];
+    float4 b;
+};
+__device__ __forceinline__ Taps load_taps(const float* cw, const float* cb, int D, int dir, int d0) {
+    Taps t;
+    const float* p = cw + ((int64_t)dir * D + d0) * 4;
+    float4 c0 = ld4(p), c1 = ld4(p + 4), c2 = ld4(p + 8), c3 = ld4(p + 12);
+    t.w[0] = make_float4(c0.x, c1.x, c2.x, c3.x);
+    t.w[1] = make_float4(c0.y, c1.y, c2.y, c3.y);
+    t.w[2] = make_float4(c0.z, c1.z, c2.z, c3.z);
+    t.w[3] = make_float4(c0.w, c1.w, c2.w, c3.w);
+    t.b = cb ? ld4(cb + (int64_t)dir * D + d0) : zero4();
+    return t;
+}
+
+}  // namespace fv

@@ -1,0 +1,143 @@
+// K1 -- depthwise causal conv1d (both scan directions) + SiLU + pooling, one pass over x.
+//
+// What it replaces in the reference (paths relative to /root/reference):
+//   x.flip([-1])                                   mamba_ssm/modules/mamba_simple_faster.py:272
+//   causal_conv1d_fn(x, conv1d) / (x_flip, conv1d_b)  :274-285   (causal-conv1d 1.1.3, un-vendored)
+//   x.reshape(pre_x_shape).mean(3) [* scaling] / .max(3)  :287-305
+// i.e. one flip copy, two conv kernels and two reductions (>= 8 full-resolution passes)
+// become one read of x.  In original token order the b-direction is the anti-causal conv
+// out_b[t] = silu(b_b + sum_k w_b[k] x[t+3-k]), so no flip is needed.
+//
+// Mapping: token-major x (B, L, D); one thread owns 4 consecutive channels of one pooled
+// position j and slides a 7-row register window over the `pool` tokens of that position
+// (+3 halo rows each side, shared through L1/L2 with the neighbouring positions).  A warp
+// therefore reads 32 x 4 channels = 256 B (bf16) / 512 B (fp32) contiguous per row: fully
+// coalesced, independent of the token permutation (rotated layers only change row numbers).
+// HBM-bound by design: algorithmic bytes = B*L*D*s read + 2*B*Lp*D*s written.
+#include "common.cuh"
+
+namespace fv {
+
+template <typename T>
+__device__ __forceinline__ float4 load_row4(const Geom& g, const T* xb, int64_t ldx, int d0, int t) {
+    if (t < 0 || t >= g.L) return zero4();
+    return ld4(xb + seq_to_row(g, t) * ldx + d0);
+}
+
+template <bool FAST>
+__device__ __forceinline__ void conv_both(const float4 (&w)[7], const Taps& tf, const Taps& tb,
+                                          float4& xf, float4& xb_) {
+    float4 af = tf.b, ab = tb.b;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        af = fma4(tf.w[k], w[k], af);      // x[c-3+k]
+        ab = fma4(tb.w[k], w[6 - k], ab);  // x[c+3-k]
+    }
+    xf = silu4<FAST>(af);
+    xb_ = silu4<FAST>(ab);
+}
+
+template <typename T, bool MAXPOOL, bool INNER1>
+__global__ void __launch_bounds__(256)
+conv_pool_fwd_kernel(Geom g, const T* __restrict__ x, int64_t ldx, int64_t xbs,
+                     const float* __restrict__ cw, const float* __restrict__ cb, float scale,
+                     T* __restrict__ u) {
+    constexpr bool FAST = is_fast<T>::value;
+    const int nvec = g.D >> 2;
+    int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (item >= (int64_t)g.B * g.Lp * nvec) return;
+    const int v = (int)(item % nvec);
+    const int64_t bj = item / nvec;
+    const int j = (int)(bj % g.Lp), b = (int)(bj / g.Lp);
+    const int d0 = v * 4;
+    const T* xb = x + (int64_t)b * xbs;
+    const Taps tf = load_taps(cw, cb, g.D, 0, d0), tb = load_taps(cw, cb, g.D, 1, d0);
+
+    float4 accf = MAXPOOL ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : zero4();
+    float4 accb = accf;
+    float4 w[7];
+    if (INNER1) {
+        constexpr int PF = 4;  // rows prefetched ahead of the window
+        const int t0 = j * g.pool;
+#pragma unroll
+        for (int i = 0; i < 6; ++i) w[i + 1] = load_row4(g, xb, ldx, d0, t0 - 3 + i);
+        float4 ring[PF];
+#pragma unroll
+        for (int i = 0; i < PF; ++i) ring[i] = load_row4(g, xb, ldx, d0, t0 + 3 + i);
+        for (int p0 = 0; p0 < g.pool; p0 += PF) {
+#pragma unroll
+            for (int i = 0; i < PF; ++i) {
+                const int p = p0 + i;
+                if (p < g.pool) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) w[k] = w[k + 1];
+                    w[6] = ring[i];
+                    ring[i] = (p + PF < g.pool) ? load_row4(g, xb, ldx, d0, t0 + 3 + p + PF) : zero4();
+                    float4 xf, xr;
+                    conv_both<FAST>(w, tf, tb, xf, xr);
+                    accf = MAXPOOL ? max4(accf, xf) : accf + xf;
+                    accb = MAXPOOL ? max4(accb, xr) : accb + xr;
+                }
+            }
+        }
+    } else {
+        for (int p = 0; p < g.pool; ++p) {
+            const int c = pooled_to_seq(g, j, p);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) w[k] = load_row4(g, xb, ldx, d0, c - 3 + k);
+            float4 xf, xr;
+            conv_both<FAST>(w, tf, tb, xf, xr);
+            accf = MAXPOOL ? max4(accf, xf) : accf + xf;
+            accb = MAXPOOL ? max4(accb, xr) : accb + xr;
+        }
+    }
+    if (!MAXPOOL) {
+        const float m = scale / (float)g.pool;
+        accf = scale4(accf, m);
+        accb = scale4(accb, m);
+    }
+    const int64_t plane = (int64_t)g.B * g.Lp * g.D;
+    T* uo = u + ((int64_t)b * g.Lp + j) * g.D + d0;
+    st4(uo, accf);
+    st4(uo + plane, accb);
+}
+
+template <typename T>
+static int launch_conv_pool(const Geom& g, const T* x, int64_t ldx, int64_t xbs, const float* cw,
+                            const float* cb, float scale, int pool_mode, T* u, cudaStream_t st) {
+    const int64_t items = (int64_t)g.B * g.Lp * (g.D / 4);
+    const int threads = 256;
+    const int64_t blocks = (items + threads - 1) / threads;
+    FV_REQUIRE(blocks < (1ll << 31), "conv_pool: grid too large");
+    dim3 grid((unsigned)blocks), block(threads);
+    const bool in1 = g.inner == 1;
+    if (pool_mode == FV_POOL_MAX) {
+        if (in1) conv_pool_fwd_kernel<T, true, true><<<grid, block, 0, st>>>(g, x, ldx, xbs, cw, cb, scale, u);
+        else conv_pool_fwd_kernel<T, true, false><<<grid, block, 0, st>>>(g, x, ldx, xbs, cw, cb, scale, u);
+    } else {
+        if (in1) conv_pool_fwd_kernel<T, false, true><<<grid, block, 0, st>>>(g, x, ldx, xbs, cw, cb, scale, u);
+        else conv_pool_fwd_kernel<T, false, false><<<grid, block, 0, st>>>(g, x, ldx, xbs, cw, cb, scale, u);
+    }
+    return finish_launch("conv_pool_fwd");
+}
+
+int check_geom(const fv_geom* g, const char* who);
+
+}  // namespace fv
+
+extern "C" int fv_conv_pool_fwd(const fv_geom* g_, int dtype, const void* x, int64_t ldx,
+                                int64_t x_bstride, const float* conv_w, const float* conv_b,
+                                float scale, int pool_mode, void* u_out, void* stream) {
+    using namespace fv;
+    if (int rc = check_geom(g_, "fv_conv_pool_fwd")) return rc;
+    FV_REQUIRE(x && conv_w && u_out, "fv_conv_pool_fwd: null pointer");
+    FV_REQUIRE(ldx % 4 == 0 && x_bstride % 4 == 0, "fv_conv_pool_fwd: ldx/x_bstride must be multiples of 4 elements");
+    FV_REQUIRE(pool_mode == FV_POOL_MEAN || pool_mode == FV_POOL_MAX, "fv_conv_pool_fwd: bad pool_mode %d", pool_mode);
+    Geom g = make_geom(g_);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == FV_F32)
+        return launch_conv_pool<float>(g, (const float*)x, ldx, x_bstride, conv_w, conv_b, scale, pool_mode, (float*)u_out, st);
+    if (dtype == FV_BF16)
+        return launch_conv_pool<bf16>(g, (const bf16*)x, ldx, x_bstride, conv_w, conv_b, scale, pool_mode, (bf16*)u_out, st);
+    return fail("fv_conv_pool_fwd: unsupported dtype %d", dtype);
+}

@@ -1,0 +1,49 @@
+// fastvim_b200 -- error reporting, launch accounting, argument checks (host side of the C ABI).
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace fv {
+
+static thread_local char g_err[512] = "";
+static thread_local int64_t g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int fail(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return 1;
+}
+int finish_launch(const char* what) {
+    ++g_launches;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
+        return 2;
+    }
+    return 0;
+}
+int check_geom(const fv_geom* g, const char* who) {
+    FV_REQUIRE(g != nullptr, "%s: null geometry", who);
+    FV_REQUIRE(g->batch > 0 && g->dim > 0 && g->outer > 0 && g->pool > 0 && g->inner > 0,
+               "%s: non-positive geometry (batch %d dim %d outer %d pool %d inner %d)", who, g->batch,
+               g->dim, g->outer, g->pool, g->inner);
+    FV_REQUIRE(g->dim % 4 == 0, "%s: dim (%d) must be a multiple of 4", who, g->dim);
+    FV_REQUIRE((int64_t)g->outer * g->pool * g->inner < (1ll << 30), "%s: sequence too long", who);
+    return 0;
+}
+
+}  // namespace fv
+
+extern "C" const char* fv_last_error(void) { return fv::g_err; }
+extern "C" int fv_version(void) { return 100; }
+extern "C" int64_t fv_launch_count(void) { return fv::g_launches; }
+extern "C" void fv_reset_launch_count(void) { fv::g_launches = 0; }

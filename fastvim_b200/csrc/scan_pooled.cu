@@ -1,0 +1,156 @@
+// K2a -- bidirectional selective scan over the POOLED sequence, dt_proj + softplus fused.
+//
+// What it replaces in the reference (paths relative to /root/reference):
+//   dt = dt_proj.weight @ dt.t(); rearrange; B/C .contiguous()       mamba_simple_faster.py:328-337, 384-394
+//   selective_scan_fn(x_c, dt, A, B, C, D=None, z=None, delta_bias, delta_softplus=True)  :343-354, 397-410
+//     -> selective_scan_fwd_kernel  csrc/selective_scan/selective_scan_fwd_kernel.cuh:67-303
+// The reference launches grid (batch, dim) x 32 threads with 14 of 128 tile slots live at
+// 224^2 and writes a (B, D, 1, 2N) fp32 checkpoint larger than its inputs.
+// Here: token-major pooled inputs, one thread per (image, channel) holding the N fp32 states
+// in registers and running BOTH directions (forward ascending, backward descending over the
+// un-flipped rows); B/C and the low-rank dt rows of the image are staged once per chunk in
+// shared memory and broadcast to the 128 channels of the CTA; output is the direction sum
+// s[b, j, d] = scan_f[j] + scan_b[j] in fp32 (the only thing the epilogue needs).
+//
+// Arithmetic per (b, d, j, dir): delta = softplus(bias + W_dt[d,:] . dt[j,:]);
+//   h[n] = exp2(delta * A[d,n] * log2e) * h[n] + delta * B[j,n] * u[j,d];  y = sum_n h[n] C[j,n]
+// (same exp2 formulation as fwd_kernel.cuh:169-171, 216).  MUFU-bound: 2*N ex2 per pooled element.
+#include "common.cuh"
+
+namespace fv {
+
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+constexpr int SCAN_THREADS = 128;
+constexpr int SCAN_LC = 32;  // pooled rows staged per chunk
+
+template <typename T, int RT, int N>
+__global__ void __launch_bounds__(SCAN_THREADS)
+scan_fwd_kernel(Geom g, const T* __restrict__ u, const T* __restrict__ xdbl, int64_t ldxd, int R,
+                const float* __restrict__ dtw, const float* __restrict__ dtb,
+                const float* __restrict__ A, int a_is_log, float* __restrict__ s) {
+    constexpr int WROW = RT + 2 * N;
+    __shared__ __align__(16) float tile[SCAN_LC][WROW];
+    const int b = blockIdx.y;
+    const int d = blockIdx.x * SCAN_THREADS + threadIdx.x;
+    const bool live = d < g.D;
+    const int dd = live ? d : 0;
+    const int nchunks = (g.Lp + SCAN_LC - 1) / SCAN_LC;
+    const int64_t plane = (int64_t)g.B * g.Lp * g.D;
+    constexpr float LOG2E = 1.4426950408889634f;
+
+#pragma unroll 1
+    for (int dir = 0; dir < 2; ++dir) {
+        float A2[N], W[RT], h[N];
+        {
+            const float* Ap = A + ((int64_t)dir * g.D + dd) * N;
+#pragma unroll
+            for (int n = 0; n < N; ++n) {
+                float a = Ap[n];
+                A2[n] = (a_is_log ? -expf(a) : a) * LOG2E;
+                h[n] = 0.f;
+            }
+            const float* Wp = dtw + ((int64_t)dir * g.D + dd) * R;
+#pragma unroll
+            for (int j = 0; j < RT; ++j) W[j] = j < R ? Wp[j] : 0.f;
+        }
+        const float bias = dtb[(int64_t)dir * g.D + dd];
+        const T* ub = u + dir * plane + (int64_t)b * g.Lp * g.D + dd;
+        const T* xd = xdbl + ((int64_t)dir * g.B + b) * g.Lp * ldxd;
+        float* sb = s + (int64_t)b * g.Lp * g.D + dd;
+
+#pragma unroll 1
+        for (int cc = 0; cc < nchunks; ++cc) {
+            const int chunk = dir == 0 ? cc : nchunks - 1 - cc;
+            const int r_lo = chunk * SCAN_LC;
+            const int rows = min(SCAN_LC, g.Lp - r_lo);
+            __syncthreads();
+            for (int i = threadIdx.x; i < rows * WROW; i += SCAN_THREADS) {
+                const int r = i / WROW, c = i - r * WROW;
+                float v = 0.f;
+                if (c < RT) {
+                    if (c < R) v = ld1(xd + (int64_t)(r_lo + r) * ldxd + c);
+                } else {
+                    v = ld1(xd + (int64_t)(r_lo + r) * ldxd + R + (c - RT));
+                }
+                tile[r][c] = v;
+            }
+            __syncthreads();
+            int r = dir == 0 ? r_lo : r_lo + rows - 1;
+            const int step = dir == 0 ? 1 : -1;
+            float un = live ? ld1(ub + (int64_t)r * g.D) : 0.f;
+#pragma unroll 1
+            for (int rr = 0; rr < rows; ++rr, r += step) {
+                const float uu = un;
+                if (rr + 1 < rows && live) un = ld1(ub + (int64_t)(r + step) * g.D);
+                const float* row = tile[r - r_lo];
+                float dt = bias;
+#pragma unroll
+                for (int j = 0; j < RT; j += 4) {
+                    float4 q = *reinterpret_cast<const float4*>(row + j);
+                    dt = fmaf(W[j], q.x, dt); dt = fmaf(W[j + 1], q.y, dt);
+                    dt = fmaf(W[j + 2], q.z, dt); dt = fmaf(W[j + 3], q.w, dt);
+                }
+                const float delta = softplus20(dt);
+                const float du = delta * uu;
+                float y = 0.f;
+#pragma unroll
+                for (int n = 0; n < N; n += 4) {
+                    float4 Bq = *reinterpret_cast<const float4*>(row + RT + n);
+                    float4 Cq = *reinterpret_cast<const float4*>(row + RT + N + n);
+                    h[n] = fmaf(ex2(delta * A2[n]), h[n], du * Bq.x);             y = fmaf(h[n], Cq.x, y);
+                    h[n + 1] = fmaf(ex2(delta * A2[n + 1]), h[n + 1], du * Bq.y); y = fmaf(h[n + 1], Cq.y, y);
+                    h[n + 2] = fmaf(ex2(delta * A2[n + 2]), h[n + 2], du * Bq.z); y = fmaf(h[n + 2], Cq.z, y);
+                    h[n + 3] = fmaf(ex2(delta * A2[n + 3]), h[n + 3], du * Bq.w); y = fmaf(h[n + 3], Cq.w, y);
+                }
+                if (live) {
+                    float* sp = sb + (int64_t)r * g.D;
+                    *sp = dir == 0 ? y : *sp + y;
+                }
+            }
+        }
+    }
+}
+
+int check_geom(const fv_geom* g, const char* who);
+
+template <typename T, int N>
+static int launch_scan(const Geom& g, const T* u, const T* xdbl, int64_t ldxd, int R, const float* dtw,
+                       const float* dtb, const float* A, int a_is_log, float* s, cudaStream_t st) {
+    dim3 grid(ceil_div(g.D, SCAN_THREADS), g.B), block(SCAN_THREADS);
+#define FV_SCAN_CASE(RT_)                                                                          \
+    if (R <= RT_) {                                                                                \
+        scan_fwd_kernel<T, RT_, N><<<grid, block, 0, st>>>(g, u, xdbl, ldxd, R, dtw, dtb, A, a_is_log, s); \
+        return finish_launch("scan_fwd");                                                          \
+    }
+    FV_SCAN_CASE(8) FV_SCAN_CASE(12) FV_SCAN_CASE(16) FV_SCAN_CASE(24) FV_SCAN_CASE(32) FV_SCAN_CASE(48) FV_SCAN_CASE(64)
+#undef FV_SCAN_CASE
+    return fail("fv_scan_fwd: dt_rank %d > 64 not supported", R);
+}
+
+}  // namespace fv
+
+extern "C" int fv_scan_fwd(const fv_geom* g_, int dtype, const void* u, const void* xdbl,
+                           int64_t ld_xdbl, int dt_rank, int dstate, const float* dt_w,
+                           const float* dt_bias, const float* A, int a_is_log, float* s_out,
+                           void* stream) {
+    using namespace fv;
+    if (int rc = check_geom(g_, "fv_scan_fwd")) return rc;
+    FV_REQUIRE(u && xdbl && dt_w && dt_bias && A && s_out, "fv_scan_fwd: null pointer");
+    FV_REQUIRE(dt_rank > 0 && ld_xdbl >= dt_rank + 2 * dstate, "fv_scan_fwd: ld_xdbl %lld < R+2N", (long long)ld_xdbl);
+    FV_REQUIRE(g_->batch <= 65535, "fv_scan_fwd: batch > 65535");
+    Geom g = make_geom(g_);
+    cudaStream_t st = (cudaStream_t)stream;
+#define FV_DISPATCH(T_)                                                                             \
+    if (dstate == 16) return launch_scan<T_, 16>(g, (const T_*)u, (const T_*)xdbl, ld_xdbl, dt_rank, dt_w, dt_bias, A, a_is_log, s_out, st); \
+    if (dstate == 8) return launch_scan<T_, 8>(g, (const T_*)u, (const T_*)xdbl, ld_xdbl, dt_rank, dt_w, dt_bias, A, a_is_log, s_out, st);   \
+    return fail("fv_scan_fwd: d_state %d not supported (8 or 16)", dstate);
+    if (dtype == FV_F32) { FV_DISPATCH(float) }
+    if (dtype == FV_BF16) { FV_DISPATCH(bf16) }
+#undef FV_DISPATCH
+    return fail("fv_scan_fwd: unsupported dtype %d", dtype);
+}

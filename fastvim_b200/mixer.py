@@ -1,0 +1,160 @@
+"""FastVim SSM mixer -- host-side mirror of the reference ``Mamba`` module.
+
+Same constructor keywords, parameter names/shapes (state-dict compatible) and ``forward``
+signature as ``mamba_ssm/modules/mamba_simple_faster.py:27-179, 181-457`` of the reference, so
+it drops into the reference's ``models/fastvim.py`` ``Block`` unchanged.  The body between
+``in_proj`` and ``out_proj`` runs on the B200 kernels of ``libfastvim_b200.so``:
+
+    in_proj (GEMM) -> K1 conv+SiLU+pool (both directions) -> x_proj (batched GEMM)
+      -> K2a bidirectional pooled scan (dt_proj + softplus fused) -> K2b broadcast + D skip +
+      LayerNorm + SiLU(z) gate -> out_proj (GEMM)
+
+in token-major layout (no (B, D, L) transposes, no flips, no repeat_interleave).  The extra
+``rotated=True`` keyword lets ``fastvim_b200.vision.Block`` fold the odd-layer token rotation
+(reference ``models/fastvim.py:192-210``) into kernel addressing instead of two copies; when
+the reference's own Block calls this module it has already permuted the tokens and
+``rotated`` stays False.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import autograd as fv_autograd
+from . import ops
+from .ops import Geometry
+
+
+class Mamba(nn.Module):
+    def __init__(self, d_model, d_state=16, d_conv=4, expand=2, dt_rank="auto", dt_min=0.001,
+                 dt_max=0.1, dt_init="random", dt_scale=1.0, dt_init_floor=1e-4, conv_bias=True,
+                 bias=False, use_fast_path=False, layer_idx=None, device=None, dtype=None,
+                 init_layer_scale=None, scanpath_type="rowwise", token_size=None,
+                 use_norm_after_ssm=True, use_our_selective_scan=False, collapse_method="mean",
+                 scaling_factor=1):
+        factory_kwargs = {"device": device, "dtype": dtype}
+        super().__init__()
+        if d_conv != 4:
+            raise NotImplementedError("fastvim_b200 kernels implement d_conv=4 (every FastVim config)")
+        self.d_model, self.d_state, self.d_conv, self.expand = d_model, d_state, d_conv, expand
+        self.d_inner = int(expand * d_model)
+        self.dt_rank = math.ceil(d_model / 16) if dt_rank == "auto" else dt_rank
+        self.use_fast_path = use_fast_path  # both reference branches compute the same function
+        self.layer_idx = layer_idx
+        self.use_our_selective_scan = use_our_selective_scan
+        self.num_of_rows, self.num_of_col = token_size[0], token_size[1]
+        self.scanpath_type = scanpath_type
+        self.scaling_factor = scaling_factor
+        self.collapse_method = collapse_method
+        self.init_layer_scale = init_layer_scale
+        if init_layer_scale is not None:
+            self.gamma = nn.Parameter(init_layer_scale * torch.ones(d_model), requires_grad=True)
+        self.in_proj = nn.Linear(d_model, self.d_inner * 2, bias=bias, **factory_kwargs)
+        self.use_norm_after_ssm = use_norm_after_ssm
+        if use_norm_after_ssm:
+            self.layernorm = nn.LayerNorm(self.d_inner, **factory_kwargs)
+        self.activation = "silu"
+        self.act = nn.SiLU()
+
+        def make_dir(special_dt_init):
+            conv = nn.Conv1d(self.d_inner, self.d_inner, bias=conv_bias, kernel_size=d_conv,
+                             groups=self.d_inner, padding=d_conv - 1, **factory_kwargs)
+            x_proj = nn.Linear(self.d_inner, self.dt_rank + d_state * 2, bias=False, **factory_kwargs)
+            dt_proj = nn.Linear(self.dt_rank, self.d_inner, bias=True, **factory_kwargs)
+            if special_dt_init:
+                # reference init, mamba_simple_faster.py:111-130.  The reference applies it to the
+                # forward direction only; dt_proj_b keeps nn.Linear's default init (:166-171).
+                dt_init_std = self.dt_rank ** -0.5 * dt_scale
+                if dt_init == "constant":
+                    nn.init.constant_(dt_proj.weight, dt_init_std)
+                elif dt_init == "random":
+                    nn.init.uniform_(dt_proj.weight, -dt_init_std, dt_init_std)
+                else:
+                    raise NotImplementedError
+                dt = torch.exp(torch.rand(self.d_inner, **factory_kwargs) * (math.log(dt_max) - math.log(dt_min))
+                               + math.log(dt_min)).clamp(min=dt_init_floor)
+                inv_dt = dt + torch.log(-torch.expm1(-dt))
+                with torch.no_grad():
+                    dt_proj.bias.copy_(inv_dt)
+                dt_proj.bias._no_reinit = True
+            A_log = torch.log(torch.arange(1, d_state + 1, dtype=torch.float32, device=device)).repeat(self.d_inner, 1)
+            A_log = nn.Parameter(A_log.contiguous())
+            A_log._no_weight_decay = True
+            Dp = nn.Parameter(torch.ones(self.d_inner, device=device))
+            Dp._no_weight_decay = True
+            return conv, x_proj, dt_proj, A_log, Dp
+
+        # creation order follows the reference so that seeded inits line up (:89-171)
+        self.conv1d, self.x_proj, self.dt_proj, self.A_log, self.D = make_dir(True)
+        self.conv1d_b, self.x_proj_b, self.dt_proj_b, self.A_b_log, self.D_b = make_dir(False)
+        self.out_proj = nn.Linear(self.d_inner, d_model, bias=bias, **factory_kwargs)
+        self.pre_x_shape = (-1, self.d_inner, self.num_of_rows, self.num_of_col)
+        self._pack_cache = {}
+
+    # ------------------------------------------------------------------ parameter packing
+    def _packed(self, act_dtype):
+        """Direction-stacked, kernel-ready copies of the small parameters, cached until any
+        parameter changes (``_version`` bump) -- inference pays the packing once."""
+        plist = list(self.parameters())
+        key = (act_dtype,) + tuple((p.data_ptr(), p._version) for p in plist if p is not None)
+        hit = self._pack_cache.get("k")
+        if hit == key:
+            return self._pack_cache["v"]
+        with torch.no_grad():
+            f32 = torch.float32
+            pk = {
+                "conv_w": torch.stack([self.conv1d.weight[:, 0], self.conv1d_b.weight[:, 0]]).to(f32).contiguous(),
+                "conv_b": None if self.conv1d.bias is None else
+                torch.stack([self.conv1d.bias, self.conv1d_b.bias]).to(f32).contiguous(),
+                "x_w_t": torch.stack([self.x_proj.weight.t(), self.x_proj_b.weight.t()]).to(act_dtype).contiguous(),
+                "dt_w": torch.stack([self.dt_proj.weight, self.dt_proj_b.weight]).to(f32).contiguous(),
+                "dt_b": torch.stack([self.dt_proj.bias, self.dt_proj_b.bias]).to(f32).contiguous(),
+                "A_log": torch.stack([self.A_log, self.A_b_log]).to(f32).contiguous(),
+                "D": torch.stack([self.D, self.D_b]).to(f32).contiguous(),
+                "in_w": self.in_proj.weight.to(act_dtype).contiguous(),
+                "in_b": None if self.in_proj.bias is None else self.in_proj.bias.to(act_dtype),
+                "out_w": self.out_proj.weight.to(act_dtype).contiguous(),
+                "out_b": None if self.out_proj.bias is None else self.out_proj.bias.to(act_dtype),
+                "ln_w": self.layernorm.weight.to(f32).contiguous() if self.use_norm_after_ssm else None,
+                "ln_b": self.layernorm.bias.to(f32).contiguous() if self.use_norm_after_ssm else None,
+            }
+        self._pack_cache = {"k": key, "v": pk}
+        return pk
+
+    def geometry(self, rotated: bool = False) -> Geometry:
+        return Geometry.grid(self.num_of_rows, self.num_of_col, rotated)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, hidden_states, inference_params=None, rotated: bool = False):
+        """hidden_states (B, L, d_model) -> (B, L, d_model)   [reference :181-457]."""
+        if inference_params is not None:
+            raise NotImplementedError("autoregressive decode is outside the FastVim vision path")
+        act_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else hidden_states.dtype
+        geom = self.geometry(rotated)
+        needs_grad = torch.is_grad_enabled() and (
+            hidden_states.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if needs_grad:
+            out = fv_autograd.mixer_forward_train(self, hidden_states, geom, act_dtype)
+        else:
+            out = self._forward_inference(hidden_states.to(act_dtype), geom, act_dtype)
+        if self.init_layer_scale is not None:
+            out = out * self.gamma
+        return out
+
+    def _forward_inference(self, h, geom, act_dtype):
+        pk = self._packed(act_dtype)
+        B, L, _ = h.shape
+        D, R, N = self.d_inner, self.dt_rank, self.d_state
+        xz = F.linear(h, pk["in_w"], pk["in_b"])                        # (B, L, 2D) token-major  [a2]
+        x, z = xz[..., :D], xz[..., D:]
+        u = ops.conv_pool_fwd(x, geom, pk["conv_w"], pk["conv_b"], float(self.scaling_factor),
+                              self.collapse_method)                      # (2, B, Lp, D)         [a3-a5]
+        xdbl = torch.bmm(u.view(2, B * geom.Lp, D), pk["x_w_t"])         # (2, B*Lp, R+2N)        [a6]
+        s = ops.scan_fwd(u, xdbl, geom, R, N, pk["dt_w"], pk["dt_b"], pk["A_log"], a_is_log=True)  # [a6-a7]
+        y = ops.gate_fwd(x, z, s, geom, pk["conv_w"], pk["conv_b"], pk["D"], pk["ln_w"], pk["ln_b"],
+                         self.layernorm.eps if self.use_norm_after_ssm else 1e-5)             # [a8-a9]
+        return F.linear(y, pk["out_w"], pk["out_b"])                     # [a10]

@@ -1,0 +1,125 @@
+/* fastvim_b200 -- C ABI of the B200-native FastVim SSM-block hot path.
+ *
+ * The reference binds its native code through pybind11 tensor-level entry points:
+ *   selective_scan_cuda.fwd / .bwd        mamba-1p1p1/csrc/selective_scan/selective_scan.cpp:226-336, 338-492, 494-497
+ *   causal_conv1d_cuda.causal_conv1d_fwd  call sites mamba_ssm/ops/selective_scan_interface.py:496-498, 751-753
+ *   Triton add+norm                       mamba_ssm/ops/triton/layernorm.py:124-191, 307-399
+ * This header is the drop-in boundary that replaces them: plain pointers and sizes, no
+ * torch types.  Contract for every entry point:
+ *   - all data pointers are DEVICE pointers owned by the caller; the library never
+ *     allocates, frees or synchronises, and launches only on `stream` (a cudaStream_t);
+ *   - returns 0 on success, non-zero on error; fv_last_error() gives the thread-local text;
+ *   - activations are `dtype` (FV_F32 | FV_BF16); parameters and scan carries are fp32;
+ *   - no mutable global state: safe to call from several host threads / streams.
+ *
+ * Layout.  Between in_proj and out_proj the reference keeps activations as (B, D, L) with
+ * L contiguous (mamba_simple_faster.py:189-193).  The B200 path keeps them TOKEN-MAJOR,
+ * (B, L, D) with D contiguous, so that (i) in_proj/out_proj are plain row-major GEMMs with
+ * no transposes, (ii) every kernel is coalesced across channels, and (iii) the odd-layer
+ * token rotation of models/fastvim.py:192-210 becomes an index map (fv_geom strides)
+ * instead of two copies.  The (B, D, L) operator API (selective_scan_fn) is served by
+ * fv_selective_scan_*.
+ */
+#ifndef FASTVIM_B200_H_
+#define FASTVIM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum { FV_F32 = 0, FV_BF16 = 1 } fv_dtype;
+typedef enum { FV_POOL_MEAN = 0, FV_POOL_MAX = 1 } fv_pool_mode;
+
+/* Sequence geometry of one mixer call.  The L tokens of an image are viewed as
+ * (outer, pool, inner): sequence position t = (o*pool + p)*inner + i, pooled position
+ * j = o*inner + i (Lp = outer*inner), and the token lives at memory row
+ * o*tok_stride_outer + p*tok_stride_pool + i*tok_stride_inner of its image.
+ *   FastVim even layer (Hr x Wc grid): (Hr, Wc, 1), strides (Wc, 1, 0)   mamba_simple_faster.py:287-297
+ *   FastVim odd layer (rotated):       (Wc, Hr, 1), strides (1, Wc, 0)   models/fastvim.py:192-210, 244-260
+ *   ChannelVim channel-first:          (Hr, Wc, tpp)                      mamba_simple_channel_faster.py:225-256
+ */
+typedef struct {
+    int32_t batch;  /* images */
+    int32_t dim;    /* d_inner channels handled by this call (a shard when channel-sharded) */
+    int32_t outer, pool, inner;
+    int64_t tok_stride_outer, tok_stride_pool, tok_stride_inner;
+} fv_geom;
+
+const char* fv_last_error(void);
+int fv_version(void);
+/* Number of kernels launched by this library on the calling thread since the last reset
+ * (bench.py's `gpu_launches`). */
+int64_t fv_launch_count(void);
+void fv_reset_launch_count(void);
+
+/* ---- K1: depthwise causal conv (both directions) + SiLU + pooling ------------------
+ * Replaces x.flip + 2x causal_conv1d_fn + 2x reshape.mean  (mamba_simple_faster.py:272-305;
+ * fused-path selective_scan_interface.py:496-508).  In original token coordinates the
+ * b-direction is the anti-causal conv.
+ *   x        (B, L, dim) token-major, row stride ldx elements, image stride x_bstride
+ *   conv_w   (2, dim, 4) fp32   [0] = conv1d.weight, [1] = conv1d_b.weight
+ *   conv_b   (2, dim)    fp32 or NULL
+ *   u_out    (2, B, Lp, dim) dtype -- pooled conv output, direction-major
+ */
+int fv_conv_pool_fwd(const fv_geom* g, int dtype, const void* x, int64_t ldx, int64_t x_bstride,
+                     const float* conv_w, const float* conv_b, float scale, int pool_mode,
+                     void* u_out, void* stream);
+
+/* ---- K2a: bidirectional selective scan over the pooled sequence, dt_proj fused -----
+ * Replaces dt_proj matmul + 2x selective_scan_fn(D=None, z=None, delta_softplus=True)
+ * (mamba_simple_faster.py:328-354, 384-410; kernel csrc/selective_scan/selective_scan_fwd_kernel.cuh:67-303).
+ *   u        (2, B, Lp, dim) dtype
+ *   xdbl     (2, B*Lp, ld_xdbl) dtype: columns [0,R) dt low-rank, [R,R+N) B, [R+N,R+2N) C  (x_proj output)
+ *   dt_w     (2, dim, R) fp32; dt_bias (2, dim) fp32; A (2, dim, N) fp32 (A_log if a_is_log)
+ *   s_out    (B, Lp, dim) fp32 = scan_f[j] + scan_b[j]  (both directions, original order)
+ */
+int fv_scan_fwd(const fv_geom* g, int dtype, const void* u, const void* xdbl, int64_t ld_xdbl,
+                int dt_rank, int dstate, const float* dt_w, const float* dt_bias, const float* A,
+                int a_is_log, float* s_out, void* stream);
+
+/* ---- K2b: broadcast-back + D skip + direction average + LayerNorm + SiLU(z) gate ---
+ * Replaces repeat_interleave, += D*x, flip/add//2, LayerNorm(d_inner), *silu(z)
+ * (mamba_simple_faster.py:356-358, 412-416, 434-441).  The conv outputs are recomputed
+ * from x instead of being stored.
+ *   ln_w/ln_b NULL => use_norm_after_ssm=False (:445-453).
+ *   y        (B, L, dim) dtype token-major, row stride ldy: the out_proj GEMM input.
+ * Channel-sharded mode (dim is a shard of d_inner): pass stats (B, L, 2) fp32; the kernel
+ * then writes the PRE-norm value to y and the shard's per-token (sum, sum of squares) to
+ * stats; after the all-reduce call fv_norm_gate_apply.
+ */
+int fv_gate_fwd(const fv_geom* g, int dtype, const void* x, const void* z, int64_t ldxz,
+                int64_t xz_bstride, const float* s, const float* conv_w, const float* conv_b,
+                const float* Dskip, const float* ln_w, const float* ln_b, float eps, void* y,
+                int64_t ldy, int64_t y_bstride, float* stats, void* stream);
+int fv_norm_gate_apply(const fv_geom* g, int dtype, int full_dim, void* y, int64_t ldy,
+                       int64_t y_bstride, const void* z, int64_t ldz, int64_t z_bstride,
+                       const float* stats, const float* ln_w, const float* ln_b, float eps,
+                       void* stream);
+
+/* ---- fused residual add + RMSNorm / LayerNorm (prenorm form) ------------------------
+ * Replaces mamba_ssm/ops/triton/layernorm.py:66-121 as used by Block.forward
+ * (models/fastvim.py:167-190): residual_out = x + residual (fp32), y = norm(residual_out)*w (+b).
+ *   residual_in may be NULL (first block); rstd_out/mean_out (rows) optional, for backward.
+ */
+int fv_add_norm_fwd(int dtype, int64_t rows, int cols, const void* x, int64_t ldx,
+                    const float* residual_in, const float* weight, const float* bias, float eps,
+                    int is_rms, void* y, int64_t ldy, float* residual_out, float* mean_out,
+                    float* rstd_out, void* stream);
+
+/* ---- operator API: selective_scan_fn on (B, D, L), L contiguous ---------------------
+ * Replaces selective_scan_cuda.fwd (selective_scan.cpp:226-336).  Real A only.
+ *   u, delta, z, out: (batch, dim, L) dtype, row stride = L (contiguous)
+ *   A (dim, N) fp32; B, C: (batch, groups, N, L) dtype ("variable") ; D, delta_bias (dim) fp32 or NULL
+ *   last_state (batch, dim, N) fp32 or NULL
+ */
+int fv_selective_scan_fwd(int dtype, int batch, int dim, int64_t L, int dstate, int groups,
+                          const void* u, const void* delta, const float* A, const void* B,
+                          const void* C, const float* D, const void* z, const float* delta_bias,
+                          int delta_softplus, void* out, float* last_state, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTVIM_B200_H_ */

@@ -1,0 +1,227 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): fp32 within 1e-4 relative, bf16 within 2e-2 relative
+(relative = max|a-b| / max|b|); pooling / broadcast / rotation indexing bit-exact.
+"""
+import math
+
+import pytest
+import torch
+
+import fastvim_oracle as O
+from util import TOL, assert_close, load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(t, dtype=None):
+    t = t.cuda()
+    return t.to(dtype) if dtype is not None and t.is_floating_point() else t
+
+
+def _mixer_from_params(p, token_size, **kw):
+    from fastvim_b200.mixer import Mamba
+
+    d_model = p["in_proj.weight"].shape[1]
+    m = Mamba(d_model, token_size=list(token_size), layer_idx=0, **kw)
+    m.load_state_dict(p, strict=True)
+    return m.cuda().eval()
+
+
+# ------------------------------------------------------------------ kernel-level
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,cols,Dm", [(14, 14, 384), (4, 6, 64), (6, 4, 48), (1, 9, 32), (16, 3, 128), (5, 1, 64)])
+@pytest.mark.parametrize("mode,sf", [("mean", 1.0), ("mean", 0.25), ("max", 1.0)])
+def test_conv_pool_fwd(dtype, rows, cols, Dm, mode, sf):
+    from fastvim_b200 import ops
+
+    torch.manual_seed(0)
+    Bt, L = 3, rows * cols
+    x = torch.randn(Bt, L, Dm)
+    cw, cb = torch.randn(2, Dm, 4) * 0.5, torch.randn(2, Dm) * 0.5
+    xq = x.to(dtype).float()  # the kernel sees the rounded input
+    xt = xq.transpose(1, 2)
+    xc_f = O.causal_conv1d_oracle(xt, cw[0], cb[0])
+    xc_b = O.causal_conv1d_oracle(xt.flip(-1), cw[1], cb[1])
+    u_f = O.pool_oracle(xc_f, rows, cols, 1, mode, sf).transpose(1, 2)
+    u_b = O.pool_oracle(xc_b, rows, cols, 1, mode, sf).flip(-1).transpose(1, 2)  # back to original row order
+    # x is a strided view (the x half of an in_proj output), as in the real call
+    xz = torch.zeros(Bt, L, 2 * Dm)
+    xz[..., :Dm] = x
+    xz = _dev(xz, dtype)
+    u = ops.conv_pool_fwd(xz[..., :Dm], ops.Geometry.grid(rows, cols), cw.cuda(), cb.cuda(), sf, mode)
+    assert u.shape == (2, Bt, rows, Dm) and u.dtype == dtype
+    assert_close(u[0], u_f, TOL[dtype], "u_f")
+    assert_close(u[1], u_b, TOL[dtype], "u_b")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_conv_pool_rotated_equals_physical_rotation(dtype):
+    """The rotated geometry must give bit-identical results to physically permuting the tokens
+    (models/fastvim.py:192-200) and running the un-rotated kernel: pure indexing."""
+    from fastvim_b200 import ops
+
+    torch.manual_seed(1)
+    Bt, H, W, Dm = 2, 5, 7, 64          # memory grid H x W; the rotated mixer sees rows=W, cols=H
+    x = _dev(torch.randn(Bt, H * W, Dm), dtype)
+    cw, cb = torch.randn(2, Dm, 4).cuda(), torch.randn(2, Dm).cuda()
+    u_rot = ops.conv_pool_fwd(x, ops.Geometry.grid(W, H, rotated=True), cw, cb)
+    x_phys = O.rotate_tokens(x, H, W).contiguous()
+    u_phys = ops.conv_pool_fwd(x_phys, ops.Geometry.grid(W, H), cw, cb)
+    assert torch.equal(u_rot, u_phys)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("Bt,Lp,Dm,R,N", [(2, 14, 384, 12, 16), (1, 128, 96, 12, 16), (3, 45, 200, 7, 16),
+                                           (2, 33, 64, 48, 16), (2, 9, 32, 2, 8)])
+def test_scan_fwd(dtype, Bt, Lp, Dm, R, N):
+    from fastvim_b200 import ops
+
+    torch.manual_seed(0)
+    u = torch.randn(2, Bt, Lp, Dm).to(dtype)
+    xdbl = (torch.randn(2, Bt * Lp, R + 2 * N) * 0.7).to(dtype)
+    dt_w = torch.randn(2, Dm, R) * R ** -0.5
+    dt_b = torch.rand(2, Dm) * 0.5 - 2.0
+    A_log = torch.log(torch.arange(1, N + 1).float()).repeat(2, Dm, 1) + 0.1 * torch.randn(2, Dm, N)
+    want = 0
+    for d in range(2):
+        uu = u[d].float().transpose(1, 2)                                  # (Bt, Dm, Lp)
+        xd = xdbl[d].float().reshape(Bt, Lp, -1)
+        delta = torch.einsum("dr,blr->bdl", dt_w[d], xd[..., :R])
+        Bm, Cm = xd[..., R:R + N].transpose(1, 2), xd[..., R + N:].transpose(1, 2)
+        if d == 1:
+            uu, delta, Bm, Cm = uu.flip(-1), delta.flip(-1), Bm.flip(-1), Cm.flip(-1)
+        s = O.selective_scan_oracle(uu, delta, -torch.exp(A_log[d]), Bm, Cm, None, None, dt_b[d], True)
+        if d == 1:
+            s = s.flip(-1)
+        want = want + s.transpose(1, 2)
+    got = ops.scan_fwd(u.cuda(), xdbl.cuda(), ops.Geometry.grid(Lp, 1), R, N, dt_w.cuda(), dt_b.cuda(),
+                       A_log.cuda(), a_is_log=True)
+    assert got.dtype == torch.float32
+    assert_close(got, want, 1e-4, "scan sum")  # inputs identical on both sides; fp32 state on both
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("cols_", [192, 384, 768, 100])
+@pytest.mark.parametrize("rms", [True, False])
+def test_add_norm_fwd(dtype, cols_, rms):
+    from fastvim_b200 import norm
+
+    torch.manual_seed(0)
+    x = torch.randn(3, 37, cols_).to(dtype)
+    res = torch.randn(3, 37, cols_)
+    w, b = torch.rand(cols_) + 0.5, (None if rms else torch.randn(cols_))
+    y_o, r_o = O.add_norm_oracle(x, w, b, res, 1e-5, rms)
+    y, r = norm.layer_norm_fn(x.cuda(), w.cuda(), None if b is None else b.cuda(), residual=res.cuda(), eps=1e-5,
+                              prenorm=True, residual_in_fp32=True, is_rms_norm=rms)
+    assert r.dtype == torch.float32 and y.dtype == dtype
+    assert torch.equal(r.cpu(), r_o)  # one fp32 add: bit-exact
+    assert_close(y, y_o.float(), TOL[dtype], "y")
+    y0 = norm.rms_norm_fn(x.cuda(), w.cuda(), None, residual=None, eps=1e-5) if rms else None
+    if rms:
+        assert_close(y0, O.add_norm_oracle(x, w, None, None, 1e-5, True)[0].float(), TOL[dtype], "y (no residual)")
+
+
+# ------------------------------------------------------------------ mixer-level
+@pytest.mark.parametrize("name", ["mixer_d32_4x6", "mixer_d32_6x4_nonorm_sf", "mixer_d48_14x14"])
+def test_mixer_forward_vs_reference_golden_fp32(name):
+    """fp32 CUDA mixer against vectors produced by the reference's own Mamba.forward."""
+    g = load_golden(name)
+    m = _mixer_from_params(g["params"], g["token_size"], use_norm_after_ssm=g["use_norm_after_ssm"],
+                           scaling_factor=g["scaling_factor"])
+    with torch.no_grad():
+        out = m(g["hidden"].cuda())
+    assert_close(out, g["out"], 1e-4, name)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("d_model,ts", [(192, (14, 14)), (192, (7, 20)), (64, (128, 2)), (96, (3, 128)), (768, (14, 14))])
+@pytest.mark.parametrize("collapse", ["mean", "max"])
+def test_mixer_forward_vs_oracle(dtype, d_model, ts, collapse):
+    if collapse == "max" and d_model != 192:
+        pytest.skip("max pooling covered at one width")
+    p = O.random_mixer_params(d_model, seed=3)
+    torch.manual_seed(0)
+    h = torch.randn(2, ts[0] * ts[1], d_model)
+    m = _mixer_from_params(p, ts, collapse_method=collapse)
+    with torch.no_grad():
+        if dtype == torch.bfloat16:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                out = m(h.cuda())
+        else:
+            out = m(h.cuda())
+    assert out.dtype == dtype
+    want = O.mixer_oracle(h, p, ts, collapse_method=collapse)
+    assert_close(out, want, TOL[dtype], f"mixer {d_model} {ts} {dtype}")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_block_rotation_folded_into_geometry(dtype):
+    """Odd layer: our Block (no token copies, rotated geometry) vs the oracle's Block.forward
+    restatement, which permutes tokens physically (models/fastvim.py:192-210)."""
+    from fastvim_b200.vision import create_block
+
+    torch.manual_seed(0)
+    d_model, ts = 64, (6, 10)
+    blk = create_block(d_model, rms_norm=True, residual_in_fp32=True, fused_add_norm=True, layer_idx=1,
+                       token_size=ts).cuda().eval()
+    with torch.no_grad():
+        for k, v in blk.named_parameters():
+            if v.dim() == 1:
+                v.add_(0.1 * torch.randn_like(v))
+    sd = {k: v.detach().cpu() for k, v in blk.state_dict().items()}
+    h, res = torch.randn(2, 60, d_model), torch.randn(2, 60, d_model)
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        out, r = blk(h.cuda().to(dtype), res.cuda())
+    want, r_o = O.block_oracle(h.to(dtype).float(), res, sd, 1, ts)
+    assert torch.equal(r.cpu(), r_o)
+    assert_close(out, want, TOL[dtype], "odd block")
+
+
+# ------------------------------------------------------------------ model-level
+def test_small_model_vs_reference_golden_fp32():
+    from fastvim_b200.vision import VisionMamba
+
+    g = load_golden("fastvim_small")
+    m = VisionMamba(img_size=(64, 96), embed_dim=32, depth=4, num_classes=10, rms_norm=True, residual_in_fp32=True,
+                    fused_add_norm=True, final_pool_type="mean", drop_path_rate=0.0)
+    m.load_state_dict(g["state_dict"], strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        logits = m(g["images"].cuda())
+    assert_close(logits, g["logits"], 1e-4, "small model logits vs reference")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fastvim_tiny_224_vs_oracle(dtype):
+    """BASELINE.json configs[0]/[1]: FastVim-T (patch16, d=192, 24 blocks), 224x224, batch 2."""
+    from fastvim_b200.vision import fastvim_tiny
+
+    torch.manual_seed(0)
+    m = fastvim_tiny(drop_path_rate=0.0).eval()
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    imgs = torch.randn(2, 3, 224, 224)
+    want = O.fastvim_oracle(imgs, sd, depth=24)
+    m = m.cuda()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        got = m(imgs.cuda())
+    assert_close(got, want, TOL[dtype], f"FastVim-T logits {dtype}")
+
+
+# ------------------------------------------------------------------ operator API
+@pytest.mark.parametrize("name", ["scan_L14_g1_full", "scan_L14_g2_full", "scan_L128_g1_full", "scan_L128_g2_full",
+                                  "scan_L300_g1_full", "scan_L300_g2_full", "scan_L64_plain", "scan_L64_constBC"])
+def test_selective_scan_fn_fwd_vs_reference_golden(name):
+    from fastvim_b200.interface import selective_scan_fn
+
+    g = load_golden(name)
+    i = {k: (v.cuda() if v is not None else None) for k, v in g["inputs"].items()}
+    with torch.no_grad():
+        out, last = selective_scan_fn(i["u"], i["delta"], i["A"], i["B"], i["C"], i["D"], z=i["z"],
+                                      delta_bias=i["delta_bias"], delta_softplus=g["delta_softplus"],
+                                      return_last_state=True)
+    # tolerances of the reference's own test (tests/ops/test_selective_scan.py:53): rtol 6e-4, atol 2e-3
+    assert torch.allclose(out.cpu(), g["out"], rtol=6e-4, atol=2e-3)
+    assert torch.allclose(last.cpu(), g["last_state"], rtol=6e-4, atol=2e-3)
+    assert_close(out, g["out"], 1e-4, "out")
+    assert_close(last, g["last_state"], 1e-4, "last_state")

@@ -1,0 +1,94 @@
+"""CPU: the oracle must reproduce the golden vectors generated from the UNMODIFIED reference
+(oracle/gen_golden.py).  This is what pins the oracle; the GPU parity tests then compare the
+CUDA path against the oracle."""
+import json
+import os
+
+import pytest
+import torch
+
+import fastvim_oracle as O
+from util import GOLDEN, load_golden, relerr
+
+SCAN_CASES = ["scan_L14_g1_full", "scan_L14_g2_full", "scan_L128_g1_full", "scan_L128_g2_full",
+              "scan_L300_g1_full", "scan_L300_g2_full", "scan_L64_plain", "scan_L64_constBC"]
+
+
+@pytest.mark.parametrize("name", SCAN_CASES)
+def test_scan_matches_reference_vectors(name):
+    g = load_golden(name)
+    ins = {k: (v.clone().requires_grad_() if v is not None else None) for k, v in g["inputs"].items()}
+    out, st = O.selective_scan_oracle(ins["u"], ins["delta"], ins["A"], ins["B"], ins["C"], ins["D"], z=ins["z"],
+                                      delta_bias=ins["delta_bias"], delta_softplus=g["delta_softplus"],
+                                      return_last_state=True)
+    out.backward(g["dout"])
+    assert relerr(out, g["out"]) < 1e-5
+    assert relerr(st, g["last_state"]) < 1e-5
+    for k, gr in g["grads"].items():
+        assert relerr(ins[k].grad, gr) < 2e-5, k
+
+
+def test_conv_matches_reference_vector():
+    g = load_golden("conv_W4")
+    assert relerr(O.causal_conv1d_oracle(g["x"], g["w"], g["b"]), g["out"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["mixer_d32_4x6", "mixer_d32_6x4_nonorm_sf", "mixer_d48_14x14"])
+def test_mixer_matches_reference_vectors(name):
+    g = load_golden(name)
+    p = {k: v.clone().requires_grad_() for k, v in g["params"].items()}
+    h = g["hidden"].clone().requires_grad_()
+    out = O.mixer_oracle(h, p, g["token_size"], use_norm_after_ssm=g["use_norm_after_ssm"],
+                         scaling_factor=g["scaling_factor"])
+    out.backward(g["dout"])
+    assert relerr(out, g["out"]) < 2e-5
+    assert relerr(h.grad, g["dhidden"]) < 5e-5
+    for k, gr in g["grads"].items():
+        assert relerr(p[k].grad, gr) < 5e-5, k
+
+
+def test_mamba_inner_matches_reference_vector():
+    g = load_golden("mamba_inner")
+    out = O.mamba_inner_oracle(g["xz"], g["conv_w"], g["conv_b"], g["x_proj_w"], g["dt_proj_w"], g["A"], None, None,
+                               g["D"], g["delta_bias"], True)
+    assert relerr(out, g["out"]) < 1e-5
+
+
+def test_rmsnorm_matches_reference_vector():
+    g = load_golden("rmsnorm")
+    y, r = O.add_norm_oracle(g["x"], g["weight"], None, g["residual"], g["eps"], True)
+    assert relerr(y, g["y"]) < 1e-6 and relerr(r, g["residual_out"]) < 1e-6
+
+
+def test_small_model_matches_reference_vectors():
+    g = load_golden("fastvim_small")
+    sd = {k: v.clone().requires_grad_() for k, v in g["state_dict"].items()}
+    logits = O.fastvim_oracle(g["images"], sd, depth=g["depth"])
+    logits.backward(g["dlogits"])
+    assert relerr(logits, g["logits"]) < 1e-5
+    for k, gr in g["grads"].items():
+        assert relerr(sd[k].grad, gr) < 2e-4, k
+
+
+def test_manifest_records_full_model_pin():
+    m = json.load(open(os.path.join(GOLDEN, "manifest.json")))
+    assert m["fastvim_tiny_224_full"]["oracle_vs_ref"] < 1e-4
+
+
+def test_rotation_is_a_pure_index_map():
+    """models/fastvim.py:192-210: rotate then inverse-rotate is the identity, bit-exact."""
+    h = torch.randn(2, 6 * 4, 5)
+    r = O.rotate_tokens(h, 6, 4)
+    assert torch.equal(O.rotate_tokens(r, 4, 6), h)
+    # element (row i, col j) moves to position j*rows + i
+    assert torch.equal(r[:, 2 * 6 + 3], h[:, 3 * 4 + 2])
+
+
+def test_pool_index_matches_reshape_mean():
+    L, outer, pool, inner = 24, 3, 4, 2
+    idx = O.pool_index(L, outer, pool, inner)
+    x = torch.randn(1, 1, L)
+    ref = O.pool_oracle(x, outer, pool, inner)
+    acc = torch.zeros(outer * inner).index_add_(0, idx, x[0, 0]) / pool
+    assert torch.allclose(acc, ref[0, 0], atol=1e-6)
+    assert torch.equal(O.broadcast_oracle(ref, outer, pool, inner)[0, 0], ref[0, 0][idx])
