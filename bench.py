@@ -1,0 +1,411 @@
+#!/usr/bin/env python
+"""bench.py -- FastVim images/s on B200 (BASELINE.json metric), with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # our arm (one rank per GPU)
+    python bench.py --impl reference [--gpus N] --steps K --warmup W   # the reference's CPU path
+
+A "step" is one forward pass of the hot path's model over one batch of synthetic images.
+Workload at every N: BASELINE.json configs[1] -- FastVim-T (patch16, d=192, 24 blocks) inference,
+224x224, bf16 autocast, batch 256 PER GPU (weak scaling: images are independent, no data-path
+collective).  Other workloads (--workload fastvim_b_224 / fastvim_t_2048 ...) exist
+for profiling; the driver's line is the default one.
+
+Keys (see DESIGN.md "Measurement"):
+  value        images/s, whole job, inputs resident in HBM, CUDA-graph replay of the forward,
+               CUDA events on the launching stream, max over ranks.
+  e2e          the same metric through the public module API with HOST (pinned) images: every
+               step copies its images host->device and its logits device->host inside the timed
+               region (double-buffered on a copy stream).
+  roofline     dominant kernel of ours: algorithmic bytes / CUDA-event duration measured live in
+               an instrumented pass of the same step, against MEASURED_PEAKS.json.
+  cpu_baseline the oracle port of the reference's selective_scan_ref / mamba_inner_ref CPU path
+               (oracle/fastvim_oracle.py) timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (factory, embed_dim, img, per-GPU batch, channels, classes)
+    "fastvim_t_224": dict(embed_dim=192, img=224, batch=256, desc="FastVim-T patch16 d192 24 blocks, 224x224 inference"),
+    "fastvim_s_224": dict(embed_dim=384, img=224, batch=256, desc="FastVim-S patch16 d384 24 blocks, 224x224 inference"),
+    "fastvim_b_224": dict(embed_dim=768, img=224, batch=128, desc="FastVim-B patch16 d768 24 blocks, 224x224 inference"),
+    "fastvim_t_2048": dict(embed_dim=192, img=2048, batch=1, desc="FastVim-T patch16 d192 24 blocks, 2048x2048 inference"),
+}
+
+
+# ----------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0=None, t1=None):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, ln in self.lines:
+            if t0 is not None and not (t0 <= ts <= t1 + 0.15):
+                continue
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- algorithmic bytes
+def algorithmic_bytes(name: str, B: int, L: int, Lp: int, D: int, d_model: int, R: int, N: int, s: int) -> int:
+    """Bytes one launch of kernel `name` must move (DESIGN.md "Kernels")."""
+    if name == "fv_conv_pool_fwd":      # read x, write pooled u for both directions
+        return B * L * D * s + 2 * B * Lp * D * s
+    if name == "fv_scan_fwd":           # read u, x_dbl (both directions), write fp32 direction sum
+        return 2 * B * Lp * D * s + 2 * B * Lp * (R + 2 * N) * s + B * Lp * D * 4
+    if name == "fv_gate_fwd":           # read x, z, s; write gated y
+        return 3 * B * L * D * s + B * Lp * D * 4
+    if name == "fv_add_norm_fwd":       # read x (+ fp32 residual), write y + fp32 residual
+        return B * L * d_model * (s + 4) * 2
+    if name == "fv_block_fwd":          # fused conv+pool+x_proj+scan+gate: x, z read twice is NOT algorithmic
+        return 3 * B * L * D * s
+    return 0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic(kernel: str):
+    """dram bytes per launch from the committed ncu --set full capture (profiles/traffic.json)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(kernel)
+    return None
+
+
+# ----------------------------------------------------------------------------- CPU (reference) arm
+def cpu_reference_throughput(workload: str, budget_s: float, steps: int, warmup: int, threads: int):
+    """images/s of the oracle port of the reference's CPU path (selective_scan_ref / mamba_inner_ref
+    semantics, fp32) on `threads` host threads, on a bounded sample of the workload."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fastvim_oracle as O
+    from fastvim_b200.vision import VisionMamba
+
+    w = WORKLOADS[workload]
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    m = VisionMamba(img_size=w["img"], embed_dim=w["embed_dim"], depth=24, rms_norm=True, residual_in_fp32=True,
+                    fused_add_norm=True, final_pool_type="mean", drop_path_rate=0.0).eval()
+    sd = {k: v.detach() for k, v in m.state_dict().items()}
+    # size the per-step sample so that (steps + warmup) steps fit the budget
+    probe_b = 1 if w["img"] > 512 else 4
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        x = torch.randn(probe_b, 3, w["img"], w["img"], generator=g)
+        O.fastvim_oracle(x, sd, depth=24)
+        t0 = time.perf_counter()
+        O.fastvim_oracle(x, sd, depth=24)
+        per_img = (time.perf_counter() - t0) / probe_b
+        sample_b = int(max(1, min(w["batch"], budget_s / max(per_img, 1e-6) / (steps + warmup))))
+        x = torch.randn(sample_b, 3, w["img"], w["img"], generator=g)
+        for _ in range(warmup):
+            O.fastvim_oracle(x, sd, depth=24)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.fastvim_oracle(x, sd, depth=24)
+        dt = time.perf_counter() - t0
+    return sample_b * steps / dt, dt / steps * 1e3, sample_b
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    val, ms, sample_b = cpu_reference_throughput(a.workload, a.cpu_budget, a.steps, a.warmup, cores)
+    w = WORKLOADS[a.workload]
+    sample = (f"{w['desc']}, fp32, oracle port of selective_scan_ref/mamba_inner_ref on {cores} host threads; "
+              f"each step = a batch of {sample_b} images (bounded sample of the {w['batch']}-image batch)")
+    line = {"impl": "reference", "metric": "FastVim inference throughput", "value": round(val, 3), "unit": "images/s",
+            "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": round(ms, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": a.workload, "desc": w["desc"], "batch_per_step": sample_b},
+            "cpu_baseline": {"value": round(val, 3), "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": round(val, 3), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    from fastvim_b200 import _lib
+    from fastvim_b200.vision import VisionMamba
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback for the product path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_gpus = world
+    w = WORKLOADS[a.workload]
+    Bt = a.batch or w["batch"]
+    img, E = w["img"], w["embed_dim"]
+
+    torch.manual_seed(0)
+    model = VisionMamba(img_size=img, embed_dim=E, depth=24, rms_norm=True, residual_in_fp32=True, fused_add_norm=True,
+                        final_pool_type="mean", drop_path_rate=0.0).eval().to(dev)
+    g = torch.Generator(device="cpu").manual_seed(100 + rank)
+    host_imgs = [torch.randn(Bt, 3, img, img, generator=g).pin_memory() for _ in range(2)]
+    host_out = [torch.empty(Bt, 1000).pin_memory() for _ in range(2)]
+
+    def fwd(x):
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            return model(x)
+
+    # ---- static buffers + CUDA graphs (two, for the double-buffered e2e loop)
+    static_in = [host_imgs[i].to(dev) for i in range(2)]
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            fwd(static_in[0])
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graphs, static_out, launches_per_step = [], [], 0
+    use_graph = not a.no_graph
+    if use_graph:
+        pool = None
+        for i in range(2):
+            gr = torch.cuda.CUDAGraph()
+            _lib.reset_launch_count()
+            with torch.cuda.graph(gr, pool=pool):
+                o = fwd(static_in[i])
+            pool = gr.pool()
+            launches_per_step = _lib.launch_count()
+            graphs.append(gr)
+            static_out.append(o)
+    else:
+        _lib.reset_launch_count()
+        fwd(static_in[0])
+        launches_per_step = _lib.launch_count()
+
+    def step(i=0):
+        if use_graph:
+            graphs[i].replay()
+            return static_out[i]
+        return fwd(static_in[i])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident timing -------------------------------------------------------------
+    for _ in range(max(a.warmup, 3)):
+        step(0)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
+    e0.record()
+    for _ in range(a.steps):
+        step(0)
+    e1.record()
+    barrier()
+    tw1 = time.perf_counter()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / a.steps
+    value = n_gpus * Bt * a.steps / (ms_total * 1e-3)
+
+    # ---- e2e: pinned host images in, logits out, every step, double-buffered ----------------
+    copy_s = torch.cuda.Stream(dev)
+    comp_s = torch.cuda.current_stream()
+    h2d_bytes = host_imgs[0].numel() * host_imgs[0].element_size()
+    d2h_bytes = host_out[0].numel() * host_out[0].element_size()
+
+    def e2e_loop(n):
+        ev_copy = [None, None]
+        ev_done = [None, None]
+        for i in range(n):
+            b = i & 1
+            with torch.cuda.stream(copy_s):
+                if ev_done[b] is not None:
+                    copy_s.wait_event(ev_done[b])      # buffer b is free once step i-2 finished
+                static_in[b].copy_(host_imgs[b], non_blocking=True)
+                ev_copy[b] = torch.cuda.Event()
+                ev_copy[b].record(copy_s)
+            comp_s.wait_event(ev_copy[b])
+            out = step(b)
+            host_out[b].copy_(out.float(), non_blocking=True)
+            ev_done[b] = torch.cuda.Event()
+            ev_done[b].record(comp_s)
+
+    e2e_loop(max(a.warmup, 3))
+    barrier()
+    t0 = time.perf_counter()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    e2e_loop(a.steps)
+    torch.cuda.synchronize()          # includes the last device->host read
+    t_e2e = time.perf_counter() - t0
+    barrier()
+    t_e2e = max_over_ranks(t_e2e)
+    e2e_value = n_gpus * Bt * a.steps / t_e2e
+    clocks = sampler.stop(tw0, tw1) if rank == 0 else None
+
+    # ---- roofline: instrumented eager pass, CUDA events around every C-ABI launch ------------
+    roof = None
+    kern_table = {}
+    if rank == 0:
+        for _ in range(2):
+            fwd(static_in[0])
+        recs = []
+        _lib.set_profile(recs)
+        for _ in range(3):
+            fwd(static_in[0])
+        _lib.set_profile(None)
+        torch.cuda.synchronize()
+        agg = {}
+        for name, ev0, ev1 in recs:
+            d = agg.setdefault(name, [0.0, 0])
+            d[0] += ev0.elapsed_time(ev1)
+            d[1] += 1
+        m0 = model.layers[0].mixer
+        L = (img // 16) ** 2
+        Lp = img // 16
+        peaks, peak_src = load_peaks()
+        for name, (tot, cnt) in agg.items():
+            ab = algorithmic_bytes(name, Bt, L, Lp, m0.d_inner, E, m0.dt_rank, m0.d_state, 2)
+            avg_ms = tot / cnt
+            kern_table[name] = {"launches_per_step": cnt // 3, "avg_us": round(avg_ms * 1e3, 2),
+                                "ms_per_step": round(tot / 3, 4), "alg_bytes": ab,
+                                "gbs": round(ab / (avg_ms * 1e-3) / 1e9, 1) if avg_ms > 0 else None}
+        if agg:
+            top = max(agg, key=lambda k: agg[k][0])
+            k = kern_table[top]
+            roof = {"kernel": top, "bound": "hbm", "achieved": k["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": round(k["gbs"] / peaks["hbm_gbs"], 4), "traffic": load_traffic(top),
+                    "alg_bytes_per_launch": k["alg_bytes"], "avg_us": k["avg_us"], "peak_source": peak_src,
+                    "share_of_step": round(k["ms_per_step"] / ms_step, 4)}
+
+    # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        cores = os.cpu_count() or 1
+        v, ms, sb = cpu_reference_throughput(a.workload, a.cpu_budget, 2, 1, cores)
+        cpu = {"value": round(v, 3), "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": f"oracle port of the reference CPU path (selective_scan_ref/mamba_inner_ref semantics), fp32, "
+                         f"{cores} threads, 2 timed steps of {sb} images each after 1 warm-up"}
+
+    if rank == 0:
+        line = {"metric": "FastVim inference throughput", "value": round(value, 1), "unit": "images/s", "n_gpus": n_gpus,
+                "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": a.workload, "desc": w["desc"], "batch_per_gpu": Bt, "global_batch": Bt * n_gpus,
+                           "sharding": f"batch-sharded x{n_gpus}, no data-path collective",
+                           "launch": "cuda_graph" if use_graph else "eager",
+                           "l2": "per-step working set (24 blocks x ~%d MB of activations) exceeds the 126 MB L2; no flush"
+                                 % (3 * Bt * L * m0.d_inner * 2 // 2**20)},
+                "e2e": {"value": round(e2e_value, 1), "unit": "images/s", "h2d_bytes_per_step": h2d_bytes,
+                        "d2h_bytes_per_step": d2h_bytes, "ms_per_step": round(t_e2e / a.steps * 1e3, 4),
+                        "note": "pinned fp32 images -> H2D -> forward -> fp32 logits D2H, double-buffered copy stream"},
+                "gpu_launches": launches_per_step * a.steps, "gpu_launches_per_step": launches_per_step,
+                "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "kernels": kern_table}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="fastvim_t_224", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the CPU legs")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        a.cpu_budget = max(a.cpu_budget, 90.0) if a.cpu_budget == 20.0 else a.cpu_budget
+        return run_reference_arm(a)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.gpus > 1 and world == 1:
+        # convenience: relaunch under torchrun (the driver launches torchrun itself)
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
+        return subprocess.call(cmd)
+    return run_ours(a)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -66,9 +66,28 @@ def lib():
     return l
 
 
+_profile = None
+
+
+def set_profile(records) -> None:
+    """bench.py's per-kernel timer: when `records` is a list, every C-ABI launch is bracketed by
+    CUDA events on the current stream and ``(name, start, stop)`` is appended to it."""
+    global _profile
+    _profile = records
+
+
 def call(name: str, *args) -> None:
     l = lib()
-    rc = getattr(l, name)(*args)
+    if _profile is not None:
+        import torch
+
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(l, name)(*args)
+        e1.record()
+        _profile.append((name, e0, e1))
+    else:
+        rc = getattr(l, name)(*args)
     if rc != 0:
         raise FastVimLibraryError(f"{name} failed (rc={rc}): {l.fv_last_error().decode()}")
 
