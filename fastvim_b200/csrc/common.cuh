@@ -103,6 +103,28 @@ __device__ __forceinline__ float4 silu4(float4 v) {
     }
     return v;
 }
+// SiLU of a conv output computed with taps pre-scaled by 0.5 (FAST) / 1 (exact): for FAST the
+// input is h = x/2 and silu(x) = h + h*tanh(h).
+__device__ __forceinline__ void silu_pair_from_half(float& ha, float& hb) {
+    __half2 h = __floats2half2_rn(ha, hb);
+    uint32_t hi = *reinterpret_cast<uint32_t*>(&h), ho;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(ho) : "r"(hi));
+    float2 t = __half22float2(*reinterpret_cast<__half2*>(&ho));
+    ha = fmaf(ha, t.x, ha);
+    hb = fmaf(hb, t.y, hb);
+}
+template <bool FAST>
+__device__ __forceinline__ float4 silu4_pre(float4 v) {
+    if (FAST) {
+        silu_pair_from_half(v.x, v.y);
+        silu_pair_from_half(v.z, v.w);
+    } else {
+        v.x = silu_exact(v.x); v.y = silu_exact(v.y); v.z = silu_exact(v.z); v.w = silu_exact(v.w);
+    }
+    return v;
+}
+template <bool FAST>
+__device__ __forceinline__ constexpr float tap_prescale() { return FAST ? 0.5f : 1.f; }
 // d silu(x)/dx = s + x*s*(1-s), s = sigmoid(x)
 __device__ __forceinline__ float sigmoidf_(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
 __device__ __forceinline__ float dsilu(float x) {
@@ -139,7 +161,8 @@ struct Taps {
     float4 w[4];
     float4 b;
 };
-__device__ __forceinline__ Taps load_taps(const float* cw, const float* cb, int D, int dir, int d0) {
+// pre: multiplies taps and bias (0.5 on the fast-SiLU path: the conv then yields h = x/2 directly)
+__device__ __forceinline__ Taps load_taps(const float* cw, const float* cb, int D, int dir, int d0, float pre = 1.f) {
     Taps t;
     const float* p = cw + ((int64_t)dir * D + d0) * 4;
     float4 c0 = ld4(p), c1 = ld4(p + 4), c2 = ld4(p + 8), c3 = ld4(p + 12);
@@ -148,7 +171,137 @@ __device__ __forceinline__ Taps load_taps(const float* cw, const float* cb, int 
     t.w[2] = make_float4(c0.z, c1.z, c2.z, c3.z);
     t.w[3] = make_float4(c0.w, c1.w, c2.w, c3.w);
     t.b = cb ? ld4(cb + (int64_t)dir * D + d0) : zero4();
+    if (pre != 1.f) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t.w[k] = scale4(t.w[k], pre);
+        t.b = scale4(t.b, pre);
+    }
     return t;
+}
+
+
+// ---- async global -> shared staging (cp.async; LDGSTS in SASS) ------------------------
+// The full-resolution kernels stage whole token rows (all channels handled by the CTA) into
+// shared memory with 16-byte cp.async: the loads are bulk, coalesced and cost no registers, so
+// the memory-level parallelism does not depend on occupancy.  Out-of-range rows are zero-filled
+// (src-size 0), which is exactly the conv's zero padding.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gptr, bool valid) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gptr), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem, const void* gptr, bool valid) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(sa), "l"(gptr), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Row table: rowtab[i] = memory token row of sequence position t_lo + i, or -1 outside [0, L).
+// Filled once per tile by the first threads (the only integer divisions of the kernel), then the
+// staging, compute and store loops index it instead of re-deriving rows.
+__device__ __forceinline__ void fill_rowtab(const Geom& g, int t_lo, int nrows, int* rowtab) {
+    for (int i = threadIdx.x; i < nrows; i += blockDim.x) {
+        const int t = t_lo + i;
+        rowtab[i] = (t >= 0 && t < g.L) ? (int)seq_to_row(g, t) : -1;
+    }
+}
+// Stages rows rowtab[0..nrows) of one image (g.D channels, token-major) into dst[nrows][g.D];
+// rows marked -1 are zero-filled.  vec16: rows, strides and base are 16-byte aligned (host-checked).
+// Requires blockDim.x >= g.D / 4 (true for every caller: one thread per 4 channels).
+template <typename T>
+__device__ __forceinline__ void stage_rows(const Geom& g, const T* __restrict__ xb, int64_t ldx,
+                                           const int* rowtab, int nrows, T* dst, bool vec16) {
+    if (vec16) {
+        constexpr int E = 16 / (int)sizeof(T);
+        const int vpr = g.D / E;
+        const int rsub = threadIdx.x / vpr, c = threadIdx.x - rsub * vpr, rpp = blockDim.x / vpr;
+        if (rsub < rpp)
+            for (int r = rsub; r < nrows; r += rpp) {
+                const int row = rowtab[r];
+                cp_async16(dst + (size_t)r * g.D + c * E, row >= 0 ? xb + (int64_t)row * ldx + c * E : xb, row >= 0);
+            }
+    } else {
+        constexpr int E = 8 / (int)sizeof(T);
+        const int vpr = g.D / E;
+        for (int v = threadIdx.x; v < vpr; v += blockDim.x)
+            for (int r = 0; r < nrows; ++r) {
+                const int row = rowtab[r];
+                cp_async8(dst + (size_t)r * g.D + v * E, row >= 0 ? xb + (int64_t)row * ldx + v * E : xb, row >= 0);
+            }
+    }
+}
+template <typename T>
+static inline bool rows_vec16(int D, const void* p, int64_t ld, int64_t bs) {
+    constexpr int E = 16 / (int)sizeof(T);
+    return D % E == 0 && ld % E == 0 && bs % E == 0 && ((uintptr_t)p % 16) == 0;
+}
+
+// ---- TMA bulk copies (cp.async.bulk; UBLKCP in SASS) completing on an mbarrier ----------
+// Whole token rows (all channels of a CTA, contiguous in memory) are moved global -> shared by
+// the TMA engine: one lane issues one row, nobody spends issue slots on address arithmetic, and
+// the consumer warps only wait on the mbarrier's phase parity.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// Both conv directions at one token from a 7-row window w[k] = x[t-3+k]:
+//   f: silu(b_f + sum_k w_f[k] x[t-3+k])      b: silu(b_b + sum_k w_b[k] x[t+3-k])
+template <bool FAST>
+__device__ __forceinline__ void conv_both(const float4 (&w)[7], const Taps& tf, const Taps& tb, float4& xf,
+                                          float4& xb_) {
+    float4 af = tf.b, ab = tb.b;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        af = fma4(tf.w[k], w[k], af);
+        ab = fma4(tb.w[k], w[6 - k], ab);
+    }
+    xf = silu4<FAST>(af);
+    xb_ = silu4<FAST>(ab);
+}
+// Same with taps loaded through load_taps(..., tap_prescale<FAST>()), window given as 7 values.
+template <bool FAST>
+__device__ __forceinline__ void conv_both_pre(const float4& r0, const float4& r1, const float4& r2, const float4& r3,
+                                              const float4& r4, const float4& r5, const float4& r6, const Taps& tf,
+                                              const Taps& tb, float4& xf, float4& xb_) {
+    float4 af = fma4(tf.w[0], r0, tf.b), ab = fma4(tb.w[0], r6, tb.b);
+    af = fma4(tf.w[1], r1, af); ab = fma4(tb.w[1], r5, ab);
+    af = fma4(tf.w[2], r2, af); ab = fma4(tb.w[2], r4, ab);
+    af = fma4(tf.w[3], r3, af); ab = fma4(tb.w[3], r3, ab);
+    xf = silu4_pre<FAST>(af);
+    xb_ = silu4_pre<FAST>(ab);
+}
+// pooled position of sequence position t
+__device__ __forceinline__ int seq_to_pooled(const Geom& g, int t) {
+    if (g.inner == 1) return t / g.pool;
+    const int q = t / g.inner, i = t - q * g.inner;
+    return (q / g.pool) * g.inner + i;
 }
 
 }  // namespace fv

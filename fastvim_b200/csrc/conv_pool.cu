@@ -24,19 +24,6 @@ __device__ __forceinline__ float4 load_row4(const Geom& g, const T* xb, int64_t 
     return ld4(xb + seq_to_row(g, t) * ldx + d0);
 }
 
-template <bool FAST>
-__device__ __forceinline__ void conv_both(const float4 (&w)[7], const Taps& tf, const Taps& tb,
-                                          float4& xf, float4& xb_) {
-    float4 af = tf.b, ab = tb.b;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        af = fma4(tf.w[k], w[k], af);      // x[c-3+k]
-        ab = fma4(tb.w[k], w[6 - k], ab);  // x[c+3-k]
-    }
-    xf = silu4<FAST>(af);
-    xb_ = silu4<FAST>(ab);
-}
-
 template <typename T, bool MAXPOOL, bool INNER1>
 __global__ void __launch_bounds__(256)
 conv_pool_fwd_kernel(Geom g, const T* __restrict__ x, int64_t ldx, int64_t xbs,
@@ -102,9 +89,110 @@ conv_pool_fwd_kernel(Geom g, const T* __restrict__ x, int64_t ldx, int64_t xbs,
     st4(uo + plane, accb);
 }
 
+// v2 for the plain (outer, pool, 1) geometry: CTA = one pooled position (b, j), all channels
+// (4 per thread).  The pool+6 token rows are staged with 16-byte cp.async (zero-filled outside
+// the sequence), in double-buffered chunks of TP tokens when the pooled group is long (2048^2:
+// pool = 128), so every global load of a chunk is in flight at once.
+template <typename T, bool MAXPOOL, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+conv_pool_staged_kernel(Geom g, int TP, int nbuf, int vec16, const T* __restrict__ x, int64_t ldx, int64_t xbs,
+                        const float* __restrict__ cw, const float* __restrict__ cb, float scale,
+                        T* __restrict__ u) {
+    constexpr bool FAST = is_fast<T>::value;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* xs = reinterpret_cast<T*>(smem_raw);
+    constexpr int G = 7;
+    const int D = g.D;
+    const int bufsz = (TP + 6) * D;
+    int* rowtab = reinterpret_cast<int*>(xs + nbuf * bufsz);  // [g.pool + 6]
+    const int j = blockIdx.x, b = blockIdx.y;
+    const int d0 = threadIdx.x * 4;
+    const bool live = d0 < g.D;
+    const int dd = live ? d0 : 0;
+    const T* xb = x + (int64_t)b * xbs;
+    const int tbase = j * g.pool;
+    const int nchunk = (g.pool + TP - 1) / TP;
+
+    fill_rowtab(g, tbase - 3, g.pool + 6, rowtab);
+    __syncthreads();
+    stage_rows(g, xb, ldx, rowtab, min(TP, g.pool) + 6, xs, vec16 != 0);
+    cp_async_commit();
+    constexpr float PRE = FAST ? 0.5f : 1.f;
+    const Taps tf = load_taps(cw, cb, g.D, 0, dd, PRE), tb = load_taps(cw, cb, g.D, 1, dd, PRE);
+    float4 accf = MAXPOOL ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : zero4();
+    float4 accb = accf;
+    for (int c = 0; c < nchunk; ++c) {
+        const int p_lo = c * TP, np = min(TP, g.pool - p_lo);
+        if (c + 1 < nchunk) {
+            const int q_lo = p_lo + TP, nq = min(TP, g.pool - q_lo);
+            stage_rows(g, xb, ldx, rowtab + q_lo, nq + 6, xs + ((c + 1) % nbuf) * bufsz, vec16 != 0);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const T* cur = xs + (c % nbuf) * bufsz + dd;
+        // groups of G tokens, fully unrolled: G + 6 smem rows per group, window in registers
+        for (int p0 = 0; p0 < np; p0 += G) {
+            float4 r[G + 6];
+            const T* xp = cur + p0 * D;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) r[k] = ld4(xp + k * D);
+#pragma unroll
+            for (int i = 0; i < G; ++i) {
+                if (p0 + i < np) {
+                    r[i + 6] = ld4(xp + (i + 6) * D);
+                    float4 xf, xr;
+                    conv_both_pre<FAST>(r[i], r[i + 1], r[i + 2], r[i + 3], r[i + 4], r[i + 5], r[i + 6], tf, tb, xf, xr);
+                    accf = MAXPOOL ? max4(accf, xf) : accf + xf;
+                    accb = MAXPOOL ? max4(accb, xr) : accb + xr;
+                }
+            }
+        }
+        __syncthreads();  // all reads of this buffer done before it is refilled two chunks later
+    }
+    if (!live) return;
+    if (!MAXPOOL) {
+        const float m = scale / (float)g.pool;
+        accf = scale4(accf, m);
+        accb = scale4(accb, m);
+    }
+    const int64_t plane = (int64_t)g.B * g.Lp * g.D;
+    T* uo = u + ((int64_t)b * g.Lp + j) * g.D + d0;
+    st4(uo, accf);
+    st4(uo + plane, accb);
+}
+
+template <typename T>
+static int launch_conv_pool_staged(const Geom& g, const T* x, int64_t ldx, int64_t xbs, const float* cw,
+                                   const float* cb, float scale, int pool_mode, T* u, cudaStream_t st) {
+    const int threads = ((g.D / 4) + 31) / 32 * 32;
+    int TP = g.pool < 32 ? g.pool : 32;
+    while (TP > 4 && (size_t)2 * (TP + 6) * g.D * sizeof(T) > 96 * 1024) TP /= 2;
+    const int nchunk = (g.pool + TP - 1) / TP;
+    const int nbuf = nchunk > 1 ? 2 : 1;
+    const size_t smem = (size_t)nbuf * (TP + 6) * g.D * sizeof(T) + (size_t)(g.pool + 6) * 4;
+    FV_REQUIRE(g.Lp <= 2147483647 && g.B <= 65535, "fv_conv_pool_fwd: batch > 65535");
+    dim3 grid(g.Lp, g.B), block(threads);
+    void (*kern)(Geom, int, int, int, const T*, int64_t, int64_t, const float*, const float*, float, T*);
+    const bool mx = pool_mode == FV_POOL_MAX;
+    if (threads <= 128) kern = mx ? conv_pool_staged_kernel<T, true, 128> : conv_pool_staged_kernel<T, false, 128>;
+    else if (threads <= 256) kern = mx ? conv_pool_staged_kernel<T, true, 256> : conv_pool_staged_kernel<T, false, 256>;
+    else if (threads <= 512) kern = mx ? conv_pool_staged_kernel<T, true, 512> : conv_pool_staged_kernel<T, false, 512>;
+    else kern = mx ? conv_pool_staged_kernel<T, true, 1024> : conv_pool_staged_kernel<T, false, 1024>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        FV_REQUIRE(e == cudaSuccess, "fv_conv_pool_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    kern<<<grid, block, smem, st>>>(g, TP, nbuf, (int)rows_vec16<T>(g.D, x, ldx, xbs), x, ldx, xbs, cw, cb, scale, u);
+    return finish_launch("conv_pool_fwd");
+}
+
 template <typename T>
 static int launch_conv_pool(const Geom& g, const T* x, int64_t ldx, int64_t xbs, const float* cw,
                             const float* cb, float scale, int pool_mode, T* u, cudaStream_t st) {
+    if (g.inner == 1 && g.D <= 4096) return launch_conv_pool_staged<T>(g, x, ldx, xbs, cw, cb, scale, pool_mode, u, st);
     const int64_t items = (int64_t)g.B * g.Lp * (g.D / 4);
     const int threads = 256;
     const int64_t blocks = (items + threads - 1) / threads;

@@ -31,6 +31,19 @@ int finish_launch(const char* what) {
     }
     return 0;
 }
+// SM count of the current device (cached per device; persistent kernels size their grids with it).
+int sm_count() {
+    static int cache[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cache[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cache[dev] = n;
+    }
+    return cache[dev];
+}
+
 int check_geom(const fv_geom* g, const char* who) {
     FV_REQUIRE(g != nullptr, "%s: null geometry", who);
     FV_REQUIRE(g->batch > 0 && g->dim > 0 && g->outer > 0 && g->pool > 0 && g->inner > 0,

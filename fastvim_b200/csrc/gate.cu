@@ -7,12 +7,22 @@
 // (>= 10 full-resolution passes incl. a flip and a (B,D,L)->(B,L,D) transpose copy) by ONE
 // kernel that reads x and z once and writes the gated out_proj input once: 3 full-resolution
 // tensors, the compulsory minimum.  The conv outputs xc_f / xc_b needed by the D skip are
-// recomputed from x (7-row sliding register window) rather than stored by K1.
+// recomputed from x rather than stored by K1.
 //
-// Mapping: token-major; a CTA owns ALL d_inner channels (4 per thread) of up to TT tokens of
-// one pooled position j, so s[b, j, :] is loaded once and the LayerNorm reduction over
-// d_inner stays inside the CTA: pre-norm values go to shared memory, per-token (sum, sumsq)
-// partials are warp-shuffled, one barrier, then normalise * gamma + beta, * silu(z), store.
+// Mapping (v4, persistent + pipelined): token-major; a tile is TT <= 8 consecutive SEQUENCE
+// positions of one image with ALL d_inner channels (4 per thread); on plain grids a tile is an
+// equal split of one pooled group (pool = 14 -> 2 x 7) so it reads a single pooled scan row.
+// The grid is persistent (SM count x resident CTAs); each CTA walks tiles blockIdx.x, +gridDim.x...
+// with a 2-stage cp.async pipeline: while tile i is computed, the TT+6 x rows (3 halo rows each
+// side; rows outside the sequence zero-filled = the conv's padding) and TT z rows of tile i+1
+// stream into the other shared-memory buffer as 16-byte LDGSTS, and its pooled scan row is
+// prefetched into registers.  The per-channel parameters (8 taps, biases, D, gamma, beta) are
+// loaded once per CTA.  Token -> memory-row tables (rotated layers, channel layouts) are built
+// by one warp two tiles ahead, so the hot loops contain no integer division.
+// Per tile: phase 1: sliding 7-row register window over the staged rows -> both convs + SiLU ->
+// (s_f + s_b + D_f xc_f + D_b xc_b)/2 -> smem, per-token (sum, sumsq) partials by warp shuffle;
+// one barrier; phase 2: LayerNorm * gamma + beta, * silu(z), 8-byte (bf16) / 16-byte (fp32)
+// coalesced stores.
 // In channel-sharded mode (2048^2 single image, d_inner split over GPUs) the CTA sees only a
 // shard of the channels: it writes the pre-norm value and the shard's per-token partial
 // statistics; fv_norm_gate_apply finishes after the all-reduce of the (B, L, 2) statistics.
@@ -20,131 +30,280 @@
 
 namespace fv {
 
-template <typename T>
-__device__ __forceinline__ float4 gload_row4(const Geom& g, const T* xb, int64_t ldx, int d0, int t, bool live) {
-    if (!live || t < 0 || t >= g.L) return zero4();
-    return ld4(xb + seq_to_row(g, t) * ldx + d0);
+int sm_count();
+
+// per-tile table in shared memory
+template <int TT>
+struct TileTab {
+    long long yoff[TT];  // element offset of each token's row in y (row * ldy), image offset included
+    int rows[TT + 6];    // memory token row of sequence positions t0-3 .. t0+TT+2 (-1: outside)
+    int jt[TT];          // pooled position of each token
+    int b, np, valid, pad;
+};
+
+template <int TT>
+__device__ __forceinline__ void fill_tiletab(const Geom& g, int64_t tile, int64_t ntiles, int tiles_per_img,
+                                             int tiles_per_group, int tile_len, int64_t ldy, int64_t ybs,
+                                             TileTab<TT>* tab) {
+    // executed by warp 0 only
+    const int lane = threadIdx.x;
+    if (tile >= ntiles) {
+        if (lane == 0) tab->valid = 0;
+        return;
+    }
+    const int b = (int)(tile / tiles_per_img), rem = (int)(tile - (int64_t)b * tiles_per_img);
+    int t0, np;
+    if (tiles_per_group > 0) {
+        const int j = rem / tiles_per_group, q = rem - j * tiles_per_group;
+        t0 = j * g.pool + q * tile_len;
+        np = min(tile_len, g.pool - q * tile_len);
+    } else {
+        t0 = rem * TT;
+        np = min(TT, g.L - t0);
+    }
+    if (lane < TT + 6) {
+        const int t = t0 - 3 + lane;
+        const int row = (lane < np + 6 && t >= 0 && t < g.L) ? (int)seq_to_row(g, t) : -1;
+        tab->rows[lane] = row;
+        if (lane >= 3 && lane < TT + 3) tab->yoff[lane - 3] = (int64_t)b * ybs + (int64_t)(row < 0 ? 0 : row) * ldy;
+    }
+    if (lane < TT) tab->jt[lane] = lane < np ? seq_to_pooled(g, t0 + lane) : 0;
+    if (lane == 0) {
+        tab->b = b;
+        tab->np = np;
+        tab->valid = 1;
+    }
 }
 
-template <typename T, bool INNER1, int MAXT>
-__global__ void __launch_bounds__(MAXT)
-gate_fwd_kernel(Geom g, int TT, const T* __restrict__ x, const T* __restrict__ z, int64_t ldxz,
-                int64_t xzbs, const float* __restrict__ s, const float* __restrict__ cw,
-                const float* __restrict__ cb, const float* __restrict__ Dskip,
-                const float* __restrict__ lnw, const float* __restrict__ lnb, float eps,
-                T* __restrict__ y, int64_t ldy, int64_t ybs, float* __restrict__ stats) {
+// Stages one tile with TMA bulk copies (warp 0, all lanes): lanes [0, np+6) own the x rows, lanes
+// [TT+6, TT+6+np) the z rows; rows outside the sequence are zero-filled by their lane.
+template <typename T, int TT>
+__device__ __forceinline__ void bulk_stage_tile(int D, const TileTab<TT>* tab, const T* __restrict__ x,
+                                                const T* __restrict__ z, int64_t ldxz, int64_t xzbs, T* buf,
+                                                uint64_t* bar, bool with_z) {
+    static_assert(2 * TT + 6 <= 32, "one lane per staged row");
+    if (!tab->valid) return;
+    const int lane = threadIdx.x & 31;
+    const int np = tab->np;
+    const uint32_t rowB = (uint32_t)D * sizeof(T);
+    int row = -1;
+    const T* src = nullptr;
+    T* dst = nullptr;
+    bool mine = false;
+    if (lane < np + 6) {
+        mine = true;
+        row = tab->rows[lane];
+        src = x;
+        dst = buf + lane * D;
+    } else if (with_z && lane >= TT + 6 && lane < TT + 6 + np) {
+        mine = true;
+        row = tab->rows[lane - (TT + 6) + 3];
+        src = z;
+        dst = buf + lane * D;  // z rows follow the TT+6 x rows
+    }
+    const unsigned copies = __ballot_sync(0xffffffffu, mine && row >= 0);
+    if (lane == 0) mbar_arrive_expect_tx(bar, (uint32_t)__popc(copies) * rowB);
+    __syncwarp();
+    if (mine) {
+        if (row >= 0) {
+            bulk_g2s(dst, src + (int64_t)tab->b * xzbs + (int64_t)row * ldxz, rowB, bar);
+        } else {
+            float4* d4 = reinterpret_cast<float4*>(dst);
+            for (int i = 0; i < (int)(rowB / 16); ++i) d4[i] = zero4();
+        }
+    }
+}
+
+// MODE: 0 = LayerNorm + gate, 1 = gate only (use_norm_after_ssm=False), 2 = channel-sharded (pre-norm + stats)
+template <typename T, int TT, int MODE, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+gate_fwd_kernel(Geom g, int64_t ntiles, int tiles_per_img, int tiles_per_group, int tile_len, int vec16, int nbuf,
+                const T* __restrict__ x, const T* __restrict__ z, int64_t ldxz, int64_t xzbs,
+                const float* __restrict__ s, const float* __restrict__ cw, const float* __restrict__ cb,
+                const float* __restrict__ Dskip, const float* __restrict__ lnw, const float* __restrict__ lnb,
+                float eps, T* __restrict__ y, int64_t ldy, int64_t ybs, float* __restrict__ stats) {
     constexpr bool FAST = is_fast<T>::value;
-    extern __shared__ __align__(16) float smem[];
-    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* vbuf = smem;                          // [TT][D]
-    float2* part = reinterpret_cast<float2*>(smem + (size_t)TT * g.D);  // [TT][nwarps]
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nthreads = blockDim.x, nwarps = nthreads >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int D = g.D;
+    // smem: vbuf[TT][D] fp32 | psum[TT][nthreads] float2 | stat[TT] float2 | nbuf x { xs[TT+6][D] T, zs[TT][D] T } |
+    //       3 x TileTab | 2 mbarriers
+    float* vbuf = reinterpret_cast<float*>(smem_raw);
+    float2* psum = reinterpret_cast<float2*>(vbuf + TT * D);
+    float2* stat = psum + TT * nthreads;
+    T* stage0 = reinterpret_cast<T*>(stat + (TT + 1) / 2 * 2);
+    const int stage_elems = (2 * TT + 6) * D;
+    TileTab<TT>* tabs = reinterpret_cast<TileTab<TT>*>(stage0 + nbuf * stage_elems);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tabs + 3);
 
-    const int j = blockIdx.y, b = blockIdx.z;
-    const int p_lo = blockIdx.x * TT;
-    const int np = min(TT, g.pool - p_lo);
     const int d0 = threadIdx.x * 4;
-    const bool live = d0 < g.D;
+    const bool live = d0 < D;
     const int dd = live ? d0 : 0;
-    const T* xb = x + (int64_t)b * xzbs;
-    const T* zb = z + (int64_t)b * xzbs;
-    T* yb = y + (int64_t)b * ybs;
-    const bool has_norm = lnw != nullptr;
-    const bool sharded = stats != nullptr;
+    const int64_t splane = (int64_t)g.B * g.Lp * D;
+    const bool use_tma = vec16 != 0;
 
-    const Taps tf = load_taps(cw, cb, g.D, 0, dd), tb = load_taps(cw, cb, g.D, 1, dd);
-    const float4 sv = ld4(s + ((int64_t)b * g.Lp + j) * g.D + dd);
-    const float4 Df = ld4(Dskip + dd), Db = ld4(Dskip + g.D + dd);
-
-    float4 w[7];
-    constexpr int PF = 4;
-    float4 ring[PF];
-    const int t0 = INNER1 ? j * g.pool + p_lo : 0;
-    if (INNER1) {
-#pragma unroll
-        for (int i = 0; i < 6; ++i) w[i + 1] = gload_row4(g, xb, ldxz, dd, t0 - 3 + i, live);
-#pragma unroll
-        for (int i = 0; i < PF; ++i) ring[i] = gload_row4(g, xb, ldxz, dd, t0 + 3 + i, live);
-    }
-    for (int p0 = 0; p0 < np; p0 += PF) {
-#pragma unroll
-        for (int i = 0; i < PF; ++i) {
-            const int p = p0 + i;
-            if (p < np) {
-                int t;
-                if (INNER1) {
-                    t = t0 + p;
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) w[k] = w[k + 1];
-                    w[6] = ring[i];
-                    ring[i] = (p + PF < np) ? gload_row4(g, xb, ldxz, dd, t0 + 3 + p + PF, live) : zero4();
-                } else {
-                    t = pooled_to_seq(g, j, p_lo + p);
-#pragma unroll
-                    for (int k = 0; k < 7; ++k) w[k] = gload_row4(g, xb, ldxz, dd, t - 3 + k, live);
-                }
-                float4 af = tf.b, ab = tb.b;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    af = fma4(tf.w[k], w[k], af);
-                    ab = fma4(tb.w[k], w[6 - k], ab);
-                }
-                af = silu4<FAST>(af);
-                ab = silu4<FAST>(ab);
-                float4 v = scale4(fma4(Db, ab, fma4(Df, af, sv)), 0.5f);
-                if (!live) v = zero4();
-                if (has_norm || sharded) {
-                    if (live) st4(vbuf + (size_t)p * g.D + d0, v);
-                    float sum = (v.x + v.y) + (v.z + v.w);
-                    float sq = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w)));
-                    sum = warp_sum(sum);
-                    sq = warp_sum(sq);
-                    if (lane == 0) part[p * nwarps + warp] = make_float2(sum, sq);
-                } else if (live) {
-                    const int64_t row = seq_to_row(g, t);
-                    float4 zz = silu4<FAST>(ld4(zb + row * ldxz + d0));
-                    st4(yb + row * ldy + d0, make_float4(v.x * zz.x, v.y * zz.y, v.z * zz.z, v.w * zz.w));
-                }
-            }
-        }
-    }
-    if (!(has_norm || sharded)) return;
-    __syncthreads();
+    // ---- per-CTA constants
+    constexpr float PRE = FAST ? 0.5f : 1.f;
+    const Taps tf = load_taps(cw, cb, D, 0, dd, PRE), tb = load_taps(cw, cb, D, 1, dd, PRE);
+    // (s_f + s_b + D_f xc_f + D_b xc_b) / 2: the 1/2 is folded into D and s
+    const float4 Df = scale4(ld4(Dskip + dd), 0.5f), Db = scale4(ld4(Dskip + D + dd), 0.5f);
     float4 gam = make_float4(1.f, 1.f, 1.f, 1.f), bet = zero4();
-    if (has_norm && live) {
-        gam = ld4(lnw + d0);
-        if (lnb) bet = ld4(lnb + d0);
+    if (MODE == 0) {
+        gam = ld4(lnw + dd);
+        if (lnb) bet = ld4(lnb + dd);
     }
-    const float invD = 1.f / (float)g.D;
-    for (int p = 0; p < np; ++p) {
-        const int t = INNER1 ? t0 + p : pooled_to_seq(g, j, p_lo + p);
-        const int64_t row = seq_to_row(g, t);
-        float sum = 0.f, sq = 0.f;
-        for (int wq = 0; wq < nwarps; ++wq) {
-            float2 q = part[p * nwarps + wq];
-            sum += q.x;
-            sq += q.y;
-        }
-        if (sharded) {
-            if (threadIdx.x == 0) {
-                float* so = stats + ((int64_t)b * g.L + row) * 2;
-                so[0] = sum;
-                so[1] = sq;
+    const float invD = 1.f / (float)D;
+
+    auto issue_stage = [&](const TileTab<TT>* tab, int slot) {
+        T* buf = stage0 + slot * stage_elems;
+        if (use_tma) {
+            if (warp == 0) bulk_stage_tile<T, TT>(D, tab, x, z, ldxz, xzbs, buf, &bars[slot], MODE != 2);
+        } else {
+            if (tab->valid) {
+                const int np = tab->np;
+                stage_rows(g, x + (int64_t)tab->b * xzbs, ldxz, tab->rows, np + 6, buf, false);
+                if (MODE != 2)
+                    stage_rows(g, z + (int64_t)tab->b * xzbs, ldxz, tab->rows + 3, np, buf + (TT + 6) * D, false);
             }
-            if (live) st4(yb + row * ldy + d0, ld4(vbuf + (size_t)p * g.D + d0));
-            continue;
+            cp_async_commit();
         }
-        if (!live) continue;
-        const float mean = sum * invD;
-        const float rstd = rsqrtf(fmaxf(sq * invD - mean * mean, 0.f) + eps);
-        float4 v = ld4(vbuf + (size_t)p * g.D + d0);
-        float4 zz = silu4<FAST>(ld4(zb + row * ldxz + d0));
-        float4 o;
-        o.x = fmaf((v.x - mean) * rstd, gam.x, bet.x) * zz.x;
-        o.y = fmaf((v.y - mean) * rstd, gam.y, bet.y) * zz.y;
-        o.z = fmaf((v.z - mean) * rstd, gam.z, bet.z) * zz.z;
-        o.w = fmaf((v.w - mean) * rstd, gam.w, bet.w) * zz.w;
-        st4(yb + row * ldy + d0, o);
+    };
+    auto wait_stage = [&](int slot, int use) {
+        if (use_tma) mbar_wait(&bars[slot], (uint32_t)(use & 1));
+        else cp_async_wait<0>();
+    };
+
+    // ---- prologue: barriers, tables of tiles 0 and 1, stage tile 0
+    int64_t tile = blockIdx.x;
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
     }
+    if (warp == 0) {
+        fill_tiletab<TT>(g, tile, ntiles, tiles_per_img, tiles_per_group, tile_len, ldy, ybs, &tabs[0]);
+        fill_tiletab<TT>(g, tile + gridDim.x, ntiles, tiles_per_img, tiles_per_group, tile_len, ldy, ybs, &tabs[1]);
+    }
+    __syncthreads();
+    issue_stage(&tabs[0], 0);
+    float4 svf, svb;
+    {
+        const float* sp = s + ((int64_t)tabs[0].b * g.Lp + tabs[0].jt[0]) * D + dd;
+        svf = ld4(sp);
+        svb = ld4(sp + splane);
+    }
+
+    for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
+        const TileTab<TT>* tab = &tabs[it % 3];
+        const TileTab<TT>* tab1 = &tabs[(it + 1) % 3];
+        const int slot = nbuf == 2 ? (it & 1) : 0;
+        const T* xs = stage0 + slot * stage_elems;
+        const T* zs = xs + (TT + 6) * D;
+        if (nbuf == 1 && it > 0) {  // single buffer (very wide fp32 rows): no prefetch
+            __syncthreads();
+            issue_stage(tab, 0);
+        }
+        wait_stage(slot, nbuf == 2 ? (it >> 1) : it);
+        __syncthreads();  // tile `it` has landed (and its zero-filled rows are visible); tile it-1 is done
+        if (nbuf == 2) issue_stage(tab1, slot ^ 1);  // prefetch tile it+1 into the other buffer
+        float4 sv = scale4(svf + svb, 0.5f);
+        if (tab1->valid) {  // prefetch the pooled scan row of tile it+1
+            const float* sp = s + ((int64_t)tab1->b * g.Lp + tab1->jt[0]) * D + dd;
+            svf = ld4(sp);
+            svb = ld4(sp + splane);
+        }
+        if (warp == 0)
+            fill_tiletab<TT>(g, tile + 2 * (int64_t)gridDim.x, ntiles, tiles_per_img, tiles_per_group, tile_len, ldy,
+                             ybs, &tabs[(it + 2) % 3]);
+        const int np = tab->np;
+        int jprev = tab->jt[0];
+
+        // ---- phase 1: sliding 7-row register window -> pre-norm value v, per-thread LN partials.
+        // Straight-line over all TT slots (slots >= np compute on stale rows and are never stored).
+        float4 r[TT + 6];
+        const T* xp = xs + dd;
+        float* vp = vbuf + dd;
+        float2* pp = psum + threadIdx.x;
+        const T* zp = zs + dd;
+#pragma unroll
+        for (int k = 0; k < 6; ++k, xp += D) r[k] = ld4(xp);
+#pragma unroll
+        for (int p = 0; p < TT; ++p, xp += D, vp += D, pp += nthreads, zp += D) {
+            r[p + 6] = ld4(xp);
+            if (tiles_per_group == 0) {  // channel layouts: the pooled row may change inside a tile
+                const int j = tab->jt[p];
+                if (j != jprev) {
+                    const float* sp = s + ((int64_t)tab->b * g.Lp + j) * D + dd;
+                    sv = scale4(ld4(sp) + ld4(sp + splane), 0.5f);
+                    jprev = j;
+                }
+            }
+            float4 af, ab;
+            conv_both_pre<FAST>(r[p], r[p + 1], r[p + 2], r[p + 3], r[p + 4], r[p + 5], r[p + 6], tf, tb, af, ab);
+            float4 v = fma4(Db, ab, fma4(Df, af, sv));
+            if (MODE == 1) {
+                if (live && p < np) {
+                    float4 zz = silu4<FAST>(ld4(zp));
+                    st4(y + tab->yoff[p] + d0, make_float4(v.x * zz.x, v.y * zz.y, v.z * zz.z, v.w * zz.w));
+                }
+            } else {
+                if (live) st4(vp, v);
+                else v = zero4();
+                *pp = make_float2((v.x + v.y) + (v.z + v.w), fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, v.w * v.w))));
+            }
+        }
+        if (MODE == 1) continue;
+        __syncthreads();
+        // ---- LN statistics: warp w reduces tokens w, w + nwarps, ... (independent shuffle chains)
+        for (int p = warp; p < np; p += nwarps) {
+            float sum = 0.f, sq = 0.f;
+            for (int k = lane; k < nthreads; k += 32) {
+                const float2 q = psum[p * nthreads + k];
+                sum += q.x;
+                sq += q.y;
+            }
+            sum = warp_sum(sum);
+            sq = warp_sum(sq);
+            if (lane == 0) {
+                if (MODE == 2) {
+                    stat[p] = make_float2(sum, sq);
+                } else {
+                    const float mean = sum * invD;
+                    stat[p] = make_float2(mean, rsqrtf(fmaxf(sq * invD - mean * mean, 0.f) + eps));
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: normalise, gate, store
+        vp = vbuf + dd;
+        zp = zs + dd;
+#pragma unroll
+        for (int p = 0; p < TT; ++p, vp += D, zp += D) {
+            if (p < np) {
+                const float2 ms = stat[p];
+                T* yo = y + tab->yoff[p] + d0;
+                if (MODE == 2) {
+                    if (threadIdx.x == 0) {
+                        float* so = stats + ((int64_t)tab->b * g.L + tab->rows[p + 3]) * 2;
+                        so[0] = ms.x;
+                        so[1] = ms.y;
+                    }
+                    if (live) st4(yo, ld4(vp));
+                } else if (live) {
+                    const float4 v = ld4(vp);
+                    const float4 zz = silu4<FAST>(ld4(zp));
+                    const float4 gs = scale4(gam, ms.y);
+                    float4 o;
+                    o.x = fmaf(v.x - ms.x, gs.x, bet.x) * zz.x;
+                    o.y = fmaf(v.y - ms.x, gs.y, bet.y) * zz.y;
+                    o.z = fmaf(v.z - ms.x, gs.z, bet.z) * zz.z;
+                    o.w = fmaf(v.w - ms.x, gs.w, bet.w) * zz.w;
+                    st4(yo, o);
+                }
+            }
+        }
+    }
+    if (!use_tma) cp_async_wait<0>();
 }
 
 // Finishes the channel-sharded path: y holds pre-norm values of this shard, stats the
@@ -182,34 +341,77 @@ norm_gate_apply_kernel(Geom g, int full_dim, T* __restrict__ y, int64_t ldy, int
 
 int check_geom(const fv_geom* g, const char* who);
 
+template <typename T, int TT>
+static size_t gate_smem(int D, int threads, int nbuf) {
+    return (size_t)TT * D * 4 + (size_t)TT * threads * 8 + (size_t)((TT + 1) / 2 * 2) * 8 +
+           (size_t)nbuf * (2 * TT + 6) * D * sizeof(T) + 3 * sizeof(TileTab<TT>) + 16;
+}
+
+template <typename T, int TT, int MODE>
+static int launch_gate_tt(const Geom& g, int tpg, int tile_len, int nbuf, const T* x, const T* z, int64_t ldxz,
+                          int64_t xzbs, const float* s, const float* cw, const float* cb, const float* Dskip,
+                          const float* lnw, const float* lnb, float eps, T* y, int64_t ldy, int64_t ybs, float* stats,
+                          cudaStream_t st) {
+    const int threads = ((g.D / 4) + 31) / 32 * 32;
+    const size_t smem = gate_smem<T, TT>(g.D, threads, nbuf);
+    FV_REQUIRE(smem <= 227 * 1024, "fv_gate_fwd: shared memory %zu too large (dim %d)", smem, g.D);
+    const int tiles_per_img = tpg > 0 ? g.Lp * tpg : ceil_div(g.L, TT);
+    const int64_t ntiles = (int64_t)tiles_per_img * g.B;
+    void (*kern)(Geom, int64_t, int, int, int, int, int, const T*, const T*, int64_t, int64_t, const float*,
+                 const float*, const float*, const float*, const float*, const float*, float, T*, int64_t, int64_t,
+                 float*);
+    if (threads <= 128) kern = gate_fwd_kernel<T, TT, MODE, 128, 4>;
+    else if (threads <= 256) kern = gate_fwd_kernel<T, TT, MODE, 256, 2>;
+    else if (threads <= 512) kern = gate_fwd_kernel<T, TT, MODE, 512, 1>;
+    else kern = gate_fwd_kernel<T, TT, MODE, 1024, 1>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        FV_REQUIRE(e == cudaSuccess, "fv_gate_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    int occ = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
+    FV_REQUIRE(e == cudaSuccess && occ > 0, "fv_gate_fwd: occupancy query failed (%s)", cudaGetErrorString(e));
+    const int64_t resident = (int64_t)sm_count() * occ;  // persistent grid: one wave
+    dim3 grid((unsigned)(ntiles < resident ? ntiles : resident)), block(threads);
+    const int vec16 = rows_vec16<T>(g.D, x, ldxz, xzbs) && ((uintptr_t)z % 16) == 0;
+    kern<<<grid, block, smem, st>>>(g, ntiles, tiles_per_img, tpg, tile_len, vec16, nbuf, x, z, ldxz, xzbs, s, cw, cb,
+                                    Dskip, lnw, lnb, eps, y, ldy, ybs, stats);
+    return finish_launch("gate_fwd");
+}
+
 template <typename T>
 static int launch_gate(const Geom& g, const T* x, const T* z, int64_t ldxz, int64_t xzbs, const float* s,
                        const float* cw, const float* cb, const float* Dskip, const float* lnw,
                        const float* lnb, float eps, T* y, int64_t ldy, int64_t ybs, float* stats,
                        cudaStream_t st) {
+    FV_REQUIRE(g.D <= 4096, "fv_gate_fwd: dim %d > 4096 not supported", g.D);
+    // Tile length <= 8 tokens.  Plain grids: split each pooled group into equal tiles (pool = 14 -> 2 x 7)
+    // so a tile reads one pooled scan row; channel layouts (inner > 1): runs of 8 sequence positions.
     const int threads = ((g.D / 4) + 31) / 32 * 32;
-    FV_REQUIRE(threads <= 1024, "fv_gate_fwd: dim %d > 4096 not supported", g.D);
-    const int nwarps = threads / 32;
-    int TT = g.pool < 16 ? g.pool : 16;
-    auto smem_of = [&](int tt) { return (size_t)tt * g.D * 4 + (size_t)tt * nwarps * 8; };
-    while (TT > 1 && smem_of(TT) > 64 * 1024) TT = (TT + 1) / 2;
-    const size_t smem = smem_of(TT);
-    FV_REQUIRE(smem <= 200 * 1024, "fv_gate_fwd: shared memory %zu too large", smem);
-    FV_REQUIRE(g.Lp <= 65535 && g.B <= 65535, "fv_gate_fwd: Lp or batch > 65535");
-    dim3 grid(ceil_div(g.pool, TT), g.Lp, g.B), block(threads);
-    void (*kern)(Geom, int, const T*, const T*, int64_t, int64_t, const float*, const float*, const float*,
-                 const float*, const float*, const float*, float, T*, int64_t, int64_t, float*);
-    const bool in1 = g.inner == 1;
-    if (threads <= 128) kern = in1 ? gate_fwd_kernel<T, true, 128> : gate_fwd_kernel<T, false, 128>;
-    else if (threads <= 256) kern = in1 ? gate_fwd_kernel<T, true, 256> : gate_fwd_kernel<T, false, 256>;
-    else if (threads <= 512) kern = in1 ? gate_fwd_kernel<T, true, 512> : gate_fwd_kernel<T, false, 512>;
-    else kern = in1 ? gate_fwd_kernel<T, true, 1024> : gate_fwd_kernel<T, false, 1024>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        FV_REQUIRE(e == cudaSuccess, "fv_gate_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    const size_t budget = 200 * 1024;
+    int maxlen = 8, nbuf = 2;
+    if (gate_smem<T, 8>(g.D, threads, 2) > budget) {
+        if (gate_smem<T, 4>(g.D, threads, 2) <= budget) maxlen = 4;
+        else if (gate_smem<T, 8>(g.D, threads, 1) <= budget) nbuf = 1;
+        else maxlen = 4, nbuf = 1;
     }
-    kern<<<grid, block, smem, st>>>(g, TT, x, z, ldxz, xzbs, s, cw, cb, Dskip, lnw, lnb, eps, y, ldy, ybs, stats);
-    return finish_launch("gate_fwd");
+    int tpg = 0, tile_len = maxlen;
+    if (g.inner == 1) {
+        tpg = (g.pool + maxlen - 1) / maxlen;
+        tile_len = (g.pool + tpg - 1) / tpg;
+    }
+#define FV_GATE_ARGS g, tpg, tile_len, nbuf, x, z, ldxz, xzbs, s, cw, cb, Dskip, lnw, lnb, eps, y, ldy, ybs, stats, st
+#define FV_GATE_TT(TT_)                                                      \
+    do {                                                                     \
+        if (stats) return launch_gate_tt<T, TT_, 2>(FV_GATE_ARGS);           \
+        if (lnw) return launch_gate_tt<T, TT_, 0>(FV_GATE_ARGS);             \
+        return launch_gate_tt<T, TT_, 1>(FV_GATE_ARGS);                      \
+    } while (0)
+    if (tile_len <= 4) FV_GATE_TT(4);
+    if (tile_len <= 7) FV_GATE_TT(7);
+    FV_GATE_TT(8);
+#undef FV_GATE_TT
+#undef FV_GATE_ARGS
 }
 
 }  // namespace fv

@@ -104,12 +104,12 @@ def conv_pool_fwd(x: Tensor, geom: Geometry, conv_w: Tensor, conv_b: Optional[Te
 
 def scan_fwd(u: Tensor, xdbl: Tensor, geom: Geometry, dt_rank: int, d_state: int, dt_w: Tensor,
              dt_bias: Tensor, A: Tensor, a_is_log: bool = False) -> Tensor:
-    """K2a.  u (2, B, Lp, D), xdbl (2, B*Lp, >=R+2N) -> s (B, Lp, D) fp32 (sum of both directions)."""
+    """K2a.  u (2, B, Lp, D), xdbl (2, B*Lp, >=R+2N) -> s (2, B, Lp, D) fp32 (one plane per direction)."""
     _check_cuda(u, xdbl)
     _, B, Lp, D = u.shape
     assert u.is_contiguous() and xdbl.dim() == 3 and xdbl.stride(2) == 1 and xdbl.shape[1] == B * Lp
     assert xdbl.stride(0) == xdbl.shape[1] * xdbl.stride(1)
-    s = torch.empty((B, Lp, D), device=u.device, dtype=torch.float32)
+    s = torch.empty((2, B, Lp, D), device=u.device, dtype=torch.float32)
     g = geom.c_struct(B, D)
     _lib.call("fv_scan_fwd", C.byref(g), _dt(u), _p(u), _p(xdbl), xdbl.stride(1), dt_rank, d_state, _p(dt_w),
               _p(dt_bias), _p(A), int(a_is_log), _p(s), _stream(u))

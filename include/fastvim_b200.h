@@ -73,7 +73,7 @@ int fv_conv_pool_fwd(const fv_geom* g, int dtype, const void* x, int64_t ldx, in
  *   u        (2, B, Lp, dim) dtype
  *   xdbl     (2, B*Lp, ld_xdbl) dtype: columns [0,R) dt low-rank, [R,R+N) B, [R+N,R+2N) C  (x_proj output)
  *   dt_w     (2, dim, R) fp32; dt_bias (2, dim) fp32; A (2, dim, N) fp32 (A_log if a_is_log)
- *   s_out    (B, Lp, dim) fp32 = scan_f[j] + scan_b[j]  (both directions, original order)
+ *   s_out    (2, B, Lp, dim) fp32: [0] = scan_f[j], [1] = scan_b[j], both in original row order
  */
 int fv_scan_fwd(const fv_geom* g, int dtype, const void* u, const void* xdbl, int64_t ld_xdbl,
                 int dt_rank, int dstate, const float* dt_w, const float* dt_bias, const float* A,
@@ -83,6 +83,7 @@ int fv_scan_fwd(const fv_geom* g, int dtype, const void* u, const void* xdbl, in
  * Replaces repeat_interleave, += D*x, flip/add//2, LayerNorm(d_inner), *silu(z)
  * (mamba_simple_faster.py:356-358, 412-416, 434-441).  The conv outputs are recomputed
  * from x instead of being stored.
+ *   s         (2, B, Lp, dim) fp32 from fv_scan_fwd (the two planes are added here)
  *   ln_w/ln_b NULL => use_norm_after_ssm=False (:445-453).
  *   y        (B, L, dim) dtype token-major, row stride ldy: the out_proj GEMM input.
  * Channel-sharded mode (dim is a shard of d_inner): pass stats (B, L, 2) fp32; the kernel

@@ -97,8 +97,8 @@ def test_scan_fwd(dtype, Bt, Lp, Dm, R, N):
         want = want + s.transpose(1, 2)
     got = ops.scan_fwd(u.cuda(), xdbl.cuda(), ops.Geometry.grid(Lp, 1), R, N, dt_w.cuda(), dt_b.cuda(),
                        A_log.cuda(), a_is_log=True)
-    assert got.dtype == torch.float32
-    assert_close(got, want, 1e-4, "scan sum")  # inputs identical on both sides; fp32 state on both
+    assert got.dtype == torch.float32 and got.shape == (2, Bt, Lp, Dm)
+    assert_close(got.sum(0), want, 1e-4, "scan sum")  # inputs identical on both sides; fp32 state on both
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])

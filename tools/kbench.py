@@ -1,0 +1,115 @@
+#!/usr/bin/env python
+"""Kernel-level timing of the C-ABI kernels at the BASELINE shapes (CUDA events, rotating buffers
+larger than L2 so every launch is L2-cold).  Prints one JSON line per kernel.
+
+    python tools/kbench.py [--shape t224|b224|t2048|c4] [--iters 20] [--only gate,scan,...]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from fastvim_b200 import ops  # noqa: E402
+
+SHAPES = {  # B, rows, cols, d_model
+    "t224": (256, 14, 14, 192), "s224": (256, 14, 14, 384), "b224": (128, 14, 14, 768),
+    "t2048": (1, 128, 128, 192), "t448": (64, 28, 28, 192),
+}
+
+
+def timeit(fn, nrot, iters):
+    """Average device time per launch: `iters` launches over rotating buffers captured in one CUDA
+    graph (so host launch overhead is not in the number), replayed 3 times, best taken."""
+    for i in range(3):
+        fn(i % nrot)
+    torch.cuda.synchronize()
+    if os.environ.get("KBENCH_EAGER"):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(i % nrot)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e-3
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(iters):
+            fn(i % nrot)
+    g.replay()
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / iters * 1e-3)
+    return best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shape", default="t224")
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--only", default="")
+    ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--rotated", action="store_true")
+    a = ap.parse_args()
+    Bt, rows, cols, dm = SHAPES[a.shape]
+    D, N, R = 2 * dm, 16, (dm + 15) // 16
+    L, Lp = rows * cols, rows
+    dt = torch.bfloat16 if a.dtype == "bf16" else torch.float32
+    s = 2 if dt == torch.bfloat16 else 4
+    dev = "cuda"
+    geom = ops.Geometry.grid(rows, cols, a.rotated)
+    per = Bt * L * 2 * D * s
+    nrot = max(2, int(300e6 // per) + 1)
+    torch.manual_seed(0)
+    xz = [torch.randn(Bt, L, 2 * D, device=dev).to(dt) for _ in range(nrot)]
+    cw, cb = torch.randn(2, D, 4, device=dev) * 0.5, torch.randn(2, D, device=dev) * 0.5
+    u = [torch.randn(2, Bt, Lp, D, device=dev).to(dt) for _ in range(nrot)]
+    xdbl = [(torch.randn(2, Bt * Lp, R + 2 * N, device=dev) * 0.5).to(dt) for _ in range(nrot)]
+    dt_w, dt_b = torch.randn(2, D, R, device=dev) * R ** -0.5, torch.rand(2, D, device=dev) - 4.0
+    A_log = torch.log(torch.arange(1, N + 1, device=dev).float()).repeat(2, D, 1).contiguous()
+    sv = [torch.randn(2, Bt, Lp, D, device=dev) for _ in range(nrot)]
+    Dk, lw, lb = torch.ones(2, D, device=dev), torch.ones(D, device=dev), torch.zeros(D, device=dev)
+    y = [torch.empty(Bt, L, D, device=dev, dtype=dt) for _ in range(nrot)]
+    hs = [torch.randn(Bt, L, dm, device=dev).to(dt) for _ in range(nrot)]
+    res = [torch.randn(Bt, L, dm, device=dev) for _ in range(nrot)]
+    nw = torch.ones(dm, device=dev)
+    only = set(a.only.split(",")) if a.only else None
+
+    def rep(name, t, nbytes):
+        print(json.dumps({"kernel": name, "shape": a.shape, "dtype": a.dtype, "us": round(t * 1e6, 2),
+                          "alg_MB": round(nbytes / 1e6, 2), "GBps": round(nbytes / t / 1e9, 1),
+                          "env": {k: v for k, v in os.environ.items() if k.startswith("FV_")}}), flush=True)
+
+    if not only or "conv_pool" in only:
+        t = timeit(lambda i: ops.conv_pool_fwd(xz[i][..., :D], geom, cw, cb), nrot, a.iters)
+        rep("conv_pool_fwd", t, Bt * L * D * s + 2 * Bt * Lp * D * s)
+    if not only or "scan" in only:
+        t = timeit(lambda i: ops.scan_fwd(u[i], xdbl[i], geom, R, N, dt_w, dt_b, A_log, True), nrot, a.iters)
+        rep("scan_fwd", t, 2 * Bt * Lp * D * s + 2 * Bt * Lp * (R + 2 * N) * s + 2 * Bt * Lp * D * 4)
+    if not only or "gate" in only:
+        t = timeit(lambda i: ops.gate_fwd(xz[i][..., :D], xz[i][..., D:], sv[i], geom, cw, cb, Dk, lw, lb, 1e-5, out=y[i]),
+                   nrot, a.iters)
+        rep("gate_fwd", t, 3 * Bt * L * D * s + 2 * Bt * Lp * D * 4)
+    if not only or "add_norm" in only:
+        t = timeit(lambda i: ops.add_norm_fwd(hs[i], res[i], nw, None, 1e-5, True), nrot, a.iters)
+        rep("add_norm_fwd", t, Bt * L * dm * (s + 4) * 2)
+    if not only or "gemm" in only:
+        w_in = torch.randn(2 * D, dm, device=dev).to(dt)
+        w_out = torch.randn(dm, D, device=dev).to(dt)
+        t = timeit(lambda i: torch.nn.functional.linear(hs[i], w_in), nrot, a.iters)
+        rep("in_proj(cublas)", t, Bt * L * (dm + 2 * D) * s)
+        t = timeit(lambda i: torch.nn.functional.linear(y[i], w_out), nrot, a.iters)
+        rep("out_proj(cublas)", t, Bt * L * (dm + D) * s)
+
+
+if __name__ == "__main__":
+    main()
