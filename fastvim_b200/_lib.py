@@ -34,6 +34,12 @@ SIGNATURES = {
     "fv_norm_gate_apply": [_G, _I, _I, _P, _L, _L, _P, _L, _L, _P, _P, _P, _F, _P],
     "fv_add_norm_fwd": [_I, _L, _I, _P, _L, _P, _P, _P, _F, _I, _P, _L, _P, _P, _P, _P],
     "fv_selective_scan_fwd": [_I, _I, _I, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P],
+    "fv_bwd_tiles_per_group": [_G, _I],
+    "fv_gate_bwd": [_G, _I, _P, _P, _L, _L, _P, _L, _L, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P],
+    "fv_scan_bwd": [_G, _I, _I, _P, _P, _L, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P],
+    "fv_reduce_planes": [_I, _P, _I, _L, _P, _P],
+    "fv_conv_pool_bwd": [_G, _I, _P, _L, _L, _P, _P, _P, _P, _P, _F, _I, _P, _P, _P, _P],
+    "fv_add_norm_bwd": [_I, _L, _I, _P, _L, _P, _P, _P, _F, _I, _P, _L, _P, _P, _P, _P],
 }
 
 _lib = None

@@ -27,53 +27,9 @@
 // shard of the channels: it writes the pre-norm value and the shard's per-token partial
 // statistics; fv_norm_gate_apply finishes after the all-reduce of the (B, L, 2) statistics.
 #include "common.cuh"
+#include "tiles.cuh"
 
 namespace fv {
-
-int sm_count();
-
-// per-tile table in shared memory
-template <int TT>
-struct TileTab {
-    long long yoff[TT];  // element offset of each token's row in y (row * ldy), image offset included
-    int rows[TT + 6];    // memory token row of sequence positions t0-3 .. t0+TT+2 (-1: outside)
-    int jt[TT];          // pooled position of each token
-    int b, np, valid, pad;
-};
-
-template <int TT>
-__device__ __forceinline__ void fill_tiletab(const Geom& g, int64_t tile, int64_t ntiles, int tiles_per_img,
-                                             int tiles_per_group, int tile_len, int64_t ldy, int64_t ybs,
-                                             TileTab<TT>* tab) {
-    // executed by warp 0 only
-    const int lane = threadIdx.x;
-    if (tile >= ntiles) {
-        if (lane == 0) tab->valid = 0;
-        return;
-    }
-    const int b = (int)(tile / tiles_per_img), rem = (int)(tile - (int64_t)b * tiles_per_img);
-    int t0, np;
-    if (tiles_per_group > 0) {
-        const int j = rem / tiles_per_group, q = rem - j * tiles_per_group;
-        t0 = j * g.pool + q * tile_len;
-        np = min(tile_len, g.pool - q * tile_len);
-    } else {
-        t0 = rem * TT;
-        np = min(TT, g.L - t0);
-    }
-    if (lane < TT + 6) {
-        const int t = t0 - 3 + lane;
-        const int row = (lane < np + 6 && t >= 0 && t < g.L) ? (int)seq_to_row(g, t) : -1;
-        tab->rows[lane] = row;
-        if (lane >= 3 && lane < TT + 3) tab->yoff[lane - 3] = (int64_t)b * ybs + (int64_t)(row < 0 ? 0 : row) * ldy;
-    }
-    if (lane < TT) tab->jt[lane] = lane < np ? seq_to_pooled(g, t0 + lane) : 0;
-    if (lane == 0) {
-        tab->b = b;
-        tab->np = np;
-        tab->valid = 1;
-    }
-}
 
 // Stages one tile with TMA bulk copies (warp 0, all lanes): lanes [0, np+6) own the x rows, lanes
 // [TT+6, TT+6+np) the z rows; rows outside the sequence are zero-filled by their lane.

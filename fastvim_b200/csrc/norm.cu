@@ -75,6 +75,123 @@ add_norm_fwd_kernel(int64_t rows, int cols, const T* __restrict__ x, int64_t ldx
     }
 }
 
+// Backward of the prenorm add + norm: r = x + residual (saved, fp32), y = norm(r) * w (+ b).
+//   g = dy * w;  RMS: dr = rstd (g - xhat mean(g xhat)),  xhat = r rstd
+//                LN : dr = rstd (g - mean(g) - xhat mean(g xhat)),  xhat = (r - mean) rstd
+//   dr += d(residual_out);  dx = dr (activation dtype), d(residual_in) = dr (fp32);  dw = sum dy xhat, db = sum dy
+// (reference: _layer_norm_bwd_kernel, mamba_ssm/ops/triton/layernorm.py:210-305).  One warp per row, rows
+// grid-strided so the per-lane dw / db accumulators stay in registers; one atomicAdd per warp at the end.
+// The statistics are recomputed from the saved fp32 row (already in registers) instead of being stored.
+template <typename T, int NV, bool RMS>
+__global__ void __launch_bounds__(NORM_WARPS * 32)
+add_norm_bwd_kernel(int64_t rows, int cols, const T* __restrict__ dy, int64_t lddy,
+                    const float* __restrict__ dres_out, const float* __restrict__ res_out,
+                    const float* __restrict__ w, float eps, T* __restrict__ dx, int64_t lddx,
+                    float* __restrict__ dres_in, float* __restrict__ dw, float* __restrict__ db) {
+    const int lane = threadIdx.x & 31;
+    const int nvec = cols >> 2;
+    const float inv = 1.f / (float)cols;
+    float4 wv[NV], aw[NV], ab[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int v = lane + i * 32;
+        wv[i] = v < nvec ? ld4(w + v * 4) : zero4();
+        aw[i] = zero4();
+        ab[i] = zero4();
+    }
+    const int64_t warp0 = (int64_t)blockIdx.x * NORM_WARPS + (threadIdx.x >> 5);
+    const int64_t nwarp = (int64_t)gridDim.x * NORM_WARPS;
+    for (int64_t row = warp0; row < rows; row += nwarp) {
+        float4 r[NV], gy[NV];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int v = lane + i * 32;
+            r[i] = v < nvec ? ld4(res_out + row * cols + v * 4) : zero4();
+            gy[i] = v < nvec ? ld4(dy + row * lddy + v * 4) : zero4();
+            s1 += (r[i].x + r[i].y) + (r[i].z + r[i].w);
+            s2 += fmaf(r[i].x, r[i].x, fmaf(r[i].y, r[i].y, fmaf(r[i].z, r[i].z, r[i].w * r[i].w)));
+        }
+        s1 = warp_sum(s1);
+        s2 = warp_sum(s2);
+        float mean = 0.f, rstd;
+        if (RMS) {
+            rstd = rsqrtf(s2 * inv + eps);
+        } else {
+            mean = s1 * inv;
+            float sq = 0.f;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int v = lane + i * 32;
+                if (v < nvec) {
+                    const float a = r[i].x - mean, b = r[i].y - mean, c = r[i].z - mean, d = r[i].w - mean;
+                    sq += fmaf(a, a, fmaf(b, b, fmaf(c, c, d * d)));
+                }
+            }
+            rstd = rsqrtf(warp_sum(sq) * inv + eps);
+        }
+        float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            // r <- xhat, gy <- g = dy * w  (dw, db use dy before the scaling)
+            r[i] = make_float4((r[i].x - mean) * rstd, (r[i].y - mean) * rstd, (r[i].z - mean) * rstd, (r[i].w - mean) * rstd);
+            if (lane + i * 32 >= nvec) r[i] = zero4();
+            aw[i] = fma4(gy[i], r[i], aw[i]);
+            ab[i] = ab[i] + gy[i];
+            gy[i] = make_float4(gy[i].x * wv[i].x, gy[i].y * wv[i].y, gy[i].z * wv[i].z, gy[i].w * wv[i].w);
+            c1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
+            c2 += fmaf(gy[i].x, r[i].x, fmaf(gy[i].y, r[i].y, fmaf(gy[i].z, r[i].z, gy[i].w * r[i].w)));
+        }
+        c1 = RMS ? 0.f : warp_sum(c1) * inv;
+        c2 = warp_sum(c2) * inv;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int v = lane + i * 32;
+            if (v < nvec) {
+                float4 o = make_float4(rstd * (gy[i].x - c1 - r[i].x * c2), rstd * (gy[i].y - c1 - r[i].y * c2),
+                                       rstd * (gy[i].z - c1 - r[i].z * c2), rstd * (gy[i].w - c1 - r[i].w * c2));
+                if (dres_out) o = o + ld4(dres_out + row * cols + v * 4);
+                if (dres_in) st4(dres_in + row * cols + v * 4, o);
+                if (dx) st4(dx + row * lddx + v * 4, o);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int v = lane + i * 32;
+        if (v < nvec) {
+            atomicAdd(dw + v * 4 + 0, aw[i].x); atomicAdd(dw + v * 4 + 1, aw[i].y);
+            atomicAdd(dw + v * 4 + 2, aw[i].z); atomicAdd(dw + v * 4 + 3, aw[i].w);
+            if (db) {
+                atomicAdd(db + v * 4 + 0, ab[i].x); atomicAdd(db + v * 4 + 1, ab[i].y);
+                atomicAdd(db + v * 4 + 2, ab[i].z); atomicAdd(db + v * 4 + 3, ab[i].w);
+            }
+        }
+    }
+}
+
+int sm_count();
+
+template <typename T>
+static int launch_add_norm_bwd(int64_t rows, int cols, const T* dy, int64_t lddy, const float* dres_out,
+                               const float* res_out, const float* w, float eps, int is_rms, T* dx, int64_t lddx,
+                               float* dres_in, float* dw, float* db, cudaStream_t st) {
+    int64_t blocks = (rows + NORM_WARPS - 1) / NORM_WARPS;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    dim3 grid((unsigned)blocks), block(NORM_WARPS * 32);
+    const int nvec = cols / 4;
+#define FV_NB_CASE(NV_)                                                                                                 \
+    if (nvec <= NV_ * 32) {                                                                                             \
+        if (is_rms) add_norm_bwd_kernel<T, NV_, true><<<grid, block, 0, st>>>(rows, cols, dy, lddy, dres_out, res_out, w, eps, dx, lddx, dres_in, dw, db); \
+        else add_norm_bwd_kernel<T, NV_, false><<<grid, block, 0, st>>>(rows, cols, dy, lddy, dres_out, res_out, w, eps, dx, lddx, dres_in, dw, db);       \
+        return finish_launch("add_norm_bwd");                                                                           \
+    }
+    FV_NB_CASE(2) FV_NB_CASE(4) FV_NB_CASE(8) FV_NB_CASE(16)
+#undef FV_NB_CASE
+    return fail("fv_add_norm_bwd: cols %d > 2048 not supported", cols);
+}
+
 template <typename T>
 static int launch_add_norm(int64_t rows, int cols, const T* x, int64_t ldx, const float* res_in,
                            const float* w, const float* bias, float eps, int is_rms, T* y, int64_t ldy,
@@ -109,4 +226,20 @@ extern "C" int fv_add_norm_fwd(int dtype, int64_t rows, int cols, const void* x,
     if (dtype == FV_BF16)
         return launch_add_norm<bf16>(rows, cols, (const bf16*)x, ldx, residual_in, weight, bias, eps, is_rms, (bf16*)y, ldy, residual_out, mean_out, rstd_out, st);
     return fail("fv_add_norm_fwd: unsupported dtype %d", dtype);
+}
+
+extern "C" int fv_add_norm_bwd(int dtype, int64_t rows, int cols, const void* dy, int64_t lddy,
+                               const float* dresidual_out, const float* residual_out, const float* weight,
+                               float eps, int is_rms, void* dx, int64_t lddx, float* dresidual_in, float* dweight,
+                               float* dbias, void* stream) {
+    using namespace fv;
+    FV_REQUIRE(dy && residual_out && weight && dweight && (dx || dresidual_in), "fv_add_norm_bwd: null pointer");
+    FV_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0, "fv_add_norm_bwd: bad shape rows %lld cols %d", (long long)rows, cols);
+    FV_REQUIRE(lddy % 4 == 0 && lddx % 4 == 0, "fv_add_norm_bwd: row strides must be multiples of 4");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == FV_F32)
+        return launch_add_norm_bwd<float>(rows, cols, (const float*)dy, lddy, dresidual_out, residual_out, weight, eps, is_rms, (float*)dx, lddx, dresidual_in, dweight, dbias, st);
+    if (dtype == FV_BF16)
+        return launch_add_norm_bwd<bf16>(rows, cols, (const bf16*)dy, lddy, dresidual_out, residual_out, weight, eps, is_rms, (bf16*)dx, lddx, dresidual_in, dweight, dbias, st);
+    return fail("fv_add_norm_bwd: unsupported dtype %d", dtype);
 }

@@ -1,0 +1,341 @@
+// K2a-bwd -- backward of the bidirectional pooled selective scan (dt_proj + softplus fused).
+//
+// What it replaces in the reference (paths relative to /root/reference):
+//   SelectiveScanFn.backward -> selective_scan_cuda.bwd        mamba_ssm/ops/selective_scan_interface.py:59-102
+//     -> selective_scan_bwd_kernel                             csrc/selective_scan/selective_scan_bwd_kernel.cuh:75-489
+//   (math: SURVEY.md Appendix A "Backward of the scan"; bwd_kernel.cuh:244-296, 439-453)
+// The reference walks 2048-element chunks last -> first, recomputes the forward states of a chunk
+// from the checkpoint x[chunk-1] written by the forward kernel, runs a reverse block scan and
+// pushes dB/dC through BlockExchange + fp32 atomics across the `dim` CTAs (:298-315).
+//
+// Here: same thread mapping as the forward (one thread per (image, channel, direction), 128
+// channels per CTA, directions in grid.z).  Pass A (only when Lp > 16) re-runs the forward
+// recurrence and checkpoints the 16 states at every 16-row chunk boundary in shared memory.
+// Pass B walks the chunks in reverse scan order; per chunk and state it recomputes the 16 states
+// of the chunk from the checkpoint (registers), then runs the reverse recurrence
+//   g_i = C_i dy_i + a_{i+1} g_{i+1}
+// accumulating du, d(delta), dA in registers.  dB/dC (sums over channels) are reduced across the
+// 32 lanes with a recursive-halving butterfly (16 shuffles per 16 values instead of 80), summed
+// over the CTA's 4 warps in shared memory and written as one partial plane per 128-channel CTA
+// column -- no atomics, deterministic; fv_reduce_planes adds the planes.  dA_log and d(dt_bias)
+// reduce over the batch with fp32 atomicAdd (as the reference does, :467-477).
+//
+// Outputs: du, dDelta (2, B, Lp, D) in the activation dtype; dBC planes (ncol, 2, B*Lp, 2N) fp32;
+// dA_log (2, D, N), d_dt_bias (2, D) fp32 (accumulated: caller zero-fills).
+// d(dt low-rank) = dDelta . W_dt and dW_dt = dDelta^T . dt are plain GEMMs done by the caller,
+// as in the reference (selective_scan_interface.py:698-737).
+#include "common.cuh"
+
+namespace fv {
+
+__device__ __forceinline__ float ex2b(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+constexpr int SB_THREADS = 128;
+constexpr int SB_LC = 16;
+
+// recursive-halving butterfly: on return lane L holds (in v[0]) the sum over all 32 lanes of
+// element idx(L) = 8*b4 + 4*b3 + 2*b2 + b1 (b_k = bit k of L); lanes L and L^1 hold the same value.
+__device__ __forceinline__ float butterfly16(float (&v)[16], int lane) {
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float send = up ? v[k] : v[k + 8], keep = up ? v[k + 8] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float send = up ? v[k] : v[k + 4], keep = up ? v[k + 4] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool up = lane & 4;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const float send = up ? v[k] : v[k + 2], keep = up ? v[k + 2] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    {
+        const bool up = lane & 2;
+        const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+__device__ __forceinline__ int butterfly_index(int lane) {
+    return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
+}
+
+template <typename T, int RT, int N>
+__global__ void __launch_bounds__(SB_THREADS, 2)
+scan_bwd_kernel(Geom g, int nplanes_ds, const T* __restrict__ u, const T* __restrict__ xdbl, int64_t ldxd, int R,
+                const float* __restrict__ dtw, const float* __restrict__ dtb, const float* __restrict__ A,
+                int a_is_log, const float* __restrict__ ds, T* __restrict__ du, T* __restrict__ ddelta,
+                float* __restrict__ dbc_planes, float* __restrict__ dA, float* __restrict__ dbias) {
+    static_assert(N == 16, "butterfly reduction is written for 16 states");
+    constexpr int WROW = RT + 2 * N;
+    extern __shared__ __align__(16) float smem[];
+    // smem: tile[LC][WROW] | us[LC][128] | dys[LC][128] | red[4 warps][LC][2N] | ckpt[nchunks][N][128]
+    float(*tile)[WROW] = reinterpret_cast<float(*)[WROW]>(smem);
+    float* us = smem + SB_LC * WROW;
+    float* dys = us + SB_LC * SB_THREADS;
+    float* red = dys + SB_LC * SB_THREADS;
+    float* ckpt = red + 4 * SB_LC * 2 * N;
+
+    const int dir = blockIdx.z, b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d = blockIdx.x * SB_THREADS + tid;
+    const bool live = d < g.D;
+    const int dd = live ? d : 0;
+    const int Lp = g.Lp;
+    const int nchunks = (Lp + SB_LC - 1) / SB_LC;
+    const int64_t plane = (int64_t)g.B * Lp * g.D;
+    constexpr float LOG2E = 1.4426950408889634f;
+
+    float A2[N], Anat[N];
+    {
+        const float* Ap = A + ((int64_t)dir * g.D + dd) * N;
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+            const float a = Ap[n];
+            Anat[n] = a_is_log ? -expf(a) : a;
+            A2[n] = Anat[n] * LOG2E;
+        }
+    }
+    const float* Wp = dtw + ((int64_t)dir * g.D + dd) * R;
+    const float bias = dtb[(int64_t)dir * g.D + dd];
+    const T* ub = u + dir * plane + (int64_t)b * Lp * g.D + dd;
+    const T* xd = xdbl + ((int64_t)dir * g.B + b) * Lp * ldxd;
+    const float* dsb = ds + (int64_t)b * Lp * g.D + dd;
+    T* dub = du + dir * plane + (int64_t)b * Lp * g.D + dd;
+    T* ddb = ddelta + dir * plane + (int64_t)b * Lp * g.D + dd;
+    const int step = dir == 0 ? 1 : -1;
+
+    auto load_tile = [&](int r_lo, int rows) {
+        for (int i = tid; i < rows * WROW; i += SB_THREADS) {
+            const int r = i / WROW, c = i - r * WROW;
+            float v = 0.f;
+            if (c < RT) {
+                if (c < R) v = ld1(xd + (int64_t)(r_lo + r) * ldxd + c);
+            } else {
+                v = ld1(xd + (int64_t)(r_lo + r) * ldxd + R + (c - RT));
+            }
+            tile[r][c] = v;
+        }
+    };
+    // pre-activation of delta at tile row `tr`
+    auto pre_of = [&](int tr) {
+        const float* row = tile[tr];
+        float dt = bias;
+        for (int j = 0; j < R; ++j) dt = fmaf(__ldg(Wp + j), row[j], dt);
+        return dt;
+    };
+
+    // ---------------- pass A: forward sweep, checkpoint states at chunk starts
+    if (nchunks > 1) {
+        float h[N];
+#pragma unroll
+        for (int n = 0; n < N; ++n) h[n] = 0.f;
+        for (int cc = 0; cc < nchunks; ++cc) {
+            const int chunk = dir == 0 ? cc : nchunks - 1 - cc;
+            const int r_lo = chunk * SB_LC, rows = min(SB_LC, Lp - r_lo);
+            __syncthreads();
+            load_tile(r_lo, rows);
+            __syncthreads();
+#pragma unroll
+            for (int n = 0; n < N; ++n) ckpt[(cc * N + n) * SB_THREADS + tid] = h[n];
+            if (cc == nchunks - 1) break;
+            const int r0 = dir == 0 ? r_lo : r_lo + rows - 1;
+            for (int rr = 0; rr < rows; ++rr) {
+                const int r = r0 + rr * step;
+                const float* row = tile[r - r_lo];
+                const float delta = softplus20(pre_of(r - r_lo));
+                const float dlu = delta * (live ? ld1(ub + (int64_t)r * g.D) : 0.f);
+#pragma unroll
+                for (int n = 0; n < N; ++n) h[n] = fmaf(ex2b(delta * A2[n]), h[n], dlu * row[RT + n]);
+            }
+        }
+    }
+
+    // ---------------- pass B: reverse sweep
+    float gcar[N], dAacc[N];
+#pragma unroll
+    for (int n = 0; n < N; ++n) gcar[n] = 0.f, dAacc[n] = 0.f;
+    float dbias_acc = 0.f;
+    for (int cc = nchunks - 1; cc >= 0; --cc) {
+        const int chunk = dir == 0 ? cc : nchunks - 1 - cc;
+        const int r_lo = chunk * SB_LC, rows = min(SB_LC, Lp - r_lo);
+        const int r0 = dir == 0 ? r_lo : r_lo + rows - 1;  // first row of the chunk in scan order
+        __syncthreads();
+        load_tile(r_lo, rows);
+        for (int i = tid; i < 4 * SB_LC * 2 * N; i += SB_THREADS) red[i] = 0.f;
+        // per-thread chunk inputs in scan order: u, dy (sum of the incoming ds planes)
+#pragma unroll
+        for (int rr = 0; rr < SB_LC; ++rr) {
+            float uv = 0.f, dyv = 0.f;
+            if (rr < rows && live) {
+                const int r = r0 + rr * step;
+                uv = ld1(ub + (int64_t)r * g.D);
+                for (int q = 0; q < nplanes_ds; ++q) dyv += dsb[q * plane + (int64_t)r * g.D];
+            }
+            us[rr * SB_THREADS + tid] = uv;
+            dys[rr * SB_THREADS + tid] = dyv;
+        }
+        __syncthreads();
+        float delta[SB_LC], ddl[SB_LC], dul[SB_LC];
+#pragma unroll
+        for (int rr = 0; rr < SB_LC; ++rr) {
+            delta[rr] = rr < rows ? softplus20(pre_of((r0 + rr * step) - r_lo)) : 0.f;
+            ddl[rr] = 0.f;
+            dul[rr] = 0.f;
+        }
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+            float hl[SB_LC], al[SB_LC];
+            float hprev = nchunks > 1 ? ckpt[(cc * N + n) * SB_THREADS + tid] : 0.f;
+            const float h_in = hprev;
+            // forward inside the chunk (delta = 0 past the end: a = 1, b = 0 keeps h)
+#pragma unroll
+            for (int rr = 0; rr < SB_LC; ++rr) {
+                const int tr = rr < rows ? (r0 + rr * step) - r_lo : 0;
+                al[rr] = ex2b(delta[rr] * A2[n]);
+                hprev = fmaf(al[rr], hprev, delta[rr] * us[rr * SB_THREADS + tid] * tile[tr][RT + n]);
+                hl[rr] = hprev;
+            }
+            // reverse
+            float gn = gcar[n];  // = a_{i+1} g_{i+1} of the first row of the next chunk in scan order
+            float dBv[SB_LC], dCv[SB_LC];
+#pragma unroll
+            for (int rr = SB_LC - 1; rr >= 0; --rr) {
+                const int tr = rr < rows ? (r0 + rr * step) - r_lo : 0;
+                const float Bn = tile[tr][RT + n], Cn = tile[tr][RT + N + n];
+                const float dyv = dys[rr * SB_THREADS + tid], uv = us[rr * SB_THREADS + tid];
+                const float gi = rr < rows ? fmaf(Cn, dyv, gn) : gn;
+                const float hm1 = rr > 0 ? hl[rr - 1] : h_in;
+                const float da_a = gi * hm1 * al[rr];  // dL/da * a
+                dCv[rr] = rr < rows ? dyv * hl[rr] : 0.f;
+                dBv[rr] = rr < rows ? gi * delta[rr] * uv : 0.f;
+                dul[rr] = fmaf(gi * delta[rr], Bn, dul[rr]);
+                ddl[rr] = fmaf(gi * Bn, uv, fmaf(da_a, Anat[n], ddl[rr]));
+                dAacc[n] = fmaf(da_a, delta[rr], dAacc[n]);
+                gn = rr < rows ? gi * al[rr] : gn;
+            }
+            gcar[n] = gn;
+            // reduce dB / dC over the 32 channels of the warp; rows indexed in scan order
+            const float sB = butterfly16(dBv, lane), sC = butterfly16(dCv, lane);
+            if ((lane & 1) == 0) {
+                const int rr = butterfly_index(lane);
+                red[(warp * SB_LC + rr) * 2 * N + n] = sB;
+                red[(warp * SB_LC + rr) * 2 * N + N + n] = sC;
+            }
+        }
+        // per-row outputs
+#pragma unroll
+        for (int rr = 0; rr < SB_LC; ++rr) {
+            if (rr < rows && live) {
+                const int r = r0 + rr * step;
+                const float pre = pre_of(r - r_lo);
+                const float dpre = pre <= 20.f ? ddl[rr] * sigmoidf_(pre) : ddl[rr];
+                dbias_acc += dpre;
+                st1(dub + (int64_t)r * g.D, dul[rr]);
+                st1(ddb + (int64_t)r * g.D, dpre);
+            }
+        }
+        __syncthreads();
+        // dB/dC partial plane of this 128-channel column: (ncol, 2, B*Lp, 2N)
+        float* outp = dbc_planes + (((int64_t)blockIdx.x * 2 + dir) * g.B + b) * Lp * 2 * N;
+        for (int i = tid; i < rows * 2 * N; i += SB_THREADS) {
+            const int rr = i / (2 * N), c = i - rr * 2 * N;
+            const float v = red[(0 * SB_LC + rr) * 2 * N + c] + red[(1 * SB_LC + rr) * 2 * N + c] +
+                            red[(2 * SB_LC + rr) * 2 * N + c] + red[(3 * SB_LC + rr) * 2 * N + c];
+            outp[(int64_t)(r0 + rr * step) * 2 * N + c] = v;
+        }
+    }
+    if (live) {
+        float* dAp = dA + ((int64_t)dir * g.D + d) * N;
+#pragma unroll
+        for (int n = 0; n < N; ++n) atomicAdd(dAp + n, a_is_log ? dAacc[n] * Anat[n] : dAacc[n]);
+        atomicAdd(dbias + (int64_t)dir * g.D + d, dbias_acc);
+    }
+}
+
+// sums `nplanes` planes of `n` floats: out[i] = sum_p in[p*n + i] (adds to the cast when `accumulate`)
+template <typename TO>
+__global__ void reduce_planes_kernel(const float* __restrict__ in, int nplanes, int64_t n, TO* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.f;
+    for (int p = 0; p < nplanes; ++p) acc += in[p * n + i];
+    st1(out + i, acc);
+}
+
+int check_geom(const fv_geom* g, const char* who);
+
+template <typename T>
+static int launch_scan_bwd(const Geom& g, int nplanes_ds, const T* u, const T* xdbl, int64_t ldxd, int R, int N,
+                           const float* dtw, const float* dtb, const float* A, int a_is_log, const float* ds, T* du,
+                           T* ddelta, float* dbc, float* dA, float* dbias, cudaStream_t st) {
+    FV_REQUIRE(N == 16, "fv_scan_bwd: d_state %d not supported (16)", N);
+    const int nchunks = ceil_div(g.Lp, SB_LC);
+    dim3 grid(ceil_div(g.D, SB_THREADS), g.B, 2), block(SB_THREADS);
+#define FV_SB_CASE(RT_)                                                                                              \
+    if (R <= RT_) {                                                                                                  \
+        const size_t smem = sizeof(float) * ((size_t)SB_LC * (RT_ + 32) + 2 * SB_LC * SB_THREADS + 4 * SB_LC * 32 +  \
+                                             (nchunks > 1 ? (size_t)nchunks * 16 * SB_THREADS : 0));                 \
+        FV_REQUIRE(smem <= 200 * 1024, "fv_scan_bwd: pooled length %d too long for the shared-memory checkpoints", g.Lp); \
+        auto kern = scan_bwd_kernel<T, RT_, 16>;                                                                     \
+        if (smem > 48 * 1024) {                                                                                      \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
+            FV_REQUIRE(e == cudaSuccess, "fv_scan_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));            \
+        }                                                                                                            \
+        kern<<<grid, block, smem, st>>>(g, nplanes_ds, u, xdbl, ldxd, R, dtw, dtb, A, a_is_log, ds, du, ddelta, dbc, \
+                                        dA, dbias);                                                                  \
+        return finish_launch("scan_bwd");                                                                            \
+    }
+    FV_SB_CASE(12) FV_SB_CASE(24) FV_SB_CASE(48) FV_SB_CASE(64)
+#undef FV_SB_CASE
+    return fail("fv_scan_bwd: dt_rank %d > 64 not supported", R);
+}
+
+}  // namespace fv
+
+extern "C" int fv_scan_bwd(const fv_geom* g_, int dtype, int nplanes_ds, const void* u, const void* xdbl,
+                           int64_t ld_xdbl, int dt_rank, int dstate, const float* dt_w, const float* dt_bias,
+                           const float* A, int a_is_log, const float* ds, void* du, void* ddelta,
+                           float* dbc_planes, float* dA, float* d_dt_bias, void* stream) {
+    using namespace fv;
+    if (int rc = check_geom(g_, "fv_scan_bwd")) return rc;
+    FV_REQUIRE(u && xdbl && dt_w && dt_bias && A && ds && du && ddelta && dbc_planes && dA && d_dt_bias,
+               "fv_scan_bwd: null pointer");
+    FV_REQUIRE(dt_rank > 0 && ld_xdbl >= dt_rank + 2 * dstate, "fv_scan_bwd: ld_xdbl %lld < R+2N", (long long)ld_xdbl);
+    FV_REQUIRE(g_->batch <= 65535 && nplanes_ds >= 1, "fv_scan_bwd: bad batch / plane count");
+    Geom g = make_geom(g_);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == FV_F32)
+        return launch_scan_bwd<float>(g, nplanes_ds, (const float*)u, (const float*)xdbl, ld_xdbl, dt_rank, dstate, dt_w,
+                                      dt_bias, A, a_is_log, ds, (float*)du, (float*)ddelta, dbc_planes, dA, d_dt_bias, st);
+    if (dtype == FV_BF16)
+        return launch_scan_bwd<bf16>(g, nplanes_ds, (const bf16*)u, (const bf16*)xdbl, ld_xdbl, dt_rank, dstate, dt_w,
+                                     dt_bias, A, a_is_log, ds, (bf16*)du, (bf16*)ddelta, dbc_planes, dA, d_dt_bias, st);
+    return fail("fv_scan_bwd: unsupported dtype %d", dtype);
+}
+
+extern "C" int fv_reduce_planes(int out_dtype, const float* in, int nplanes, int64_t n, void* out, void* stream) {
+    using namespace fv;
+    FV_REQUIRE(in && out && nplanes >= 1 && n > 0, "fv_reduce_planes: bad arguments");
+    dim3 grid((unsigned)((n + 255) / 256)), block(256);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_dtype == FV_F32) reduce_planes_kernel<float><<<grid, block, 0, st>>>(in, nplanes, n, (float*)out);
+    else if (out_dtype == FV_BF16) reduce_planes_kernel<bf16><<<grid, block, 0, st>>>(in, nplanes, n, (bf16*)out);
+    else return fail("fv_reduce_planes: unsupported dtype %d", out_dtype);
+    return finish_launch("reduce_planes");
+}

@@ -181,3 +181,95 @@ def selective_scan_fwd(u: Tensor, delta: Tensor, A: Tensor, B: Tensor, Cm: Tenso
     _lib.call("fv_selective_scan_fwd", _dt(u), batch, dim, L, N, groups, _p(u), _p(delta), _p(A), _p(B), _p(Cm),
               _p(D), _p(z), _p(delta_bias), int(delta_softplus), _p(out), _p(last), _stream(u))
     return out, last
+
+
+# --------------------------------------------------------------------------- backward wrappers
+def bwd_tiles_per_group(geom: Geometry, batch: int, dim: int, dtype: torch.dtype) -> int:
+    g = geom.c_struct(batch, dim)
+    n = _lib.lib().fv_bwd_tiles_per_group(C.byref(g), FV_F32 if dtype == torch.float32 else FV_BF16)
+    if n <= 0:
+        raise _lib.FastVimLibraryError("backward kernels need a plain (outer, pool, 1) geometry")
+    return int(n)
+
+
+def gate_bwd(x: Tensor, z: Tensor, dy: Tensor, s: Tensor, geom: Geometry, conv_w: Tensor, conv_b: Optional[Tensor],
+             Dskip: Tensor, ln_w: Optional[Tensor], ln_b: Optional[Tensor], eps: float, dz: Tensor):
+    """K2b-bwd.  Writes dz in place (the z half of the d(xz) buffer); returns
+    (e (B, L, D), ds_planes (tpg, B, Lp, D) fp32, dDskip (2, D), dln_w, dln_b)."""
+    _check_cuda(x, z, dy, s)
+    B, L, D = x.shape
+    ldx, bs = _tokmajor(x, "x")
+    assert _tokmajor(z, "z") == (ldx, bs) and _tokmajor(dz, "dz") == (ldx, bs)
+    lddy, dybs = _tokmajor(dy, "dy")
+    tpg = bwd_tiles_per_group(geom, B, D, x.dtype)
+    e = torch.empty((B, L, D), device=x.device, dtype=x.dtype)
+    ds = torch.empty((tpg, B, geom.Lp, D), device=x.device, dtype=torch.float32)
+    dD = torch.zeros((2, D), device=x.device, dtype=torch.float32)
+    dlw = torch.zeros(D, device=x.device, dtype=torch.float32) if ln_w is not None else None
+    dlb = torch.zeros(D, device=x.device, dtype=torch.float32) if ln_w is not None else None
+    g = geom.c_struct(B, D)
+    _lib.call("fv_gate_bwd", C.byref(g), _dt(x), _p(x), _p(z), ldx, bs, _p(dy), lddy, dybs, _p(s), _p(conv_w),
+              _p(conv_b), _p(Dskip), _p(ln_w), _p(ln_b), float(eps), _p(dz), _p(e), _p(ds), _p(dD), _p(dlw), _p(dlb),
+              _stream(x))
+    return e, ds, dD, dlw, dlb
+
+
+def scan_bwd(ds: Tensor, u: Tensor, xdbl: Tensor, geom: Geometry, dt_rank: int, d_state: int, dt_w: Tensor,
+             dt_bias: Tensor, A: Tensor, a_is_log: bool = True):
+    """K2a-bwd -> (du, ddelta (2, B, Lp, D) act dtype, dBC (2, B*Lp, 2N) act dtype, dA (2, D, N), d_dt_bias (2, D))."""
+    _check_cuda(ds, u, xdbl)
+    _, B, Lp, D = u.shape
+    assert u.is_contiguous() and ds.is_contiguous() and ds.dtype == torch.float32 and xdbl.stride(2) == 1
+    ncol = (D + 127) // 128
+    du = torch.empty_like(u)
+    ddelta = torch.empty_like(u)
+    planes = torch.empty((ncol, 2, B * Lp, 2 * d_state), device=u.device, dtype=torch.float32)
+    dA = torch.zeros((2, D, d_state), device=u.device, dtype=torch.float32)
+    dbias = torch.zeros((2, D), device=u.device, dtype=torch.float32)
+    g = geom.c_struct(B, D)
+    _lib.call("fv_scan_bwd", C.byref(g), _dt(u), ds.shape[0], _p(u), _p(xdbl), xdbl.stride(1), dt_rank, d_state,
+              _p(dt_w), _p(dt_bias), _p(A), int(a_is_log), _p(ds), _p(du), _p(ddelta), _p(planes), _p(dA), _p(dbias),
+              _stream(u))
+    dbc = torch.empty((2, B * Lp, 2 * d_state), device=u.device, dtype=u.dtype)
+    _lib.call("fv_reduce_planes", _dt(u), _p(planes), ncol, dbc.numel(), _p(dbc), _stream(u))
+    return du, ddelta, dbc, dA, dbias
+
+
+def conv_pool_bwd(x: Tensor, e: Tensor, du: Tensor, geom: Geometry, conv_w: Tensor, conv_b: Optional[Tensor],
+                  Dskip: Tensor, scale: float, dx: Tensor):
+    """K1-bwd.  Writes dx in place (the x half of the d(xz) buffer); returns (dconv_w (2, D, 4), dconv_b (2, D))."""
+    _check_cuda(x, e, du)
+    B, L, D = x.shape
+    ldx, bs = _tokmajor(x, "x")
+    assert _tokmajor(dx, "dx") == (ldx, bs) and e.is_contiguous() and du.is_contiguous()
+    dcw = torch.zeros((2, D, 4), device=x.device, dtype=torch.float32)
+    dcb = torch.zeros((2, D), device=x.device, dtype=torch.float32) if conv_b is not None else None
+    g = geom.c_struct(B, D)
+    _lib.call("fv_conv_pool_bwd", C.byref(g), _dt(x), _p(x), ldx, bs, _p(e), _p(du), _p(conv_w), _p(conv_b),
+              _p(Dskip), float(scale), FV_POOL_MEAN, _p(dx), _p(dcw), _p(dcb), _stream(x))
+    return dcw, dcb
+
+
+def add_norm_bwd(dy: Tensor, dres_out: Optional[Tensor], res_out: Tensor, weight: Tensor, eps: float, is_rms: bool,
+                 has_bias: bool, x_dtype: torch.dtype, want_dx: bool, want_dres: bool):
+    """-> (dx (x_dtype) | None, dresidual_in fp32 | None, dweight, dbias | None)"""
+    _check_cuda(dy, res_out, weight)
+    shape = res_out.shape
+    cols = shape[-1]
+    dy2 = dy.reshape(-1, cols)
+    if dy2.stride(1) != 1:
+        dy2 = dy2.contiguous()
+    rows = dy2.shape[0]
+    res2 = res_out.reshape(rows, cols)
+    assert res2.is_contiguous() and res2.dtype == torch.float32
+    if dres_out is not None:
+        dres_out = dres_out.reshape(rows, cols).float().contiguous()
+    if dy2.dtype != x_dtype:
+        dy2 = dy2.to(x_dtype)
+    dx = torch.empty((rows, cols), device=dy.device, dtype=x_dtype) if want_dx else None
+    dres = torch.empty((rows, cols), device=dy.device, dtype=torch.float32) if want_dres else None
+    dw = torch.zeros(cols, device=dy.device, dtype=torch.float32)
+    db = torch.zeros(cols, device=dy.device, dtype=torch.float32) if has_bias else None
+    _lib.call("fv_add_norm_bwd", _dt(dy2), rows, cols, _p(dy2), dy2.stride(0), _p(dres_out), _p(res2), _p(weight),
+              float(eps), int(is_rms), _p(dx), cols, _p(dres), _p(dw), _p(db), _stream(dy))
+    return (None if dx is None else dx.reshape(shape), None if dres is None else dres.reshape(shape), dw, db)

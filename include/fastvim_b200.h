@@ -120,6 +120,55 @@ int fv_selective_scan_fwd(int dtype, int batch, int dim, int64_t L, int dstate, 
                           const void* C, const float* D, const void* z, const float* delta_bias,
                           int delta_softplus, void* out, float* last_state, void* stream);
 
+
+/* ======================= backward (training) entry points ==============================
+ * Replace SelectiveScanFn.backward / selective_scan_cuda.bwd (selective_scan_interface.py:59-102,
+ * csrc/selective_scan/selective_scan.cpp:338-492), FastVim_MambaInnerFnNoOutProj_withoutZ.backward
+ * (selective_scan_interface.py:605-776), causal_conv1d_bwd (:751-753) and the Triton
+ * _layer_norm_bwd_kernel (ops/triton/layernorm.py:210-305).  Plain (outer, pool, 1) geometries,
+ * mean pooling.  Parameter-gradient outputs are ACCUMULATED (caller zero-fills).
+ */
+
+/* number of tiles the backward kernels cut one pooled group into (= planes of ds) */
+int fv_bwd_tiles_per_group(const fv_geom* g, int dtype);
+
+/* K2b-bwd.  dy (B, L, dim) dtype, row stride lddy.  Outputs: dz (same layout/strides as z: the z half
+ * of the d(xz) buffer), e (B, L, dim) dtype contiguous = dL/dv / 2, ds_planes (tiles_per_group, B, Lp, dim)
+ * fp32, dDskip (2, dim), dln_w, dln_b (dim) fp32 accumulated. */
+int fv_gate_bwd(const fv_geom* g, int dtype, const void* x, const void* z, int64_t ldxz, int64_t xz_bstride,
+                const void* dy, int64_t lddy, int64_t dy_bstride, const float* s, const float* conv_w,
+                const float* conv_b, const float* Dskip, const float* ln_w, const float* ln_b, float eps,
+                void* dz, void* e_out, float* ds_planes, float* dDskip, float* dln_w, float* dln_b,
+                void* stream);
+
+/* K2a-bwd.  ds (nplanes_ds, B, Lp, dim) fp32 (summed on load; the same gradient feeds both directions).
+ * Outputs: du, ddelta (2, B, Lp, dim) dtype (ddelta = gradient of the dt_proj pre-activation);
+ * dbc_planes (ceil(dim/128), 2, B*Lp, 2N) fp32 partial sums over 128-channel columns of [dB | dC]
+ * (add them with fv_reduce_planes); dA (2, dim, N) (gradient of A_log if a_is_log), d_dt_bias (2, dim)
+ * fp32 accumulated. */
+int fv_scan_bwd(const fv_geom* g, int dtype, int nplanes_ds, const void* u, const void* xdbl,
+                int64_t ld_xdbl, int dt_rank, int dstate, const float* dt_w, const float* dt_bias,
+                const float* A, int a_is_log, const float* ds, void* du, void* ddelta,
+                float* dbc_planes, float* dA, float* d_dt_bias, void* stream);
+
+/* out[i] = sum_p in[p*n + i], out dtype FV_F32 | FV_BF16 */
+int fv_reduce_planes(int out_dtype, const float* in, int nplanes, int64_t n, void* out, void* stream);
+
+/* K1-bwd.  e from fv_gate_bwd, du (2, B, Lp, dim) dtype = total gradient of the pooled conv outputs.
+ * Outputs: dx (same layout/strides as x: the x half of the d(xz) buffer), dconv_w (2, dim, 4),
+ * dconv_b (2, dim) fp32 accumulated. */
+int fv_conv_pool_bwd(const fv_geom* g, int dtype, const void* x, int64_t ldx, int64_t x_bstride,
+                     const void* e, const void* du, const float* conv_w, const float* conv_b,
+                     const float* Dskip, float scale, int pool_mode, void* dx, float* dconv_w,
+                     float* dconv_b, void* stream);
+
+/* add + norm backward.  residual_out is the fp32 sum saved by the forward; dresidual_out (grad of that
+ * output) may be NULL.  dx (dtype) and/or dresidual_in (fp32) receive the same gradient. */
+int fv_add_norm_bwd(int dtype, int64_t rows, int cols, const void* dy, int64_t lddy,
+                    const float* dresidual_out, const float* residual_out, const float* weight,
+                    float eps, int is_rms, void* dx, int64_t lddx, float* dresidual_in, float* dweight,
+                    float* dbias, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -225,3 +225,90 @@ def test_selective_scan_fn_fwd_vs_reference_golden(name):
     assert torch.allclose(last.cpu(), g["last_state"], rtol=6e-4, atol=2e-3)
     assert_close(out, g["out"], 1e-4, "out")
     assert_close(last, g["last_state"], 1e-4, "last_state")
+
+
+# ------------------------------------------------------------------ backward (training path)
+def _oracle_mixer_grads(h, p, ts, dout, **kw):
+    p = {k: v.clone().double().requires_grad_(True) for k, v in p.items()}
+    h = h.clone().double().requires_grad_(True)
+    out = O.mixer_oracle(h, p, ts, **kw)
+    out.backward(dout.double())
+    return out.detach(), h.grad, {k: v.grad for k, v in p.items()}
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("d_model,ts,norm", [(192, (14, 14), True), (64, (5, 9), True), (96, (3, 40), True),
+                                              (64, (20, 2), False), (768, (14, 14), True)])
+def test_mixer_backward_vs_oracle(dtype, d_model, ts, norm):
+    """Gradients of the CUDA training path (MixerFn: gate_bwd, scan_bwd, conv_pool_bwd) w.r.t. the input
+    and every parameter against autograd through the fp64 oracle."""
+    p = O.random_mixer_params(d_model, seed=5)
+    if not norm:
+        p = {k: v for k, v in p.items() if not k.startswith("layernorm")}
+    torch.manual_seed(1)
+    Bt = 2
+    h = torch.randn(Bt, ts[0] * ts[1], d_model)
+    dout = torch.randn(Bt, ts[0] * ts[1], d_model)
+    m = _mixer_from_params(p, ts, use_norm_after_ssm=norm).train()
+    hc = h.cuda().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        out = m(hc)
+    out.backward(dout.cuda().to(out.dtype))
+    want_out, want_dh, want = _oracle_mixer_grads(h, p, ts, dout, use_norm_after_ssm=norm)
+    tol = TOL[dtype]
+    assert_close(out, want_out, tol, "out")
+    assert_close(hc.grad, want_dh, tol, "d hidden")
+    got = dict(m.named_parameters())
+    for k, g in want.items():
+        assert got[k].grad is not None, k
+        # bf16: weight gradients are sums of bf16-rounded products; allow 2x the activation tolerance
+        assert_close(got[k].grad, g, tol if dtype == torch.float32 else 2 * tol, f"d {k}")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rms", [True, False])
+@pytest.mark.parametrize("cols_", [192, 768, 100])
+def test_add_norm_backward(dtype, rms, cols_):
+    from fastvim_b200 import norm
+
+    torch.manual_seed(0)
+    x = torch.randn(3, 37, cols_).to(dtype)
+    res = torch.randn(3, 37, cols_)
+    w, b = torch.rand(cols_) + 0.5, (None if rms else torch.randn(cols_))
+    gy, gr = torch.randn(3, 37, cols_), torch.randn(3, 37, cols_)
+    xo, ro, wo = x.double().requires_grad_(True), res.double().requires_grad_(True), w.double().requires_grad_(True)
+    bo = None if b is None else b.double().requires_grad_(True)
+    y_o, r_o = O.add_norm_oracle(xo, wo, bo, ro, 1e-5, rms)
+    (y_o * gy.double()).sum().backward(retain_graph=True)
+    (r_o * gr.double()).sum().backward()
+    xc, rc, wc = x.cuda().requires_grad_(True), res.cuda().requires_grad_(True), w.cuda().requires_grad_(True)
+    bc = None if b is None else b.cuda().requires_grad_(True)
+    y, r = norm.layer_norm_fn(xc, wc, bc, residual=rc, eps=1e-5, prenorm=True, residual_in_fp32=True, is_rms_norm=rms)
+    ((y.float() * gy.cuda()).sum() + (r * gr.cuda()).sum()).backward()
+    tol = TOL[dtype]
+    assert_close(xc.grad, xo.grad, tol, "dx")
+    assert_close(rc.grad, ro.grad, tol, "dresidual")
+    assert_close(wc.grad, wo.grad, tol, "dweight")
+    if b is not None:
+        assert_close(bc.grad, bo.grad, tol, "dbias")
+
+
+def test_small_model_training_step_grads_fp32():
+    """4-block FastVim (rotated odd layers included): loss gradients of every parameter vs the oracle."""
+    from fastvim_b200.vision import VisionMamba
+
+    torch.manual_seed(0)
+    m = VisionMamba(img_size=(64, 96), embed_dim=32, depth=4, num_classes=10, rms_norm=True, residual_in_fp32=True,
+                    fused_add_norm=True, final_pool_type="mean", drop_path_rate=0.0)
+    sd = {k: v.detach().clone().double().requires_grad_(True) for k, v in m.state_dict().items()}
+    imgs = torch.randn(2, 3, 64, 96)
+    tgt = torch.tensor([3, 7])
+    logits_o = O.fastvim_oracle(imgs.double(), sd, depth=4)
+    torch.nn.functional.cross_entropy(logits_o, tgt).backward()
+    m = m.cuda().train()
+    logits = m(imgs.cuda())
+    torch.nn.functional.cross_entropy(logits.float(), tgt.cuda()).backward()
+    assert_close(logits, logits_o.detach(), 1e-4, "logits")
+    for k, v in m.named_parameters():
+        assert v.grad is not None, k
+        assert_close(v.grad, sd[k].grad, 2e-4, f"d {k}")
