@@ -218,7 +218,13 @@ def run_ours(a):
                         final_pool_type="mean", drop_path_rate=0.0).eval().to(dev)
     if w.get("train"):
         return run_train(a, model, w, Bt, dev, rank, world, local)
-    g = torch.Generator(device="cpu").manual_seed(100 + rank)
+    # one very large image: d_inner channels sharded over the ranks (strong scaling), same image on every rank
+    sharded = img >= 1024 and world > 1
+    if sharded:
+        from fastvim_b200.sharded import shard_model_channels
+        shard_model_channels(model, None, a.out_mode)
+    n_img_step = Bt if sharded else Bt * n_gpus
+    g = torch.Generator(device="cpu").manual_seed(100 + (0 if sharded else rank))
     host_imgs = [torch.randn(Bt, 3, img, img, generator=g).pin_memory() for _ in range(2)]
     host_out = [torch.empty(Bt, 1000).pin_memory() for _ in range(2)]
 
@@ -238,17 +244,22 @@ def run_ours(a):
     graphs, static_out, launches_per_step = [], [], 0
     use_graph = not a.no_graph
     if use_graph:
-        pool = None
-        for i in range(2):
-            gr = torch.cuda.CUDAGraph()
-            _lib.reset_launch_count()
-            with torch.cuda.graph(gr, pool=pool):
-                o = fwd(static_in[i])
-            pool = gr.pool()
-            launches_per_step = _lib.launch_count()
-            graphs.append(gr)
-            static_out.append(o)
-    else:
+        try:
+            pool = None
+            for i in range(2):
+                gr = torch.cuda.CUDAGraph()
+                _lib.reset_launch_count()
+                with torch.cuda.graph(gr, pool=pool):
+                    o = fwd(static_in[i])
+                pool = gr.pool()
+                launches_per_step = _lib.launch_count()
+                graphs.append(gr)
+                static_out.append(o)
+        except Exception as ex:  # launch mode only (e.g. a collective that cannot be captured): run eagerly
+            sys.stderr.write(f"[bench] CUDA graph capture failed ({type(ex).__name__}: {ex}); running eagerly\n")
+            use_graph, graphs, static_out = False, [], []
+            torch.cuda.synchronize()
+    if not use_graph:
         _lib.reset_launch_count()
         fwd(static_in[0])
         launches_per_step = _lib.launch_count()
@@ -289,7 +300,7 @@ def run_ours(a):
     tw1 = time.perf_counter()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / a.steps
-    value = n_gpus * Bt * a.steps / (ms_total * 1e-3)
+    value = n_img_step * a.steps / (ms_total * 1e-3)
 
     # ---- e2e: pinned host images in, logits out, every step, double-buffered ----------------
     copy_s = torch.cuda.Stream(dev)
@@ -324,13 +335,13 @@ def run_ours(a):
     t_e2e = time.perf_counter() - t0
     barrier()
     t_e2e = max_over_ranks(t_e2e)
-    e2e_value = n_gpus * Bt * a.steps / t_e2e
+    e2e_value = n_img_step * a.steps / t_e2e
     clocks = sampler.stop(tw0, tw1) if rank == 0 else None
 
     # ---- roofline: instrumented eager pass, CUDA events around every C-ABI launch ------------
     roof = None
     kern_table = {}
-    if rank == 0:
+    if rank == 0 or sharded:   # sharded: the forward contains collectives, every rank must run it
         for _ in range(2):
             fwd(static_in[0])
         recs = []
@@ -345,11 +356,13 @@ def run_ours(a):
             d[0] += ev0.elapsed_time(ev1)
             d[1] += 1
         m0 = model.layers[0].mixer
+        m0 = getattr(m0, "mixer", m0)          # channel-sharded wrapper
+        D_loc = m0.d_inner // (world if sharded else 1)
         L = (img // 16) ** 2
         Lp = img // 16
         peaks, peak_src = load_peaks()
         for name, (tot, cnt) in agg.items():
-            ab = algorithmic_bytes(name, Bt, L, Lp, m0.d_inner, E, m0.dt_rank, m0.d_state, 2)
+            ab = algorithmic_bytes(name, Bt, L, Lp, D_loc, E, m0.dt_rank, m0.d_state, 2)
             avg_ms = tot / cnt
             kern_table[name] = {"launches_per_step": cnt // 3, "avg_us": round(avg_ms * 1e3, 2),
                                 "ms_per_step": round(tot / 3, 4), "alg_bytes": ab,
@@ -374,9 +387,11 @@ def run_ours(a):
     if rank == 0:
         line = {"metric": "FastVim inference throughput", "value": round(value, 1), "unit": "images/s", "n_gpus": n_gpus,
                 "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": a.workload, "desc": w["desc"], "batch_per_gpu": Bt, "global_batch": Bt * n_gpus,
-                           "sharding": f"batch-sharded x{n_gpus}, no data-path collective",
+                "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": a.workload, "desc": w["desc"], "batch_per_gpu": Bt, "global_batch": n_img_step,
+                           "sharding": (f"d_inner channel-sharded x{n_gpus}: all-reduce x_proj partials + LN stats, "
+                                        f"{a.out_mode} around out_proj (NCCL)") if sharded else
+                           f"batch-sharded x{n_gpus}, no data-path collective",
                            "launch": "cuda_graph" if use_graph else "eager",
                            "l2": "per-step working set (24 blocks x ~%d MB of activations) exceeds the 126 MB L2; no flush"
                                  % (3 * Bt * L * m0.d_inner * 2 // 2**20)},
@@ -387,7 +402,13 @@ def run_ours(a):
                 "clocks": clocks, "roofline": roof, "cpu_baseline": cpu, "kernels": kern_table}
         print(json.dumps(line), flush=True)
     if world > 1:
+        torch.cuda.synchronize()
         dist.barrier()
+        if sharded:
+            # CUDA graphs holding captured NCCL collectives are still alive: skip the communicator teardown
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
         dist.destroy_process_group()
     return 0
 
@@ -499,6 +520,8 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the workload's)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--out-mode", default="gather", choices=["gather", "reduce"],
+                    help="channel-sharded 2048^2 mode: all-gather y before out_proj, or row-sharded out_proj + all-reduce")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the CPU legs")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -1,0 +1,51 @@
+"""Run under torchrun on >= 2 GPUs (tests/test_gpu_multi.py launches it): the d_inner-channel-sharded
+mixer / model must reproduce the single-GPU result (fp32 within 1e-4, bf16 within 2e-2 relative)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def relerr(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+def main():
+    from fastvim_b200.sharded import shard_model_channels
+    from fastvim_b200.vision import VisionMamba
+
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    ok = True
+    for (img, E, depth, norm) in [((64, 96), 64, 4, True), ((128, 128), 64, 2, False), ((256, 256), 192, 2, True)]:
+        for out_mode in ("gather", "reduce"):
+            for dtype in (torch.float32, torch.bfloat16):
+                torch.manual_seed(0)
+                m = VisionMamba(img_size=img, embed_dim=E, depth=depth, num_classes=10, rms_norm=True, residual_in_fp32=True,
+                                fused_add_norm=True, final_pool_type="mean", drop_path_rate=0.0,
+                                use_norm_after_ssm=norm).eval().cuda()
+                x = torch.randn(1, 3, *img, device="cuda")
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+                    want = m(x).float()
+                    shard_model_channels(m, None, out_mode)
+                    got = m(x).float()
+                e = relerr(got, want)
+                tol = 1e-4 if dtype == torch.float32 else 2e-2
+                good = e <= tol
+                ok &= good
+                if rank == 0:
+                    print(f"[sharded x{world}] img {img} E {E} norm {norm} {out_mode} {dtype}: rel err {e:.2e} {'ok' if good else 'FAIL'}",
+                          flush=True)
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    sys.exit(0 if int(t.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()

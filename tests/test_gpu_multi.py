@@ -1,0 +1,23 @@
+"""Multi-GPU paths on real devices (needs >= 2 GPUs; skipped otherwise)."""
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _torchrun(script, nproc, *args, port=29533):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr",
+           "127.0.0.1", "--master-port", str(port), script, *args]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+
+
+def test_channel_sharded_model_matches_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    r = _torchrun(os.path.join(HERE, "dist_sharded_check.py"), 2)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
