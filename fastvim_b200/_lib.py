@@ -32,6 +32,9 @@ SIGNATURES = {
     "fv_scan_fwd": [_G, _I, _P, _P, _L, _I, _I, _P, _P, _P, _I, _P, _P],
     "fv_gate_fwd": [_G, _I, _P, _P, _L, _L, _P, _P, _P, _P, _P, _P, _F, _P, _L, _L, _P, _P],
     "fv_norm_gate_apply": [_G, _I, _I, _P, _L, _L, _P, _L, _L, _P, _P, _P, _F, _P],
+    "fv_block_fwd_supported": [_G, _I, _I, _I],
+    "fv_block_fwd": [_G, _I, _P, _P, _L, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _F, _F, _I, _P, _L, _L,
+                     _P, _P, _P, _P],
     "fv_add_norm_fwd": [_I, _L, _I, _P, _L, _P, _P, _P, _F, _I, _P, _L, _P, _P, _P, _P],
     "fv_selective_scan_fwd": [_I, _I, _I, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P],
     "fv_bwd_tiles_per_group": [_G, _I],

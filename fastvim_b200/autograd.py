@@ -24,12 +24,19 @@ class MixerFn(torch.autograd.Function):
         ln_w / ln_b (D) | None: fp32."""
         B, L, _ = h.shape
         D = conv_w.shape[1]
+        from . import mixer as _mixer
+
         xz = F.linear(h, in_w, in_b)
         x, z = xz[..., :D], xz[..., D:]
-        u = ops.conv_pool_fwd(x, geom, conv_w, conv_b, scale, "mean")
-        xdbl = torch.bmm(u.view(2, B * geom.Lp, D), x_w.transpose(1, 2))
-        s = ops.scan_fwd(u, xdbl, geom, dt_rank, d_state, dt_w, dt_b, A_log, a_is_log=True)
-        y = ops.gate_fwd(x, z, s, geom, conv_w, conv_b, Dk, ln_w, ln_b, eps)
+        if _mixer.FUSED_BLOCK and ops.block_fwd_supported(geom, B, D, xz.dtype, dt_rank, d_state):
+            y, u, xdbl, s = ops.block_fwd(x, z, geom, conv_w, conv_b, x_w.contiguous(), dt_w.to(xz.dtype).contiguous(),
+                                          dt_b, A_log, Dk, ln_w, ln_b, eps, scale, dt_rank, d_state, a_is_log=True,
+                                          save=True, exp_mode=_mixer.FUSED_EXP_MODE)
+        else:
+            u = ops.conv_pool_fwd(x, geom, conv_w, conv_b, scale, "mean")
+            xdbl = torch.bmm(u.view(2, B * geom.Lp, D), x_w.transpose(1, 2))
+            s = ops.scan_fwd(u, xdbl, geom, dt_rank, d_state, dt_w, dt_b, A_log, a_is_log=True)
+            y = ops.gate_fwd(x, z, s, geom, conv_w, conv_b, Dk, ln_w, ln_b, eps)
         out = F.linear(y, out_w, out_b)
         ctx.save_for_backward(h, in_w, conv_w, conv_b, x_w, dt_w, dt_b, A_log, Dk, ln_w, ln_b, out_w, xz, u, xdbl, s, y)
         ctx.meta = (geom, scale, eps, d_state, dt_rank, in_b is not None, out_b is not None)

@@ -18,6 +18,7 @@ the reference's own Block calls this module it has already permuted the tokens a
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional
 
 import torch
@@ -27,6 +28,13 @@ import torch.nn.functional as F
 from . import autograd as fv_autograd
 from . import ops
 from .ops import Geometry
+
+
+# Use the one-launch fused block interior (fv_block_fwd) whenever the configuration qualifies; the
+# four-launch path (K1 -> x_proj -> K2a -> K2b) covers everything else (fp32, long sequences, channel
+# layouts, max pooling).  Module-level switches so tests and tools/kbench.py can compare the two.
+FUSED_BLOCK = os.environ.get("FASTVIM_FUSED_BLOCK", "1") != "0"
+FUSED_EXP_MODE = int(os.environ.get("FASTVIM_FUSED_EXP_MODE", "0"))
 
 
 class Mamba(nn.Module):
@@ -111,6 +119,8 @@ class Mamba(nn.Module):
                 "conv_b": None if self.conv1d.bias is None else
                 torch.stack([self.conv1d.bias, self.conv1d_b.bias]).to(f32).contiguous(),
                 "x_w_t": torch.stack([self.x_proj.weight.t(), self.x_proj_b.weight.t()]).to(act_dtype).contiguous(),
+                "x_w": torch.stack([self.x_proj.weight, self.x_proj_b.weight]).to(act_dtype).contiguous(),
+                "dt_w_act": torch.stack([self.dt_proj.weight, self.dt_proj_b.weight]).to(act_dtype).contiguous(),
                 "dt_w": torch.stack([self.dt_proj.weight, self.dt_proj_b.weight]).to(f32).contiguous(),
                 "dt_b": torch.stack([self.dt_proj.bias, self.dt_proj_b.bias]).to(f32).contiguous(),
                 "A_log": torch.stack([self.A_log, self.A_b_log]).to(f32).contiguous(),
@@ -151,6 +161,14 @@ class Mamba(nn.Module):
         D, R, N = self.d_inner, self.dt_rank, self.d_state
         xz = F.linear(h, pk["in_w"], pk["in_b"])                        # (B, L, 2D) token-major  [a2]
         x, z = xz[..., :D], xz[..., D:]
+        eps = self.layernorm.eps if self.use_norm_after_ssm else 1e-5
+        if (FUSED_BLOCK and self.collapse_method == "mean"
+                and ops.block_fwd_supported(geom, B, D, xz.dtype, R, N)):
+            # one launch for [a3-a9]: the image's x stays resident in shared memory (csrc/block_fwd.cu)
+            y = ops.block_fwd(x, z, geom, pk["conv_w"], pk["conv_b"], pk["x_w"], pk["dt_w_act"], pk["dt_b"],
+                              pk["A_log"], pk["D"], pk["ln_w"], pk["ln_b"], eps, float(self.scaling_factor), R, N,
+                              a_is_log=True, exp_mode=FUSED_EXP_MODE)
+            return F.linear(y, pk["out_w"], pk["out_b"])                 # [a10]
         u = ops.conv_pool_fwd(x, geom, pk["conv_w"], pk["conv_b"], float(self.scaling_factor),
                               self.collapse_method)                      # (2, B, Lp, D)         [a3-a5]
         xdbl = torch.bmm(u.view(2, B * geom.Lp, D), pk["x_w_t"])         # (2, B*Lp, R+2N)        [a6]

@@ -133,6 +133,41 @@ def gate_fwd(x: Tensor, z: Tensor, s: Tensor, geom: Geometry, conv_w: Tensor, co
     return y
 
 
+def block_fwd_supported(geom: Geometry, batch: int, dim: int, dtype: torch.dtype, dt_rank: int, d_state: int) -> bool:
+    """True when the fused one-launch block interior (``fv_block_fwd``) handles this configuration."""
+    if dtype != torch.bfloat16:
+        return False
+    g = geom.c_struct(batch, dim)
+    return bool(_lib.lib().fv_block_fwd_supported(C.byref(g), FV_BF16, int(dt_rank), int(d_state)))
+
+
+def block_fwd(x: Tensor, z: Tensor, geom: Geometry, conv_w: Tensor, conv_b: Optional[Tensor], xproj_w: Tensor,
+              dt_w: Tensor, dt_bias: Tensor, A: Tensor, Dskip: Tensor, ln_w: Optional[Tensor], ln_b: Optional[Tensor],
+              eps: float, scale: float, dt_rank: int, d_state: int, a_is_log: bool = True, save: bool = False,
+              exp_mode: int = 0):
+    """K-fused.  x, z (B, L, D) bf16 halves of the in_proj output -> y (B, L, D) bf16 (the out_proj input).
+    xproj_w (2, R+2N, D) bf16, dt_w (2, D, R) bf16.  With ``save`` also returns the pooled intermediates
+    (u (2, B, Lp, D) bf16, xdbl (2, B*Lp, R+2N) bf16, s (2, B, Lp, D) fp32) the backward kernels need."""
+    _check_cuda(x, z, xproj_w, dt_w)
+    B, L, D = x.shape
+    assert L == geom.L and x.dtype == torch.bfloat16 and xproj_w.dtype == torch.bfloat16 and dt_w.dtype == torch.bfloat16
+    ldx, bs = _tokmajor(x, "x")
+    assert _tokmajor(z, "z") == (ldx, bs), "x and z must be the two halves of one in_proj output"
+    assert xproj_w.is_contiguous() and dt_w.is_contiguous()
+    y = torch.empty((B, L, D), device=x.device, dtype=x.dtype)
+    ncols = dt_rank + 2 * d_state
+    u = xdbl = s = None
+    if save:
+        u = torch.empty((2, B, geom.Lp, D), device=x.device, dtype=x.dtype)
+        xdbl = torch.empty((2, B * geom.Lp, ncols), device=x.device, dtype=x.dtype)
+        s = torch.empty((2, B, geom.Lp, D), device=x.device, dtype=torch.float32)
+    g = geom.c_struct(B, D)
+    _lib.call("fv_block_fwd", C.byref(g), FV_BF16, _p(x), _p(z), ldx, bs, _p(conv_w), _p(conv_b), _p(xproj_w), _p(dt_w),
+              _p(dt_bias), _p(A), int(a_is_log), int(dt_rank), int(d_state), _p(Dskip), _p(ln_w), _p(ln_b), float(eps),
+              float(scale), int(exp_mode), _p(y), y.stride(1), y.stride(0), _p(u), _p(xdbl), _p(s), _stream(x))
+    return (y, u, xdbl, s) if save else y
+
+
 def norm_gate_apply(y: Tensor, z: Tensor, stats: Tensor, geom: Geometry, full_dim: int,
                     ln_w: Optional[Tensor], ln_b: Optional[Tensor], eps: float = 1e-5) -> Tensor:
     B, L, D = y.shape

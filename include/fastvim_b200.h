@@ -99,6 +99,31 @@ int fv_norm_gate_apply(const fv_geom* g, int dtype, int full_dim, void* y, int64
                        const float* stats, const float* ln_w, const float* ln_b, float eps,
                        void* stream);
 
+/* ---- K-fused: the whole block interior (K1 + x_proj + dt_proj + K2a + K2b) in one launch ------
+ * Replaces mamba_simple_faster.py:272-453 between the in_proj output and the out_proj input for the
+ * common case: bf16, plain (outer, pool, 1) geometry, mean pooling, d_state 16, dim <= 384, and one
+ * image's (L + 6) x dim bf16 slab + pooled buffers fitting the 227 KB of shared memory of one SM
+ * (224^2 FastVim-T: 196 x 384).  A persistent CTA per SM keeps the image's x resident in shared memory,
+ * so HBM sees x and z once and y once.  fv_block_fwd_supported() returns 1 when the configuration
+ * qualifies; callers use the four-launch path (fv_conv_pool_fwd .. fv_gate_fwd) otherwise.
+ *   x, z       (B, L, dim) bf16 token-major halves of the in_proj output, row stride ldxz
+ *   xproj_w    (2, R+2N, dim) bf16   [x_proj.weight, x_proj_b.weight]
+ *   dt_w       (2, dim, R) bf16      [dt_proj.weight, dt_proj_b.weight]
+ *   conv_w, conv_b, dt_bias, A, Dskip, ln_w, ln_b: fp32 as in the calls above (ln_w NULL => no norm)
+ *   scale      scaling_factor (the mean's 1/pool is applied inside)
+ *   exp_mode   0: fp32 ex2.approx for the decay factors; 1: ex2.approx.f16x2
+ *   y          (B, L, dim) bf16, row stride ldy
+ *   u_out (2, B, Lp, dim) bf16, xdbl_out (2, B*Lp, R+2N) bf16, s_out (2, B, Lp, dim) fp32: optional
+ *              (NULL) copies of the pooled intermediates, saved for the backward kernels.
+ */
+int fv_block_fwd_supported(const fv_geom* g, int dtype, int dt_rank, int dstate);
+int fv_block_fwd(const fv_geom* g, int dtype, const void* x, const void* z, int64_t ldxz,
+                 int64_t xz_bstride, const float* conv_w, const float* conv_b, const void* xproj_w,
+                 const void* dt_w, const float* dt_bias, const float* A, int a_is_log, int dt_rank,
+                 int dstate, const float* Dskip, const float* ln_w, const float* ln_b, float eps,
+                 float scale, int exp_mode, void* y, int64_t ldy, int64_t y_bstride, void* u_out,
+                 void* xdbl_out, float* s_out, void* stream);
+
 /* ---- fused residual add + RMSNorm / LayerNorm (prenorm form) ------------------------
  * Replaces mamba_ssm/ops/triton/layernorm.py:66-121 as used by Block.forward
  * (models/fastvim.py:167-190): residual_out = x + residual (fp32), y = norm(residual_out)*w (+b).

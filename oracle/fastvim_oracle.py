@@ -195,6 +195,30 @@ def mixer_oracle(hidden, p: Dict[str, Tensor], token_size: Sequence[int], *,
     return o
 
 
+def block_interior_oracle(x, z, rows, cols, conv_w, conv_b, x_w, dt_w, dt_b, A_log, Dk, ln_w, ln_b,
+                          eps=1e-5, scaling_factor=1.0):
+    """The block interior alone -- ``mamba_simple_faster.py:269-453`` between the in_proj output and
+    the out_proj input -- from direction-stacked parameters (the layout the fused CUDA kernel takes):
+    x, z (Bt, L, D) token-major; conv_w (2, D, 4), conv_b (2, D), x_w (2, R+2N, D), dt_w (2, D, R),
+    dt_b (2, D), A_log (2, D, N), Dk (2, D), ln_w / ln_b (D) or None.  Returns the gated (Bt, L, D).
+    Implemented as ``mixer_oracle`` with identity in_proj / out_proj."""
+    Dm = x.shape[-1]
+    eye2, eye = torch.eye(2 * Dm, dtype=x.dtype), torch.eye(Dm, dtype=x.dtype)
+    p = {"in_proj.weight": eye2, "out_proj.weight": eye,
+         "conv1d.weight": conv_w[0][:, None, :], "conv1d_b.weight": conv_w[1][:, None, :],
+         "x_proj.weight": x_w[0], "x_proj_b.weight": x_w[1],
+         "dt_proj.weight": dt_w[0], "dt_proj_b.weight": dt_w[1],
+         "dt_proj.bias": dt_b[0], "dt_proj_b.bias": dt_b[1],
+         "A_log": A_log[0], "A_b_log": A_log[1], "D": Dk[0], "D_b": Dk[1]}
+    if conv_b is not None:
+        p["conv1d.bias"], p["conv1d_b.bias"] = conv_b[0], conv_b[1]
+    if ln_w is not None:
+        p["layernorm.weight"] = ln_w
+        p["layernorm.bias"] = ln_b if ln_b is not None else torch.zeros_like(ln_w)
+    return mixer_oracle(torch.cat([x, z], dim=-1), p, (rows, cols), d_state=A_log.shape[-1],
+                        use_norm_after_ssm=ln_w is not None, scaling_factor=scaling_factor, ln_eps=eps)
+
+
 def mamba_inner_oracle(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A,
                        B=None, C=None, D=None, delta_bias=None, delta_softplus=True,
                        has_z=True):

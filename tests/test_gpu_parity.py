@@ -312,3 +312,102 @@ def test_small_model_training_step_grads_fp32():
     for k, v in m.named_parameters():
         assert v.grad is not None, k
         assert_close(v.grad, sd[k].grad, 2e-4, f"d {k}")
+
+
+# ------------------------------------------------------------------ fused one-launch block interior
+def _four_launch(ops, x, z, geom, cw, cb, xw, dtw, dtb, A_log, Dk, lw, lb, sf, R, N):
+    Bt, L, Dm = x.shape
+    u = ops.conv_pool_fwd(x, geom, cw, cb, sf, "mean")
+    xdbl = torch.bmm(u.view(2, Bt * geom.Lp, Dm), xw.transpose(1, 2))
+    s = ops.scan_fwd(u, xdbl, geom, R, N, dtw, dtb, A_log, a_is_log=True)
+    y = ops.gate_fwd(x, z, s, geom, cw, cb, Dk, lw, lb, 1e-5)
+    return y, u, xdbl, s
+
+
+@pytest.mark.parametrize("Bt,rows,cols,Dm,R,rot,norm,sf", [
+    (3, 14, 14, 384, 12, False, True, 1.0),      # FastVim-T 224^2 (unrolled pool-14 path)
+    (3, 14, 14, 384, 12, True, True, 1.0),       # odd layer: rotated geometry
+    (160, 14, 14, 384, 12, False, True, 1.0),    # more images than SMs: persistent loop + next-image refill
+    (301, 4, 6, 64, 4, True, True, 0.5),         # many small images, generic pool path, scaling factor
+    (2, 7, 20, 192, 12, False, True, 1.0),       # non-square grid
+    (2, 3, 128, 192, 12, False, False, 1.0),     # long rows, no LayerNorm (use_norm_after_ssm=False)
+    (2, 14, 14, 256, 8, False, True, 1.0),
+    (2, 33, 5, 96, 24, False, True, 1.0),        # > 16 pooled rows (two MMA row tiles), dt_rank 24
+    (2, 14, 14, 128, 48, True, False, 1.0),      # dt_rank 48 (three k-steps)
+])
+@pytest.mark.parametrize("exp_mode", [0, 1])
+def test_block_fwd_fused_vs_four_launch_and_oracle(Bt, rows, cols, Dm, R, rot, norm, sf, exp_mode):
+    """fv_block_fwd (one launch, x resident in shared memory) against (i) the four-launch path on the same
+    device tensors and (ii) the fp32 CPU oracle of the block interior."""
+    from fastvim_b200 import ops
+
+    if exp_mode == 1 and Bt > 3:
+        pytest.skip("f16x2 exp variant checked on the small cases")
+    torch.manual_seed(0)
+    N, L = 16, rows * cols
+    geom = ops.Geometry.grid(rows, cols, rot)
+    assert ops.block_fwd_supported(geom, Bt, Dm, torch.bfloat16, R, N)
+    xz = torch.randn(Bt, L, 2 * Dm).bfloat16().cuda()
+    x, z = xz[..., :Dm], xz[..., Dm:]
+    cw, cb = (torch.randn(2, Dm, 4) * 0.5).cuda(), (torch.randn(2, Dm) * 0.5).cuda()
+    xw = (torch.randn(2, R + 2 * N, Dm) * Dm ** -0.5).bfloat16().cuda()
+    dtw = (torch.randn(2, Dm, R) * R ** -0.5).bfloat16().cuda()
+    dtb = (torch.rand(2, Dm) * 4.0 - 5.0).cuda()
+    A_log = (torch.log(torch.arange(1, N + 1).float()).repeat(2, Dm, 1) + 0.1 * torch.randn(2, Dm, N)).cuda()
+    Dk = (1.0 + 0.2 * torch.randn(2, Dm)).cuda()
+    lw = (1.0 + 0.2 * torch.randn(Dm)).cuda() if norm else None
+    lb = (0.2 * torch.randn(Dm)).cuda() if norm else None
+    y, u, xdbl, s = ops.block_fwd(x, z, geom, cw, cb, xw, dtw, dtb, A_log, Dk, lw, lb, 1e-5, sf, R, N, True,
+                                  save=True, exp_mode=exp_mode)
+    y2 = ops.block_fwd(x, z, geom, cw, cb, xw, dtw, dtb, A_log, Dk, lw, lb, 1e-5, sf, R, N, True, exp_mode=exp_mode)
+    assert torch.equal(y, y2)  # deterministic; the optional saves do not change the result
+    yr, ur, xdblr, sr = _four_launch(ops, x, z, geom, cw, cb, xw, dtw.float(), dtb, A_log, Dk, lw, lb, sf, R, N)
+    tol = TOL[torch.bfloat16]
+    assert_close(u, ur, tol, "pooled u")
+    assert_close(xdbl, xdblr, tol, "x_dbl")
+    assert_close(s.sum(0), sr.sum(0), tol, "scan output")
+    assert_close(y, yr, tol, "y vs four-launch path")
+    # fp32 oracle of the block interior on the same (bf16-rounded) inputs
+    xs, zs = x.float().cpu(), z.float().cpu()
+    if rot:   # memory grid is (cols, rows) row-major; the mixer sequence is its column-major walk
+        xs = xs.view(Bt, cols, rows, Dm).transpose(1, 2).reshape(Bt, L, Dm)
+        zs = zs.view(Bt, cols, rows, Dm).transpose(1, 2).reshape(Bt, L, Dm)
+    want = O.block_interior_oracle(xs, zs, rows, cols, cw.cpu(), cb.cpu(), xw.float().cpu(), dtw.float().cpu(),
+                                   dtb.cpu(), A_log.cpu(), Dk.cpu(), None if lw is None else lw.cpu(),
+                                   None if lb is None else lb.cpu(), 1e-5, sf)
+    if rot:
+        want = want.view(Bt, rows, cols, Dm).transpose(1, 2).reshape(Bt, L, Dm)
+    assert_close(y, want, tol, "y vs oracle")
+
+
+def test_block_fwd_unsupported_configs_are_refused():
+    from fastvim_b200 import _lib, ops
+
+    g = ops.Geometry.grid(14, 14)
+    assert not ops.block_fwd_supported(g, 2, 384, torch.float32, 12, 16)      # fp32: slab would not fit
+    assert not ops.block_fwd_supported(g, 2, 1536, torch.bfloat16, 48, 16)    # FastVim-B width: four-launch path
+    assert not ops.block_fwd_supported(ops.Geometry.grid(128, 128), 1, 384, torch.bfloat16, 12, 16)   # 2048^2
+    assert not ops.block_fwd_supported(ops.Geometry(14, 14, 8, 14 * 8, 8, 1), 2, 384, torch.bfloat16, 12, 16)  # channel layout
+    x = torch.zeros(1, 128 * 128, 768, dtype=torch.bfloat16, device="cuda")
+    with pytest.raises(_lib.FastVimLibraryError):
+        ops.block_fwd(x[..., :384], x[..., 384:], ops.Geometry.grid(128, 128), torch.zeros(2, 384, 4).cuda(), None,
+                      torch.zeros(2, 44, 384).bfloat16().cuda(), torch.zeros(2, 384, 12).bfloat16().cuda(),
+                      torch.zeros(2, 384).cuda(), torch.zeros(2, 384, 16).cuda(), torch.ones(2, 384).cuda(), None, None,
+                      1e-5, 1.0, 12, 16)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_mixer_bf16_fused_and_four_launch_agree_with_oracle(fused, monkeypatch):
+    from fastvim_b200 import mixer as M
+
+    monkeypatch.setattr(M, "FUSED_BLOCK", fused)
+    p = O.random_mixer_params(192, seed=5)
+    torch.manual_seed(1)
+    h = torch.randn(4, 196, 192)
+    m = _mixer_from_params(p, (14, 14))
+    from fastvim_b200 import _lib
+    _lib.reset_launch_count()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        out = m(h.cuda())
+    assert _lib.launch_count() == (1 if fused else 3)
+    assert_close(out, O.mixer_oracle(h, p, (14, 14)), TOL[torch.bfloat16], "mixer bf16")
