@@ -33,10 +33,15 @@ SIGNATURES = {
     "fv_gate_fwd": [_G, _I, _P, _P, _L, _L, _P, _P, _P, _P, _P, _P, _F, _P, _L, _L, _P, _P],
     "fv_norm_gate_apply": [_G, _I, _I, _P, _L, _L, _P, _L, _L, _P, _P, _P, _F, _P],
     "fv_block_fwd_supported": [_G, _I, _I, _I],
-    "fv_block_fwd": [_G, _I, _P, _P, _L, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _F, _F, _I, _P, _L, _L,
+    "fv_block_pack_xproj_bytes": [_I, _I],
+    "fv_block_pack_xproj": [_I, _I, _P, _P, _P],
+    "fv_block_fwd": [_G, _I, _P, _P, _L, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _F, _F, _P, _L, _L,
                      _P, _P, _P, _P],
     "fv_add_norm_fwd": [_I, _L, _I, _P, _L, _P, _P, _P, _F, _I, _P, _L, _P, _P, _P, _P],
     "fv_selective_scan_fwd": [_I, _I, _I, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P],
+    "fv_causal_conv1d_fwd": [_I, _I, _I, _L, _P, _L, _L, _P, _P, _I, _P, _P],
+    "fv_pool_bdl_fwd": [_I, _I, _I, _I, _I, _I, _P, _I, _F, _P, _P],
+    "fv_bcast_skip_bdl_fwd": [_I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
     "fv_bwd_tiles_per_group": [_G, _I],
     "fv_gate_bwd": [_G, _I, _P, _P, _L, _L, _P, _L, _L, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P],
     "fv_scan_bwd": [_G, _I, _I, _P, _P, _L, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P],
@@ -70,7 +75,7 @@ def lib():
     for name, args in SIGNATURES.items():
         fn = getattr(l, name)
         fn.argtypes = args
-        fn.restype = C.c_int
+        fn.restype = C.c_int64 if name.endswith("_bytes") else C.c_int
     _lib = l
     return l
 

@@ -48,3 +48,102 @@ def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_
         None if delta_bias is None else delta_bias.float().contiguous(), bool(delta_softplus),
         want_last_state=return_last_state)
     return (out, last) if return_last_state else out
+
+
+# --------------------------------------------------------------------------- fused "inner" functions (forward)
+def _no_grad_only(name, *tensors):
+    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
+        raise NotImplementedError(
+            f"fastvim_b200.interface.{name}: forward only.  Training goes through fastvim_b200.mixer.Mamba "
+            "(autograd.MixerFn), which implements the backward of the live module branch")
+
+
+def _inner(x, z, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C, D, delta_bias,
+           B_proj_bias, C_proj_bias, delta_softplus):
+    """conv1d(+SiLU) -> x_proj -> dt_proj -> selective scan (u = conv output, D skip, z gate) on (batch, dim, L)
+    tensors: the forward of MambaInnerFnNoOutProj (selective_scan_interface.py:208-330)."""
+    batch, dim, L = x.shape
+    R, N = delta_proj_weight.shape[1], A.shape[-1]
+    act = x.dtype
+    xc = ops.causal_conv1d_fwd(x, conv1d_weight.reshape(dim, -1), conv1d_bias, True)            # :231-233
+    # x_proj / dt_proj are GEMMs (cuBLAS through torch), in the activation dtype as under autocast (:221-226)
+    x_dbl = torch.nn.functional.linear(xc.transpose(1, 2).reshape(batch * L, dim), x_proj_weight.to(act))   # :237-239
+    delta = (delta_proj_weight.to(act) @ x_dbl[:, :R].t()).reshape(dim, batch, L).permute(1, 0, 2).contiguous()  # :240-243
+    if B is None:
+        B = x_dbl[:, R:R + N]
+        if B_proj_bias is not None:
+            B = B + B_proj_bias.to(B.dtype)
+        B = B.reshape(batch, L, N).transpose(1, 2)[:, None].contiguous()                        # :248-262
+    if C is None:
+        C = x_dbl[:, -N:]
+        if C_proj_bias is not None:
+            C = C + C_proj_bias.to(C.dtype)
+        C = C.reshape(batch, L, N).transpose(1, 2)[:, None].contiguous()                        # :263-277
+    return selective_scan_fn(xc, delta, A, B, C, D, z=z, delta_bias=delta_bias, delta_softplus=delta_softplus)
+
+
+def mamba_inner_fn_no_out_proj(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B=None, C=None,
+                               D=None, delta_bias=None, B_proj_bias=None, C_proj_bias=None, delta_softplus=True):
+    """xz: (batch, 2*dim, L) -> (batch, dim, L).  Reference :1652-1681."""
+    _no_grad_only("mamba_inner_fn_no_out_proj", xz, conv1d_weight, x_proj_weight, delta_proj_weight, A, D)
+    if A.is_complex():
+        raise NotImplementedError("complex A is not used by any FastVim model and is not implemented")
+    if xz.stride(-1) != 1:
+        xz = xz.contiguous()
+    x, z = xz.chunk(2, dim=1)
+    return _inner(x, z.contiguous(), conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C, D,
+                  delta_bias, B_proj_bias, C_proj_bias, delta_softplus)
+
+
+def mamba_inner_fn_no_out_proj_withoutZ(x, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B=None,
+                                        C=None, D=None, delta_bias=None, B_proj_bias=None, C_proj_bias=None,
+                                        delta_softplus=True):
+    """x: (batch, dim, L) -> (batch, dim, L), no z gate.  Reference :1684-1713."""
+    _no_grad_only("mamba_inner_fn_no_out_proj_withoutZ", x, conv1d_weight, x_proj_weight, delta_proj_weight, A, D)
+    if A.is_complex():
+        raise NotImplementedError("complex A is not used by any FastVim model and is not implemented")
+    if x.stride(-1) != 1:
+        x = x.contiguous()
+    return _inner(x, None, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C, D, delta_bias,
+                  B_proj_bias, C_proj_bias, delta_softplus)
+
+
+def FastVim_mamba_inner_fn_no_out_proj_withoutZ(x, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A,
+                                                B=None, C=None, D=None, delta_bias=None, B_proj_bias=None,
+                                                C_proj_bias=None, delta_softplus=True, num_of_col=14,
+                                                collapse_method="mean", scaling_factor=1, pre_x_shape=None):
+    """x: (batch, dim, L) -> (batch, dim, L): conv -> mean over ``num_of_col`` -> x_proj / dt_proj -> scan over the
+    pooled sequence -> repeat_interleave + D * conv.  Reference :1716-1753, forward :452-603.  As in the reference
+    (:503-508) only ``collapse_method="mean"`` is defined for this function."""
+    _no_grad_only("FastVim_mamba_inner_fn_no_out_proj_withoutZ", x, conv1d_weight, x_proj_weight, delta_proj_weight, A, D)
+    if A.is_complex():
+        raise NotImplementedError("complex A is not used by any FastVim model and is not implemented")
+    if collapse_method != "mean":
+        raise NotImplementedError("FastVim_mamba_inner_fn_no_out_proj_withoutZ defines collapse_method='mean' only "
+                                  "(reference selective_scan_interface.py:503-508)")
+    if B is not None or C is not None:
+        raise NotImplementedError("input-independent B / C are not used by FastVim and are not implemented here")
+    if x.stride(-1) != 1:
+        x = x.contiguous()
+    batch, dim, L = x.shape
+    if pre_x_shape is not None and int(pre_x_shape[-1]) != int(num_of_col):
+        raise ValueError(f"pre_x_shape {tuple(pre_x_shape)} does not end with num_of_col={num_of_col}")
+    if L % num_of_col:
+        raise ValueError(f"seqlen {L} is not a multiple of num_of_col {num_of_col}")
+    rows = L // num_of_col
+    R, N = delta_proj_weight.shape[1], A.shape[-1]
+    act = x.dtype
+    xc = ops.causal_conv1d_fwd(x, conv1d_weight.reshape(dim, -1), conv1d_bias, True)            # :496-498
+    u = ops.pool_bdl_fwd(xc, rows, num_of_col, 1, "mean", float(scaling_factor))                # :503-508
+    x_dbl = torch.nn.functional.linear(u.transpose(1, 2).reshape(batch * rows, dim), x_proj_weight.to(act))  # :512-514
+    delta = (delta_proj_weight.to(act) @ x_dbl[:, :R].t()).reshape(dim, batch, rows).permute(1, 0, 2).contiguous()
+    Bm = x_dbl[:, R:R + N]
+    Cm = x_dbl[:, -N:]
+    if B_proj_bias is not None:
+        Bm = Bm + B_proj_bias.to(Bm.dtype)
+    if C_proj_bias is not None:
+        Cm = Cm + C_proj_bias.to(Cm.dtype)
+    Bm = Bm.reshape(batch, rows, N).transpose(1, 2)[:, None].contiguous()
+    Cm = Cm.reshape(batch, rows, N).transpose(1, 2)[:, None].contiguous()
+    s = selective_scan_fn(u, delta, A, Bm, Cm, None, None, delta_bias, delta_softplus)          # :556-566
+    return ops.bcast_skip_bdl_fwd(s, xc, D, rows, num_of_col, 1)                                # :570-571

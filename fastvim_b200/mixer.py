@@ -34,7 +34,6 @@ from .ops import Geometry
 # four-launch path (K1 -> x_proj -> K2a -> K2b) covers everything else (fp32, long sequences, channel
 # layouts, max pooling).  Module-level switches so tests and tools/kbench.py can compare the two.
 FUSED_BLOCK = os.environ.get("FASTVIM_FUSED_BLOCK", "1") != "0"
-FUSED_EXP_MODE = int(os.environ.get("FASTVIM_FUSED_EXP_MODE", "0"))
 
 
 class Mamba(nn.Module):
@@ -120,7 +119,6 @@ class Mamba(nn.Module):
                 torch.stack([self.conv1d.bias, self.conv1d_b.bias]).to(f32).contiguous(),
                 "x_w_t": torch.stack([self.x_proj.weight.t(), self.x_proj_b.weight.t()]).to(act_dtype).contiguous(),
                 "x_w": torch.stack([self.x_proj.weight, self.x_proj_b.weight]).to(act_dtype).contiguous(),
-                "dt_w_act": torch.stack([self.dt_proj.weight, self.dt_proj_b.weight]).to(act_dtype).contiguous(),
                 "dt_w": torch.stack([self.dt_proj.weight, self.dt_proj_b.weight]).to(f32).contiguous(),
                 "dt_b": torch.stack([self.dt_proj.bias, self.dt_proj_b.bias]).to(f32).contiguous(),
                 "A_log": torch.stack([self.A_log, self.A_b_log]).to(f32).contiguous(),
@@ -132,6 +130,8 @@ class Mamba(nn.Module):
                 "ln_w": self.layernorm.weight.to(f32).contiguous() if self.use_norm_after_ssm else None,
                 "ln_b": self.layernorm.bias.to(f32).contiguous() if self.use_norm_after_ssm else None,
             }
+            if act_dtype == torch.bfloat16 and pk["x_w"].is_cuda:
+                pk["x_w_packed"] = ops.block_pack_xproj(pk["x_w"])   # fragment order for the fused block kernel
         self._pack_cache = {"k": key, "v": pk}
         return pk
 
@@ -165,9 +165,9 @@ class Mamba(nn.Module):
         if (FUSED_BLOCK and self.collapse_method == "mean"
                 and ops.block_fwd_supported(geom, B, D, xz.dtype, R, N)):
             # one launch for [a3-a9]: the image's x stays resident in shared memory (csrc/block_fwd.cu)
-            y = ops.block_fwd(x, z, geom, pk["conv_w"], pk["conv_b"], pk["x_w"], pk["dt_w_act"], pk["dt_b"],
+            y = ops.block_fwd(x, z, geom, pk["conv_w"], pk["conv_b"], pk["x_w"], pk["dt_w"], pk["dt_b"],
                               pk["A_log"], pk["D"], pk["ln_w"], pk["ln_b"], eps, float(self.scaling_factor), R, N,
-                              a_is_log=True, exp_mode=FUSED_EXP_MODE)
+                              a_is_log=True, xproj_w_packed=pk.get("x_w_packed"))
             return F.linear(y, pk["out_w"], pk["out_b"])                 # [a10]
         u = ops.conv_pool_fwd(x, geom, pk["conv_w"], pk["conv_b"], float(self.scaling_factor),
                               self.collapse_method)                      # (2, B, Lp, D)         [a3-a5]

@@ -141,19 +141,34 @@ def block_fwd_supported(geom: Geometry, batch: int, dim: int, dtype: torch.dtype
     return bool(_lib.lib().fv_block_fwd_supported(C.byref(g), FV_BF16, int(dt_rank), int(d_state)))
 
 
+def block_pack_xproj(xproj_w: Tensor) -> Optional[Tensor]:
+    """(2, R+2N, D) bf16 x_proj weights -> MMA-fragment order for ``block_fwd`` (None when D % 64 != 0)."""
+    _check_cuda(xproj_w)
+    _, ncols, D = xproj_w.shape
+    nbytes = int(_lib.lib().fv_block_pack_xproj_bytes(D, ncols))
+    if nbytes == 0:
+        return None
+    assert xproj_w.dtype == torch.bfloat16 and xproj_w.is_contiguous()
+    packed = torch.empty(nbytes, device=xproj_w.device, dtype=torch.uint8)
+    _lib.call("fv_block_pack_xproj", D, ncols, _p(xproj_w), _p(packed), _stream(xproj_w))
+    return packed
+
+
 def block_fwd(x: Tensor, z: Tensor, geom: Geometry, conv_w: Tensor, conv_b: Optional[Tensor], xproj_w: Tensor,
               dt_w: Tensor, dt_bias: Tensor, A: Tensor, Dskip: Tensor, ln_w: Optional[Tensor], ln_b: Optional[Tensor],
               eps: float, scale: float, dt_rank: int, d_state: int, a_is_log: bool = True, save: bool = False,
-              exp_mode: int = 0):
+              xproj_w_packed: Optional[Tensor] = None):
     """K-fused.  x, z (B, L, D) bf16 halves of the in_proj output -> y (B, L, D) bf16 (the out_proj input).
-    xproj_w (2, R+2N, D) bf16, dt_w (2, D, R) bf16.  With ``save`` also returns the pooled intermediates
+    xproj_w (2, R+2N, D) bf16, dt_w (2, D, R) fp32.  With ``save`` also returns the pooled intermediates
     (u (2, B, Lp, D) bf16, xdbl (2, B*Lp, R+2N) bf16, s (2, B, Lp, D) fp32) the backward kernels need."""
     _check_cuda(x, z, xproj_w, dt_w)
     B, L, D = x.shape
-    assert L == geom.L and x.dtype == torch.bfloat16 and xproj_w.dtype == torch.bfloat16 and dt_w.dtype == torch.bfloat16
+    assert L == geom.L and x.dtype == torch.bfloat16 and xproj_w.dtype == torch.bfloat16 and dt_w.dtype == torch.float32
     ldx, bs = _tokmajor(x, "x")
     assert _tokmajor(z, "z") == (ldx, bs), "x and z must be the two halves of one in_proj output"
     assert xproj_w.is_contiguous() and dt_w.is_contiguous()
+    if xproj_w_packed is None:
+        xproj_w_packed = block_pack_xproj(xproj_w)
     y = torch.empty((B, L, D), device=x.device, dtype=x.dtype)
     ncols = dt_rank + 2 * d_state
     u = xdbl = s = None
@@ -162,9 +177,9 @@ def block_fwd(x: Tensor, z: Tensor, geom: Geometry, conv_w: Tensor, conv_b: Opti
         xdbl = torch.empty((2, B * geom.Lp, ncols), device=x.device, dtype=x.dtype)
         s = torch.empty((2, B, geom.Lp, D), device=x.device, dtype=torch.float32)
     g = geom.c_struct(B, D)
-    _lib.call("fv_block_fwd", C.byref(g), FV_BF16, _p(x), _p(z), ldx, bs, _p(conv_w), _p(conv_b), _p(xproj_w), _p(dt_w),
-              _p(dt_bias), _p(A), int(a_is_log), int(dt_rank), int(d_state), _p(Dskip), _p(ln_w), _p(ln_b), float(eps),
-              float(scale), int(exp_mode), _p(y), y.stride(1), y.stride(0), _p(u), _p(xdbl), _p(s), _stream(x))
+    _lib.call("fv_block_fwd", C.byref(g), FV_BF16, _p(x), _p(z), ldx, bs, _p(conv_w), _p(conv_b), _p(xproj_w), _p(xproj_w_packed),
+              _p(dt_w), _p(dt_bias), _p(A), int(a_is_log), int(dt_rank), int(d_state), _p(Dskip), _p(ln_w), _p(ln_b), float(eps),
+              float(scale), _p(y), y.stride(1), y.stride(0), _p(u), _p(xdbl), _p(s), _stream(x))
     return (y, u, xdbl, s) if save else y
 
 
@@ -216,6 +231,41 @@ def selective_scan_fwd(u: Tensor, delta: Tensor, A: Tensor, B: Tensor, Cm: Tenso
     _lib.call("fv_selective_scan_fwd", _dt(u), batch, dim, L, N, groups, _p(u), _p(delta), _p(A), _p(B), _p(Cm),
               _p(D), _p(z), _p(delta_bias), int(delta_softplus), _p(out), _p(last), _stream(u))
     return out, last
+
+
+# --------------------------------------------------------------------------- (B, D, L) operator-API helpers
+def causal_conv1d_fwd(x: Tensor, weight: Tensor, bias: Optional[Tensor], silu: bool = True) -> Tensor:
+    """x (B, D, L) with unit stride along L (any batch / channel strides), weight (D, 4) -> (B, D, L) contiguous."""
+    _check_cuda(x, weight)
+    B, D, L = x.shape
+    assert x.stride(2) == 1 and weight.shape == (D, 4)
+    out = torch.empty((B, D, L), device=x.device, dtype=x.dtype)
+    _lib.call("fv_causal_conv1d_fwd", _dt(x), B, D, L, _p(x), x.stride(0), x.stride(1), _p(_f32c(weight)),
+              _p(_f32c(bias)), int(silu), _p(out), _stream(x))
+    return out
+
+
+def pool_bdl_fwd(xc: Tensor, outer: int, pool: int, inner: int = 1, mode: str = "mean", scale: float = 1.0) -> Tensor:
+    """(B, D, outer*pool*inner) contiguous -> (B, D, outer*inner): mean * scale, or max, over the pool axis."""
+    _check_cuda(xc)
+    B, D, L = xc.shape
+    assert L == outer * pool * inner and xc.is_contiguous()
+    out = torch.empty((B, D, outer * inner), device=xc.device, dtype=xc.dtype)
+    _lib.call("fv_pool_bdl_fwd", _dt(xc), B, D, outer, pool, inner, _p(xc), FV_POOL_MAX if mode == "max" else FV_POOL_MEAN,
+              float(scale), _p(out), _stream(xc))
+    return out
+
+
+def bcast_skip_bdl_fwd(s: Tensor, xc: Optional[Tensor], Dskip: Optional[Tensor], outer: int, pool: int,
+                       inner: int = 1) -> Tensor:
+    """out[b, d, t] = s[b, d, pool_index(t)] + D[d] * xc[b, d, t]; s (B, D, outer*inner), xc (B, D, L) contiguous."""
+    _check_cuda(s, xc)
+    B, D, Lp = s.shape
+    assert Lp == outer * inner and s.is_contiguous() and (xc is None or xc.is_contiguous())
+    out = torch.empty((B, D, outer * pool * inner), device=s.device, dtype=s.dtype)
+    _lib.call("fv_bcast_skip_bdl_fwd", _dt(s), B, D, outer, pool, inner, _p(s), _p(xc), _p(_f32c(Dskip)), _p(out),
+              _stream(s))
+    return out
 
 
 # --------------------------------------------------------------------------- backward wrappers

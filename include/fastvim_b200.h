@@ -101,27 +101,31 @@ int fv_norm_gate_apply(const fv_geom* g, int dtype, int full_dim, void* y, int64
 
 /* ---- K-fused: the whole block interior (K1 + x_proj + dt_proj + K2a + K2b) in one launch ------
  * Replaces mamba_simple_faster.py:272-453 between the in_proj output and the out_proj input for the
- * common case: bf16, plain (outer, pool, 1) geometry, mean pooling, d_state 16, dim <= 384, and one
+ * common case: bf16, plain (outer, pool, 1) geometry, mean pooling, d_state 16, dt_rank <= 16, dim <= 384, and one
  * image's (L + 6) x dim bf16 slab + pooled buffers fitting the 227 KB of shared memory of one SM
  * (224^2 FastVim-T: 196 x 384).  A persistent CTA per SM keeps the image's x resident in shared memory,
  * so HBM sees x and z once and y once.  fv_block_fwd_supported() returns 1 when the configuration
  * qualifies; callers use the four-launch path (fv_conv_pool_fwd .. fv_gate_fwd) otherwise.
  *   x, z       (B, L, dim) bf16 token-major halves of the in_proj output, row stride ldxz
  *   xproj_w    (2, R+2N, dim) bf16   [x_proj.weight, x_proj_b.weight]
- *   dt_w       (2, dim, R) bf16      [dt_proj.weight, dt_proj_b.weight]
+ *   xproj_w_packed  the same weights in MMA-fragment order, produced once per weight version by
+ *              fv_block_pack_xproj into fv_block_pack_xproj_bytes(dim, R+2N) bytes (dim % 64 == 0); NULL =>
+ *              the kernel gathers fragments from xproj_w (slower: 24 scattered 4-byte loads per lane)
+ *   dt_w       (2, dim, R) fp32      [dt_proj.weight, dt_proj_b.weight]; R in {4, 8, 12, 16}
  *   conv_w, conv_b, dt_bias, A, Dskip, ln_w, ln_b: fp32 as in the calls above (ln_w NULL => no norm)
  *   scale      scaling_factor (the mean's 1/pool is applied inside)
- *   exp_mode   0: fp32 ex2.approx for the decay factors; 1: ex2.approx.f16x2
  *   y          (B, L, dim) bf16, row stride ldy
  *   u_out (2, B, Lp, dim) bf16, xdbl_out (2, B*Lp, R+2N) bf16, s_out (2, B, Lp, dim) fp32: optional
  *              (NULL) copies of the pooled intermediates, saved for the backward kernels.
  */
 int fv_block_fwd_supported(const fv_geom* g, int dtype, int dt_rank, int dstate);
+int64_t fv_block_pack_xproj_bytes(int dim, int ncols);
+int fv_block_pack_xproj(int dim, int ncols, const void* xproj_w, void* packed, void* stream);
 int fv_block_fwd(const fv_geom* g, int dtype, const void* x, const void* z, int64_t ldxz,
                  int64_t xz_bstride, const float* conv_w, const float* conv_b, const void* xproj_w,
-                 const void* dt_w, const float* dt_bias, const float* A, int a_is_log, int dt_rank,
+                 const void* xproj_w_packed, const float* dt_w, const float* dt_bias, const float* A, int a_is_log, int dt_rank,
                  int dstate, const float* Dskip, const float* ln_w, const float* ln_b, float eps,
-                 float scale, int exp_mode, void* y, int64_t ldy, int64_t y_bstride, void* u_out,
+                 float scale, void* y, int64_t ldy, int64_t y_bstride, void* u_out,
                  void* xdbl_out, float* s_out, void* stream);
 
 /* ---- fused residual add + RMSNorm / LayerNorm (prenorm form) ------------------------
@@ -145,6 +149,22 @@ int fv_selective_scan_fwd(int dtype, int batch, int dim, int64_t L, int dstate, 
                           const void* C, const float* D, const void* z, const float* delta_bias,
                           int delta_softplus, void* out, float* last_state, void* stream);
 
+
+/* ---- operator API helpers on (batch, dim, L), L contiguous ---------------------------------
+ * The reference's fused autograd functions (selective_scan_interface.py:208-330, 452-605) call, on
+ * (B, D, L) tensors: causal_conv1d_cuda.causal_conv1d_fwd(x, w, bias, None, True) (:496-498; third-party
+ * causal-conv1d 1.1.3), conv1d_out.reshape(pre_x_shape).mean(3) (:503-508), selective_scan_cuda.fwd, and
+ * out.repeat_interleave(num_of_col, 2) + D * conv1d_out (:570-571).  These serve that API in the same layout.
+ *   x (batch, dim, L) with strides (x_bstride, x_dstride, 1); w (dim, 4) fp32; bias (dim) fp32 or NULL
+ *   out, xc (batch, dim, L) contiguous; pooled tensors (batch, dim, outer*inner) contiguous
+ */
+int fv_causal_conv1d_fwd(int dtype, int batch, int dim, int64_t L, const void* x, int64_t x_bstride,
+                         int64_t x_dstride, const float* w, const float* bias, int silu, void* out,
+                         void* stream);
+int fv_pool_bdl_fwd(int dtype, int batch, int dim, int outer, int pool, int inner, const void* x,
+                    int pool_mode, float scale, void* out, void* stream);
+int fv_bcast_skip_bdl_fwd(int dtype, int batch, int dim, int outer, int pool, int inner, const void* s,
+                          const void* xc, const float* Dskip, void* out, void* stream);
 
 /* ======================= backward (training) entry points ==============================
  * Replace SelectiveScanFn.backward / selective_scan_cuda.bwd (selective_scan_interface.py:59-102,

@@ -101,11 +101,11 @@ def main():
         rep("gate_fwd", t, 3 * Bt * L * D * s + 2 * Bt * Lp * D * 4)
     if (not only or "block" in only) and ops.block_fwd_supported(geom, Bt, D, dt, R, N):
         xw = (torch.randn(2, R + 2 * N, D, device=dev) * D ** -0.5).to(dt)
-        dtwa = dt_w.to(dt)
-        for em in (0, 1):
-            t = timeit(lambda i: ops.block_fwd(xz[i][..., :D], xz[i][..., D:], geom, cw, cb, xw, dtwa, dt_b, A_log, Dk,
-                                               lw, lb, 1e-5, 1.0, R, N, True, exp_mode=em), nrot, a.iters)
-            rep("block_fwd(exp_mode=%d)" % em, t, 3 * Bt * L * D * s)
+        dtwa = dt_w
+        xwp = ops.block_pack_xproj(xw)
+        t = timeit(lambda i: ops.block_fwd(xz[i][..., :D], xz[i][..., D:], geom, cw, cb, xw, dtwa, dt_b, A_log, Dk,
+                                           lw, lb, 1e-5, 1.0, R, N, True, xproj_w_packed=xwp), nrot, a.iters)
+        rep("block_fwd", t, 3 * Bt * L * D * s)
     if not only or "add_norm" in only:
         t = timeit(lambda i: ops.add_norm_fwd(hs[i], res[i], nw, None, 1e-5, True), nrot, a.iters)
         rep("add_norm_fwd", t, Bt * L * dm * (s + 4) * 2)
