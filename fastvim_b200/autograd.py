@@ -26,7 +26,7 @@ class MixerFn(torch.autograd.Function):
         D = conv_w.shape[1]
         from . import mixer as _mixer
 
-        xz = F.linear(h, in_w, in_b)
+        xz = _mixer.linear(h, in_w, in_b)
         x, z = xz[..., :D], xz[..., D:]
         if _mixer.FUSED_BLOCK and ops.block_fwd_supported(geom, B, D, xz.dtype, dt_rank, d_state):
             y, u, xdbl, s = ops.block_fwd(x, z, geom, conv_w, conv_b, x_w.contiguous(), dt_w.contiguous(),
@@ -37,7 +37,7 @@ class MixerFn(torch.autograd.Function):
             xdbl = torch.bmm(u.view(2, B * geom.Lp, D), x_w.transpose(1, 2))
             s = ops.scan_fwd(u, xdbl, geom, dt_rank, d_state, dt_w, dt_b, A_log, a_is_log=True)
             y = ops.gate_fwd(x, z, s, geom, conv_w, conv_b, Dk, ln_w, ln_b, eps)
-        out = F.linear(y, out_w, out_b)
+        out = _mixer.linear(y, out_w, out_b)
         ctx.save_for_backward(h, in_w, conv_w, conv_b, x_w, dt_w, dt_b, A_log, Dk, ln_w, ln_b, out_w, xz, u, xdbl, s, y)
         ctx.meta = (geom, scale, eps, d_state, dt_rank, in_b is not None, out_b is not None)
         return out

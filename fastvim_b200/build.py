@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 sys.stderr.write(log)
     if force or _stale(LIB, objs):
         r = subprocess.run(["nvcc", "-shared", "-o", LIB] + objs +
-                           ["-gencode", "arch=compute_100a,code=sm_100a", "-lcuda"],
+                           ["-gencode", "arch=compute_100a,code=sm_100a"],
                            capture_output=True, text=True)
         if r.returncode:
             raise RuntimeError(f"link failed:\n{r.stderr[-4000:]}")

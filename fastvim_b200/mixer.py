@@ -34,6 +34,19 @@ from .ops import Geometry
 # four-launch path (K1 -> x_proj -> K2a -> K2b) covers everything else (fp32, long sequences, channel
 # layouts, max pooling).  Module-level switches so tests and tools/kbench.py can compare the two.
 FUSED_BLOCK = os.environ.get("FASTVIM_FUSED_BLOCK", "1") != "0"
+# in_proj / out_proj on the hand-written tcgen05 / TMEM / TMA GEMM (csrc/gemm_tc.cu) when the shape qualifies
+# (bf16, no bias, K % 64 == 0, N % 64 == 0, weight block fits shared memory); cuBLAS through F.linear otherwise.
+TC_GEMM = os.environ.get("FASTVIM_TC_GEMM", "1") != "0"
+
+
+def linear(x, w, b):
+    """y = x @ w.T (+ b).  x (..., K), w (N, K)."""
+    if (TC_GEMM and b is None and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.is_cuda
+            and x.stride(-1) == 1 and ops.gemm_supported(x.numel() // x.shape[-1], w.shape[0], w.shape[1])):
+        x2 = x.reshape(-1, x.shape[-1])
+        if x2.stride(0) % 8 == 0 and x2.data_ptr() % 16 == 0 and w.is_contiguous():
+            return ops.gemm_bf16_tn(x2, w).view(*x.shape[:-1], w.shape[0])
+    return F.linear(x, w, b)
 
 
 class Mamba(nn.Module):
@@ -159,7 +172,7 @@ class Mamba(nn.Module):
         pk = self._packed(act_dtype)
         B, L, _ = h.shape
         D, R, N = self.d_inner, self.dt_rank, self.d_state
-        xz = F.linear(h, pk["in_w"], pk["in_b"])                        # (B, L, 2D) token-major  [a2]
+        xz = linear(h, pk["in_w"], pk["in_b"])                          # (B, L, 2D) token-major  [a2]
         x, z = xz[..., :D], xz[..., D:]
         eps = self.layernorm.eps if self.use_norm_after_ssm else 1e-5
         if (FUSED_BLOCK and self.collapse_method == "mean"
@@ -168,11 +181,11 @@ class Mamba(nn.Module):
             y = ops.block_fwd(x, z, geom, pk["conv_w"], pk["conv_b"], pk["x_w"], pk["dt_w"], pk["dt_b"],
                               pk["A_log"], pk["D"], pk["ln_w"], pk["ln_b"], eps, float(self.scaling_factor), R, N,
                               a_is_log=True, xproj_w_packed=pk.get("x_w_packed"))
-            return F.linear(y, pk["out_w"], pk["out_b"])                 # [a10]
+            return linear(y, pk["out_w"], pk["out_b"])                   # [a10]
         u = ops.conv_pool_fwd(x, geom, pk["conv_w"], pk["conv_b"], float(self.scaling_factor),
                               self.collapse_method)                      # (2, B, Lp, D)         [a3-a5]
         xdbl = torch.bmm(u.view(2, B * geom.Lp, D), pk["x_w_t"])         # (2, B*Lp, R+2N)        [a6]
         s = ops.scan_fwd(u, xdbl, geom, R, N, pk["dt_w"], pk["dt_b"], pk["A_log"], a_is_log=True)  # [a6-a7]
         y = ops.gate_fwd(x, z, s, geom, pk["conv_w"], pk["conv_b"], pk["D"], pk["ln_w"], pk["ln_b"],
                          self.layernorm.eps if self.use_norm_after_ssm else 1e-5)             # [a8-a9]
-        return F.linear(y, pk["out_w"], pk["out_b"])                     # [a10]
+        return linear(y, pk["out_w"], pk["out_b"])                       # [a10]

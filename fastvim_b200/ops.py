@@ -233,6 +233,26 @@ def selective_scan_fwd(u: Tensor, delta: Tensor, A: Tensor, B: Tensor, Cm: Tenso
     return out, last
 
 
+# --------------------------------------------------------------------------- tcgen05 GEMMs
+def gemm_supported(M: int, N: int, K: int) -> bool:
+    """Shapes the tcgen05 GEMM handles (K % 64 == 0, N % 64 == 0, the CTA's W block fits shared memory)."""
+    return bool(_lib.lib().fv_gemm_supported(int(M), int(N), int(K)))
+
+
+def gemm_bf16_tn(a: Tensor, w: Tensor, out: Optional[Tensor] = None) -> Tensor:
+    """a (..., K) bf16, w (N, K) bf16 -> (..., N) bf16 = a @ w.T on the tcgen05 tensor cores (fp32 accumulate)."""
+    _check_cuda(a, w)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.dim() == 2 and w.stride(1) == 1
+    K = a.shape[-1]
+    a2 = a.reshape(-1, K)
+    if a2.stride(1) != 1:
+        a2 = a2.contiguous()
+    M, N = a2.shape[0], w.shape[0]
+    c = out if out is not None else torch.empty((M, N), device=a.device, dtype=a.dtype)
+    _lib.call("fv_gemm_bf16_tn", M, N, K, _p(a2), a2.stride(0), _p(w), w.stride(0), _p(c), c.stride(0), _stream(a))
+    return c.reshape(*a.shape[:-1], N)
+
+
 # --------------------------------------------------------------------------- (B, D, L) operator-API helpers
 def causal_conv1d_fwd(x: Tensor, weight: Tensor, bias: Optional[Tensor], silu: bool = True) -> Tensor:
     """x (B, D, L) with unit stride along L (any batch / channel strides), weight (D, 4) -> (B, D, L) contiguous."""

@@ -116,6 +116,12 @@ def main():
         rep("in_proj(cublas)", t, Bt * L * (dm + 2 * D) * s)
         t = timeit(lambda i: torch.nn.functional.linear(y[i], w_out), nrot, a.iters)
         rep("out_proj(cublas)", t, Bt * L * (dm + D) * s)
+        if dt == torch.bfloat16 and ops.gemm_supported(Bt * L, 2 * D, dm) and ops.gemm_supported(Bt * L, dm, D):
+            xzo = [torch.empty(Bt, L, 2 * D, device=dev, dtype=dt) for _ in range(nrot)]
+            t = timeit(lambda i: ops.gemm_bf16_tn(hs[i], w_in, out=xzo[i].view(Bt * L, 2 * D)), nrot, a.iters)
+            rep("in_proj(tcgen05)", t, Bt * L * (dm + 2 * D) * s)
+            t = timeit(lambda i: ops.gemm_bf16_tn(y[i], w_out), nrot, a.iters)
+            rep("out_proj(tcgen05)", t, Bt * L * (dm + D) * s)
 
 
 if __name__ == "__main__":
