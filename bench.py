@@ -112,8 +112,11 @@ def algorithmic_bytes(name: str, B: int, L: int, Lp: int, D: int, d_model: int, 
         return 3 * B * L * D * s + B * Lp * D * 4
     if name == "fv_add_norm_fwd":       # read x (+ fp32 residual), write y + fp32 residual
         return B * L * d_model * (s + 4) * 2
-    if name == "fv_block_fwd":          # fused conv+pool+x_proj+scan+gate: x, z read twice is NOT algorithmic
+    if name == "fv_block_fwd":          # fused conv+pool+x_proj+scan+gate: x, z read once, y written once
         return 3 * B * L * D * s
+    if name.startswith("fv_gemm_bf16_tn["):   # A read, W read, C written (bf16)
+        M, N, K = (int(v) for v in name[name.index("[") + 1:-1].split("x"))
+        return (M * K + N * K + M * N) * 2
     return 0
 
 

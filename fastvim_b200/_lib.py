@@ -101,7 +101,10 @@ def call(name: str, *args) -> None:
         e0.record()
         rc = getattr(l, name)(*args)
         e1.record()
-        _profile.append((name, e0, e1))
+        tag = name
+        if name == "fv_gemm_bf16_tn":   # several GEMM shapes share one entry point: tag the record with (M, N, K)
+            tag = "fv_gemm_bf16_tn[%dx%dx%d]" % (int(args[0]), int(args[1]), int(args[2]))
+        _profile.append((tag, e0, e1))
     else:
         rc = getattr(l, name)(*args)
     if rc != 0:
