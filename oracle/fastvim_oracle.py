@@ -134,7 +134,7 @@ def broadcast_oracle(s, outer, pool, inner=1):
 def mixer_oracle(hidden, p: Dict[str, Tensor], token_size: Sequence[int], *,
                  d_state=16, dt_rank=None, use_norm_after_ssm=True,
                  collapse_method="mean", scaling_factor=1.0, ln_eps=1e-5,
-                 return_intermediates=False):
+                 return_intermediates=False, layout=None):
     """FastVim ``Mamba.forward`` live branch, ``mamba_simple_faster.py:181-457``
     (the branch every shipped config takes, ``use_fast_path=False``, :269-453).
 
@@ -146,7 +146,12 @@ def mixer_oracle(hidden, p: Dict[str, Tensor], token_size: Sequence[int], *,
     """
     Bt, L, _ = hidden.shape
     rows, cols = token_size
-    assert L == rows * cols
+    # ``layout`` = (outer, pool, inner) generalises the pooling to the ChannelVim variants
+    # (mamba_simple_channel_faster.py:225-256, 325-340): Channel-First (rows, cols, tpp), Spatial-First
+    # (tpp*rows, cols, 1).  Default: FastVim (rows, cols, 1).  Below, ``rows`` = pooled length, ``cols`` = pool.
+    outer, pool, inner = layout if layout is not None else (rows, cols, 1)
+    assert L == outer * pool * inner
+    rows, cols = outer * inner, pool
     D2 = p["in_proj.weight"].shape[0]
     Dm = D2 // 2
     R = dt_rank if dt_rank is not None else p["dt_proj.weight"].shape[1]
@@ -159,8 +164,8 @@ def mixer_oracle(hidden, p: Dict[str, Tensor], token_size: Sequence[int], *,
     x_flip = x.flip([-1])                                    # :272
     xc = causal_conv1d_oracle(x, p["conv1d.weight"][:, 0], p.get("conv1d.bias"))            # :274-279
     xc_b = causal_conv1d_oracle(x_flip, p["conv1d_b.weight"][:, 0], p.get("conv1d_b.bias"))  # :280-285
-    u = pool_oracle(xc, rows, cols, 1, collapse_method, scaling_factor)      # :287-305
-    u_b = pool_oracle(xc_b, rows, cols, 1, collapse_method, scaling_factor)
+    u = pool_oracle(xc, outer, pool, inner, collapse_method, scaling_factor)      # :287-305
+    u_b = pool_oracle(xc_b, outer, pool, inner, collapse_method, scaling_factor)
 
     inter = {}
 
@@ -174,7 +179,7 @@ def mixer_oracle(hidden, p: Dict[str, Tensor], token_size: Sequence[int], *,
                                   delta_bias=p[f"dt_proj{tag}.bias"].float(), delta_softplus=True,
                                   compute_dtype=hidden.dtype if hidden.dtype == torch.float64
                                   else torch.float32)                                            # :343-354
-        y = broadcast_oracle(s, rows, cols, 1)                                                   # :356
+        y = broadcast_oracle(s, outer, pool, inner)                                              # :356
         y = y + p["D" + tag].float().to(y.dtype)[None, :, None] * xc_full                        # :358
         if return_intermediates:
             inter[f"x_dbl{tag}"], inter[f"scan{tag}"] = x_dbl, s

@@ -139,6 +139,26 @@ def main():
                         scaling_factor=sf, dout=g, out=out.detach(), dhidden=h.grad, grads=grads),
              oracle_vs_ref=max(errs.values()))
 
+    print("[3b] FastChannelVim mixer (mamba_simple_channel_faster.py:176-420), both scan orders")
+    for name, d_model, ts, tpp, order in (("cmixer_d32_4x6_t3_channel_first", 32, (4, 6), 3, "Channel-First"),
+                                          ("cmixer_d32_6x4_t2_spatial_first", 32, (6, 4), 2, "Spatial-First")):
+        torch.manual_seed(0)
+        m = ref.mscf.Mamba(d_model, token_size=list(ts), layer_idx=0, scan_order=order)
+        with torch.no_grad():
+            for k, v in m.named_parameters():
+                if k in ("D", "D_b", "layernorm.weight", "A_log", "A_b_log", "layernorm.bias"):
+                    v.add_(0.1 * torch.randn_like(v))
+        h = torch.randn(2, ts[0] * ts[1] * tpp, d_model)
+        with torch.no_grad():
+            out = m(h, tpp)
+        params = {k: v.detach().clone() for k, v in m.named_parameters()}
+        layout = (ts[0], ts[1], tpp) if order == "Channel-First" else (tpp * ts[0], ts[1], 1)
+        out_o = O.mixer_oracle(h, params, ts, layout=layout)
+        e = relerr(out_o, out)
+        assert e < 5e-5, (name, e)
+        save(name, dict(params=params, hidden=h, token_size=ts, tokens_per_patch=tpp, scan_order=order, out=out),
+             oracle_vs_ref=e)
+
     print("[4] mamba_inner_ref  (selective_scan_interface.py:1757-1810, without out_proj)")
     torch.manual_seed(0)
     Bt, Dm, L, N, R = 2, 16, 40, 8, 3

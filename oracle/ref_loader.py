@@ -175,7 +175,9 @@ def load_reference():
     ln.layer_norm_fn = _layer_norm_fn
     import models.fastvim as fastvim  # noqa: E402
 
-    ns = types.SimpleNamespace(ssi=ssi, msf=msf, ln=ln, fastvim=fastvim)
+    import mamba_ssm.modules.mamba_simple_channel_faster as mscf  # noqa: E402  (FastChannelVim mixer)
+
+    ns = types.SimpleNamespace(ssi=ssi, msf=msf, mscf=mscf, ln=ln, fastvim=fastvim)
     _loaded = ns
     return ns
 

@@ -69,3 +69,38 @@ def test_ops_refuse_cpu_tensors():
 
     with pytest.raises(_lib.FastVimLibraryError):
         ops.conv_pool_fwd(torch.zeros(1, 4, 8), ops.Geometry.grid(2, 2), torch.zeros(2, 8, 4), None)
+
+
+def test_compat_shims_resolve_reference_module_paths():
+    """fastvim_b200/compat first on sys.path: the reference's own import lines (models/fastvim.py:9, 15-18;
+    mamba_simple_faster.py:17-24) bind to the B200 implementation."""
+    import importlib
+    import sys
+
+    compat = os.path.join(ROOT, "fastvim_b200", "compat")
+    saved = {k: v for k, v in sys.modules.items() if k == "mamba_ssm" or k.startswith("mamba_ssm.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, compat)
+    try:
+        msf = importlib.import_module("mamba_ssm.modules.mamba_simple_faster")
+        mscf = importlib.import_module("mamba_ssm.modules.mamba_simple_channel_faster")
+        ln = importlib.import_module("mamba_ssm.ops.triton.layernorm")
+        ssi = importlib.import_module("mamba_ssm.ops.selective_scan_interface")
+        from fastvim_b200 import interface, mixer, mixer_channel, norm
+
+        assert msf.Mamba is mixer.Mamba and mscf.Mamba is mixer_channel.Mamba
+        assert ln.RMSNorm is norm.RMSNorm and ln.rms_norm_fn is norm.rms_norm_fn and ln.layer_norm_fn is norm.layer_norm_fn
+        for fn in ("selective_scan_fn", "mamba_inner_fn_no_out_proj", "mamba_inner_fn_no_out_proj_withoutZ",
+                   "FastVim_mamba_inner_fn_no_out_proj_withoutZ"):
+            assert getattr(ssi, fn) is getattr(interface, fn)
+        # same parameter names / shapes as the reference module (state-dict compatible)
+        m = msf.Mamba(32, token_size=[4, 6], layer_idx=0)
+        names = set(dict(m.named_parameters()))
+        assert {"in_proj.weight", "conv1d.weight", "conv1d_b.weight", "x_proj.weight", "x_proj_b.weight", "dt_proj.weight",
+                "dt_proj_b.bias", "A_log", "A_b_log", "D", "D_b", "layernorm.weight", "out_proj.weight"} <= names
+    finally:
+        sys.path.remove(compat)
+        for k in [k for k in sys.modules if k == "mamba_ssm" or k.startswith("mamba_ssm.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)

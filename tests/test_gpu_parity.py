@@ -506,3 +506,40 @@ def test_gemm_tcgen05_vs_torch(M, N, K):
     az = torch.zeros(M, 2 * K, dtype=torch.bfloat16, device="cuda")
     az[:, :K] = a
     assert torch.equal(ops.gemm_bf16_tn(az[:, :K], w), c)
+
+
+# ------------------------------------------------------------------ FastChannelVim mixer (channel layouts)
+@pytest.mark.parametrize("name", ["cmixer_d32_4x6_t3_channel_first", "cmixer_d32_6x4_t2_spatial_first"])
+def test_channel_mixer_vs_reference_golden_fp32(name):
+    """fp32 CUDA FastChannelVim mixer against vectors produced by the reference's own module."""
+    from fastvim_b200.mixer_channel import Mamba
+
+    g = load_golden(name)
+    m = Mamba(g["params"]["in_proj.weight"].shape[1], token_size=list(g["token_size"]), layer_idx=0,
+              scan_order=g["scan_order"])
+    m.load_state_dict(g["params"], strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        out = m(g["hidden"].cuda(), g["tokens_per_patch"])
+    assert_close(out, g["out"], 1e-4, name)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("order", ["Channel-First", "Spatial-First"])
+def test_channel_mixer_jumpcp_shape_vs_oracle(dtype, order):
+    """BASELINE.json configs[3] shape: FastChannelVim-S/16 mixer (d_model 384), 14 x 14 patches x 8 channels = 1568 tokens."""
+    from fastvim_b200.mixer_channel import Mamba
+
+    p = O.random_mixer_params(384, seed=7)
+    torch.manual_seed(0)
+    tpp, ts = 8, (14, 14)
+    h = torch.randn(2, ts[0] * ts[1] * tpp, 384)
+    m = Mamba(384, token_size=list(ts), layer_idx=0, scan_order=order)
+    m.load_state_dict(p, strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        out = m(h.cuda(), tpp)
+    layout = (ts[0], ts[1], tpp) if order == "Channel-First" else (tpp * ts[0], ts[1], 1)
+    want = O.mixer_oracle(h, p, ts, layout=layout)
+    assert out.dtype == dtype
+    assert_close(out, want, TOL[dtype], f"channel mixer {order} {dtype}")

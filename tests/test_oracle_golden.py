@@ -92,3 +92,14 @@ def test_pool_index_matches_reshape_mean():
     acc = torch.zeros(outer * inner).index_add_(0, idx, x[0, 0]) / pool
     assert torch.allclose(acc, ref[0, 0], atol=1e-6)
     assert torch.equal(O.broadcast_oracle(ref, outer, pool, inner)[0, 0], ref[0, 0][idx])
+
+
+@pytest.mark.parametrize("name", ["cmixer_d32_4x6_t3_channel_first", "cmixer_d32_6x4_t2_spatial_first"])
+def test_channel_mixer_oracle_matches_reference_vector(name):
+    """(outer, pool, inner) generalisation of the mixer oracle against the reference's own FastChannelVim mixer
+    (mamba_simple_channel_faster.py:176-420), both scan orders."""
+    g = load_golden(name)
+    ts, tpp = g["token_size"], g["tokens_per_patch"]
+    layout = (ts[0], ts[1], tpp) if g["scan_order"] == "Channel-First" else (tpp * ts[0], ts[1], 1)
+    out = O.mixer_oracle(g["hidden"], g["params"], ts, layout=layout)
+    assert relerr(out, g["out"]) < 2e-5
