@@ -132,11 +132,185 @@ scan_fwd_kernel(Geom g, const T* __restrict__ u, const T* __restrict__ xdbl, int
     }
 }
 
+// ---- chunk-parallel variant for long pooled sequences with few images (2048^2: B = 1, Lp = 128) --------------
+// The kernel above gives one thread the whole chain of Lp steps: at B = 1 that is 768 threads on 6 SMs and every
+// step exposes the full LDS -> dt dot -> softplus -> ex2 -> FMA latency (72 us per launch, half of the 2048^2 step).
+// Here the chain of each (channel, direction) is cut into NCH chunks of CL steps owned by different threads:
+//   pass 1  every chunk scans from a zero state: S_k[n] (local end state) and sum_k(delta); since the decay of a
+//           chunk is the product of exp2(delta*A2) = exp2(A2 * sum(delta)), no running product is kept;
+//   combine every thread folds the (P, S) pairs of the chunks before it -> its start state (<= NCH-1 cheap steps);
+//   pass 2  the chunk is scanned again from the true start state, producing y.
+// Critical path 2*CL + NCH steps instead of Lp, and NCH times more warps to hide latency.  delta is computed once
+// (pass 1) and kept in registers for pass 2.
+constexpr int SCK_CH = 32;   // channels per CTA
+constexpr int SCK_CL = 16;   // steps per chunk
+
+template <typename T, int RT, int N>
+__global__ void __launch_bounds__(SCK_CH * 16)
+scan_fwd_chunked_kernel(Geom g, int nch, const T* __restrict__ u, const T* __restrict__ xdbl, int64_t ldxd, int R,
+                        const float* __restrict__ dtw, const float* __restrict__ dtb,
+                        const float* __restrict__ A, int a_is_log, float* __restrict__ s) {
+    constexpr int WROW = RT + 2 * N;
+    extern __shared__ __align__(16) float sck_smem[];
+    float* tile = sck_smem;                                    // [Lp][WROW]   dt | B | C rows of this image / direction
+    float* carry = tile + (size_t)g.Lp * WROW;                 // [nch][SCK_CH][N]  local end states
+    float* sumd = carry + (size_t)nch * SCK_CH * N;            // [nch][SCK_CH]     sum of delta per chunk
+    const int dir = blockIdx.z, b = blockIdx.y;
+    const int c = threadIdx.x & (SCK_CH - 1), k = threadIdx.x / SCK_CH;   // channel in CTA, chunk
+    const int d = blockIdx.x * SCK_CH + c;
+    const bool live = d < g.D;
+    const int dd = live ? d : 0;
+    const int64_t plane = (int64_t)g.B * g.Lp * g.D;
+    constexpr float LOG2E = 1.4426950408889634f;
+    const int Lp = g.Lp;
+
+    // stage [dt | B | C] of the whole pooled sequence (fp32)
+    const T* xd = xdbl + ((int64_t)dir * g.B + b) * Lp * ldxd;
+    for (int i = threadIdx.x; i < Lp * WROW; i += blockDim.x) {
+        const int r = i / WROW, cc = i - r * WROW;
+        float v = 0.f;
+        if (cc < RT) {
+            if (cc < R) v = ld1(xd + (int64_t)r * ldxd + cc);
+        } else {
+            v = ld1(xd + (int64_t)r * ldxd + R + (cc - RT));
+        }
+        tile[i] = v;
+    }
+    float A2[N], h[N], W[RT];
+    {
+        const float* Ap = A + ((int64_t)dir * g.D + dd) * N;
+#pragma unroll
+        for (int n = 0; n < N; ++n) {
+            const float a = Ap[n];
+            A2[n] = (a_is_log ? -expf(a) : a) * LOG2E;
+            h[n] = 0.f;
+        }
+        const float* Wp = dtw + ((int64_t)dir * g.D + dd) * R;
+#pragma unroll
+        for (int j = 0; j < RT; ++j) W[j] = j < R ? Wp[j] : 0.f;
+    }
+    const float bias = dtb[(int64_t)dir * g.D + dd];
+    const T* ub = u + dir * plane + (int64_t)b * Lp * g.D + dd;
+    float* sb = s + dir * plane + (int64_t)b * Lp * g.D + dd;
+    // scan position p = k*CL + i  <->  pooled row j = dir ? Lp-1-p : p
+    const int p0 = k * SCK_CL, steps = max(0, min(SCK_CL, Lp - p0));
+    float uu[SCK_CL], dl[SCK_CL];
+#pragma unroll
+    for (int i = 0; i < SCK_CL; ++i) {
+        const int p = p0 + i, j = dir ? Lp - 1 - p : p;
+        uu[i] = (i < steps && live) ? ld1(ub + (int64_t)j * g.D) : 0.f;
+    }
+    __syncthreads();
+    // ---- pass 1: local scan from zero
+    float sd = 0.f;
+#pragma unroll
+    for (int i = 0; i < SCK_CL; ++i) {
+        dl[i] = 0.f;
+        if (i < steps) {
+            const int p = p0 + i, j = dir ? Lp - 1 - p : p;
+            const float* row = tile + (size_t)j * WROW;
+            float dt = bias;
+#pragma unroll
+            for (int q4 = 0; q4 < RT; q4 += 4) {
+                const float4 q = *reinterpret_cast<const float4*>(row + q4);
+                dt = fmaf(W[q4], q.x, dt); dt = fmaf(W[q4 + 1], q.y, dt);
+                dt = fmaf(W[q4 + 2], q.z, dt); dt = fmaf(W[q4 + 3], q.w, dt);
+            }
+            const float delta = softplus_fast(dt);
+            dl[i] = delta;
+            sd += delta;
+            const float du = delta * uu[i];
+#pragma unroll
+            for (int n = 0; n < N; n += 4) {
+                const float4 Bq = *reinterpret_cast<const float4*>(row + RT + n);
+                h[n] = fmaf(ex2(delta * A2[n]), h[n], du * Bq.x);
+                h[n + 1] = fmaf(ex2(delta * A2[n + 1]), h[n + 1], du * Bq.y);
+                h[n + 2] = fmaf(ex2(delta * A2[n + 2]), h[n + 2], du * Bq.z);
+                h[n + 3] = fmaf(ex2(delta * A2[n + 3]), h[n + 3], du * Bq.w);
+            }
+        }
+    }
+    {
+        float* cp = carry + ((size_t)k * SCK_CH + c) * N;
+#pragma unroll
+        for (int n = 0; n < N; n += 4) *reinterpret_cast<float4*>(cp + n) = make_float4(h[n], h[n + 1], h[n + 2], h[n + 3]);
+        sumd[k * SCK_CH + c] = sd;
+    }
+    __syncthreads();
+    // ---- combine: start state of chunk k = fold of chunks 0..k-1 (in scan order)
+#pragma unroll
+    for (int n = 0; n < N; ++n) h[n] = 0.f;
+    for (int kk = 0; kk < k; ++kk) {
+        const float sdk = sumd[kk * SCK_CH + c];
+        const float* cp = carry + ((size_t)kk * SCK_CH + c) * N;
+#pragma unroll
+        for (int n = 0; n < N; n += 4) {
+            const float4 Sq = *reinterpret_cast<const float4*>(cp + n);
+            h[n] = fmaf(ex2(sdk * A2[n]), h[n], Sq.x);
+            h[n + 1] = fmaf(ex2(sdk * A2[n + 1]), h[n + 1], Sq.y);
+            h[n + 2] = fmaf(ex2(sdk * A2[n + 2]), h[n + 2], Sq.z);
+            h[n + 3] = fmaf(ex2(sdk * A2[n + 3]), h[n + 3], Sq.w);
+        }
+    }
+    // ---- pass 2: the chunk again, from the true start state
+#pragma unroll
+    for (int i = 0; i < SCK_CL; ++i) {
+        if (i < steps) {
+            const int p = p0 + i, j = dir ? Lp - 1 - p : p;
+            const float* row = tile + (size_t)j * WROW;
+            const float delta = dl[i], du = delta * uu[i];
+            float y0 = 0.f, y1 = 0.f;
+#pragma unroll
+            for (int n = 0; n < N; n += 4) {
+                const float4 Bq = *reinterpret_cast<const float4*>(row + RT + n);
+                const float4 Cq = *reinterpret_cast<const float4*>(row + RT + N + n);
+                h[n] = fmaf(ex2(delta * A2[n]), h[n], du * Bq.x);             y0 = fmaf(h[n], Cq.x, y0);
+                h[n + 1] = fmaf(ex2(delta * A2[n + 1]), h[n + 1], du * Bq.y); y1 = fmaf(h[n + 1], Cq.y, y1);
+                h[n + 2] = fmaf(ex2(delta * A2[n + 2]), h[n + 2], du * Bq.z); y0 = fmaf(h[n + 2], Cq.z, y0);
+                h[n + 3] = fmaf(ex2(delta * A2[n + 3]), h[n + 3], du * Bq.w); y1 = fmaf(h[n + 3], Cq.w, y1);
+            }
+            if (live) sb[(int64_t)j * g.D] = y0 + y1;
+        }
+    }
+}
+
 int check_geom(const fv_geom* g, const char* who);
+int sm_count();
+
+template <typename T, int N>
+static int launch_scan_chunked(const Geom& g, const T* u, const T* xdbl, int64_t ldxd, int R, const float* dtw,
+                               const float* dtb, const float* A, int a_is_log, float* s, cudaStream_t st, bool* done) {
+    *done = false;
+    const int nch = ceil_div(g.Lp, SCK_CL);
+    if (R > 16 || nch < 2 || nch > 16) return 0;   // <= 512 threads (128 registers each)
+    const int RT = R <= 8 ? 8 : (R <= 12 ? 12 : 16);
+    const size_t smem = ((size_t)g.Lp * (RT + 2 * N) + (size_t)nch * SCK_CH * N + (size_t)nch * SCK_CH) * sizeof(float);
+    if (smem > 200 * 1024) return 0;
+    dim3 grid(ceil_div(g.D, SCK_CH), g.B, 2), block(SCK_CH * nch);
+#define FV_SCK_CASE(RT_)                                                                                              \
+    if (RT == RT_) {                                                                                                  \
+        if (smem > 48 * 1024) {                                                                                       \
+            cudaError_t e = cudaFuncSetAttribute(scan_fwd_chunked_kernel<T, RT_, N>,                                  \
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
+            FV_REQUIRE(e == cudaSuccess, "fv_scan_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));             \
+        }                                                                                                             \
+        scan_fwd_chunked_kernel<T, RT_, N><<<grid, block, smem, st>>>(g, nch, u, xdbl, ldxd, R, dtw, dtb, A, a_is_log, s); \
+    }
+    FV_SCK_CASE(8) FV_SCK_CASE(12) FV_SCK_CASE(16)
+#undef FV_SCK_CASE
+    *done = true;
+    return finish_launch("scan_fwd_chunked");
+}
 
 template <typename T, int N>
 static int launch_scan(const Geom& g, const T* u, const T* xdbl, int64_t ldxd, int R, const float* dtw,
                        const float* dtb, const float* A, int a_is_log, float* s, cudaStream_t st) {
+    // few images and a long pooled sequence: the one-thread-per-chain kernel would leave most SMs idle
+    if (g.Lp >= 2 * SCK_CL && (int64_t)ceil_div(g.D, SCAN_THREADS) * g.B * 2 < sm_count()) {
+        bool done = false;
+        const int rc = launch_scan_chunked<T, N>(g, u, xdbl, ldxd, R, dtw, dtb, A, a_is_log, s, st, &done);
+        if (rc || done) return rc;
+    }
     dim3 grid(ceil_div(g.D, SCAN_THREADS), g.B, 2), block(SCAN_THREADS);
 #define FV_SCAN_CASE(RT_)                                                                          \
     if (R <= RT_) {                                                                                \
