@@ -14,9 +14,13 @@
 // therefore reads 32 x 4 channels = 256 B (bf16) / 512 B (fp32) contiguous per row: fully
 // coalesced, independent of the token permutation (rotated layers only change row numbers).
 // HBM-bound by design: algorithmic bytes = B*L*D*s read + 2*B*Lp*D*s written.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace fv {
+
+int sm_count();
 
 template <typename T>
 __device__ __forceinline__ float4 load_row4(const Geom& g, const T* xb, int64_t ldx, int d0, int t) {
@@ -164,6 +168,117 @@ conv_pool_staged_kernel(Geom g, int TP, int nbuf, int vec16, const T* __restrict
     st4(uo + plane, accb);
 }
 
+// v3 for long pooled groups and few images (2048^2: one image, pool = 128): the staged kernel above would run only
+// Lp = 128 CTAs, each walking 128 tokens serially (23 us for 12.8 MB).  Here a thread-block CLUSTER of NS CTAs owns
+// one pooled position: CTA `rank` convolves tokens [rank*np, (rank+1)*np) of the group (its own 3-token halos staged
+// with cp.async like above), the partial sums / maxima meet in rank 0 through distributed shared memory
+// (cluster.map_shared_rank), and rank 0 scales and stores.  NS x more CTAs, no workspace, no atomics.
+template <typename T, bool MAXPOOL, int MAXT>
+__global__ void __launch_bounds__(MAXT)
+conv_pool_cluster_kernel(Geom g, int NS, int np_seg, int vec16, const T* __restrict__ x, int64_t ldx, int64_t xbs,
+                         const float* __restrict__ cw, const float* __restrict__ cb, float scale,
+                         T* __restrict__ u) {
+    constexpr bool FAST = is_fast<T>::value;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int G = 7;
+    const int D = g.D;
+    float4* part = reinterpret_cast<float4*>(smem_raw);                     // [2][blockDim.x] partial results of this CTA
+    T* xs = reinterpret_cast<T*>(part + 2 * blockDim.x);                    // [np_seg + 6][D]
+    int* rowtab = reinterpret_cast<int*>(xs + (size_t)(np_seg + 6) * D);    // [np_seg + 6]
+    const int rank = (int)cluster.block_rank();
+    const int j = blockIdx.x / NS, b = blockIdx.y;
+    const int d0 = threadIdx.x * 4;
+    const bool live = d0 < g.D;
+    const int dd = live ? d0 : 0;
+    const T* xb = x + (int64_t)b * xbs;
+    const int p_lo = rank * np_seg, np = max(0, min(np_seg, g.pool - p_lo));
+    const int tbase = j * g.pool + p_lo;
+
+    fill_rowtab(g, tbase - 3, np + 6, rowtab);
+    __syncthreads();
+    if (np > 0) stage_rows(g, xb, ldx, rowtab, np + 6, xs, vec16 != 0);
+    cp_async_commit();
+    constexpr float PRE = FAST ? 0.5f : 1.f;
+    const Taps tf = load_taps(cw, cb, g.D, 0, dd, PRE), tb = load_taps(cw, cb, g.D, 1, dd, PRE);
+    float4 accf = MAXPOOL ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : zero4();
+    float4 accb = accf;
+    cp_async_wait<0>();
+    __syncthreads();
+    for (int p0 = 0; p0 < np; p0 += G) {
+        float4 r[G + 6];
+        const T* xp = xs + dd + p0 * D;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) r[k] = ld4(xp + k * D);
+#pragma unroll
+        for (int i = 0; i < G; ++i) {
+            if (p0 + i < np) {
+                r[i + 6] = ld4(xp + (i + 6) * D);
+                float4 xf, xr;
+                conv_both_pre<FAST>(r[i], r[i + 1], r[i + 2], r[i + 3], r[i + 4], r[i + 5], r[i + 6], tf, tb, xf, xr);
+                accf = MAXPOOL ? max4(accf, xf) : accf + xf;
+                accb = MAXPOOL ? max4(accb, xr) : accb + xr;
+            }
+        }
+    }
+    part[threadIdx.x] = accf;
+    part[blockDim.x + threadIdx.x] = accb;
+    cluster.sync();  // every CTA's partials are visible cluster-wide
+    if (rank == 0 && live) {
+        for (int r = 1; r < NS; ++r) {
+            const float4* rp = cluster.map_shared_rank(part, r);
+            const float4 pf = rp[threadIdx.x], pb = rp[blockDim.x + threadIdx.x];
+            accf = MAXPOOL ? max4(accf, pf) : accf + pf;
+            accb = MAXPOOL ? max4(accb, pb) : accb + pb;
+        }
+        if (!MAXPOOL) {
+            const float m = scale / (float)g.pool;
+            accf = scale4(accf, m);
+            accb = scale4(accb, m);
+        }
+        const int64_t plane = (int64_t)g.B * g.Lp * g.D;
+        T* uo = u + ((int64_t)b * g.Lp + j) * g.D + d0;
+        st4(uo, accf);
+        st4(uo + plane, accb);
+    }
+    cluster.sync();  // keep every CTA's shared memory alive until rank 0 has read it
+}
+
+template <typename T>
+static int launch_conv_pool_cluster(const Geom& g, int NS, const T* x, int64_t ldx, int64_t xbs, const float* cw,
+                                    const float* cb, float scale, int pool_mode, T* u, cudaStream_t st) {
+    const int threads = ((g.D / 4) + 31) / 32 * 32;
+    const int np_seg = (g.pool + NS - 1) / NS;
+    const size_t smem = (size_t)2 * threads * sizeof(float4) + (size_t)(np_seg + 6) * g.D * sizeof(T) + (size_t)(np_seg + 6) * 4;
+    void (*kern)(Geom, int, int, int, const T*, int64_t, int64_t, const float*, const float*, float, T*);
+    const bool mx = pool_mode == FV_POOL_MAX;
+    if (threads <= 128) kern = mx ? conv_pool_cluster_kernel<T, true, 128> : conv_pool_cluster_kernel<T, false, 128>;
+    else if (threads <= 256) kern = mx ? conv_pool_cluster_kernel<T, true, 256> : conv_pool_cluster_kernel<T, false, 256>;
+    else if (threads <= 512) kern = mx ? conv_pool_cluster_kernel<T, true, 512> : conv_pool_cluster_kernel<T, false, 512>;
+    else kern = mx ? conv_pool_cluster_kernel<T, true, 1024> : conv_pool_cluster_kernel<T, false, 1024>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        FV_REQUIRE(e == cudaSuccess, "fv_conv_pool_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(g.Lp * NS), (unsigned)g.B);
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)NS;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int vec16 = (int)rows_vec16<T>(g.D, x, ldx, xbs);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, g, NS, np_seg, vec16, x, ldx, xbs, cw, cb, scale, u);
+    FV_REQUIRE(e == cudaSuccess, "fv_conv_pool_fwd: cluster launch failed: %s", cudaGetErrorString(e));
+    return finish_launch("conv_pool_fwd");
+}
+
 template <typename T>
 static int launch_conv_pool_staged(const Geom& g, const T* x, int64_t ldx, int64_t xbs, const float* cw,
                                    const float* cb, float scale, int pool_mode, T* u, cudaStream_t st) {
@@ -192,7 +307,15 @@ static int launch_conv_pool_staged(const Geom& g, const T* x, int64_t ldx, int64
 template <typename T>
 static int launch_conv_pool(const Geom& g, const T* x, int64_t ldx, int64_t xbs, const float* cw,
                             const float* cb, float scale, int pool_mode, T* u, cudaStream_t st) {
-    if (g.inner == 1 && g.D <= 4096) return launch_conv_pool_staged<T>(g, x, ldx, xbs, cw, cb, scale, pool_mode, u, st);
+    if (g.inner == 1 && g.D <= 4096) {
+        // long pooled groups, too few (image, pooled position) pairs to fill the GPU: one cluster per position
+        if (g.pool >= 32 && (int64_t)g.Lp * g.B < 2 * sm_count() && g.B <= 65535) {
+            int NS = 8;
+            while (NS > 2 && g.pool / NS < 8) NS >>= 1;
+            return launch_conv_pool_cluster<T>(g, NS, x, ldx, xbs, cw, cb, scale, pool_mode, u, st);
+        }
+        return launch_conv_pool_staged<T>(g, x, ldx, xbs, cw, cb, scale, pool_mode, u, st);
+    }
     const int64_t items = (int64_t)g.B * g.Lp * (g.D / 4);
     const int threads = 256;
     const int64_t blocks = (items + threads - 1) / threads;

@@ -56,6 +56,33 @@ def test_conv_pool_fwd(dtype, rows, cols, Dm, mode, sf):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("Bt,rows,cols,Dm,rot,mode", [(1, 128, 128, 384, False, "mean"), (1, 128, 128, 384, True, "mean"),
+                                                      (2, 3, 100, 64, False, "mean"), (1, 5, 37, 48, False, "max"),
+                                                      (1, 2, 300, 96, True, "mean")])
+def test_conv_pool_fwd_long_pool_cluster_path(dtype, Bt, rows, cols, Dm, rot, mode):
+    """Long pooled groups with few images (2048^2 shape) take the thread-block-cluster kernel (partials meet in
+    distributed shared memory); ragged segment splits, rotation and max pooling included."""
+    from fastvim_b200 import ops
+
+    torch.manual_seed(0)
+    L = rows * cols
+    x = torch.randn(Bt, L, Dm)
+    cw, cb = torch.randn(2, Dm, 4) * 0.5, torch.randn(2, Dm) * 0.5
+    xq = x.to(dtype).float()
+    xt = xq.transpose(1, 2)
+    xc_f = O.causal_conv1d_oracle(xt, cw[0], cb[0])
+    xc_b = O.causal_conv1d_oracle(xt.flip(-1), cw[1], cb[1])
+    u_f = O.pool_oracle(xc_f, rows, cols, 1, mode, 1.0).transpose(1, 2)
+    u_b = O.pool_oracle(xc_b, rows, cols, 1, mode, 1.0).flip(-1).transpose(1, 2)
+    xm = xq
+    if rot:   # store the tokens so that the mixer's sequence is the column-major walk of a (cols, rows) memory grid
+        xm = xq.view(Bt, rows, cols, Dm).transpose(1, 2).reshape(Bt, L, Dm)
+    u = ops.conv_pool_fwd(_dev(xm.contiguous(), dtype), ops.Geometry.grid(rows, cols, rot), cw.cuda(), cb.cuda(), 1.0, mode)
+    assert_close(u[0], u_f, TOL[dtype], "u_f")
+    assert_close(u[1], u_b, TOL[dtype], "u_b")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_conv_pool_rotated_equals_physical_rotation(dtype):
     """The rotated geometry must give bit-identical results to physically permuting the tokens
     (models/fastvim.py:192-200) and running the un-rotated kernel: pure indexing."""
