@@ -5,9 +5,10 @@
 //   out_proj  F.linear(y, out_proj.weight, out_proj.bias)                                          :442-444
 //
 // B200 mapping (one CTA per SM, persistent over 128-row tiles of A):
-//   * W is small (192 x 384 / 256 x 192 bf16): the CTA's column block of W is loaded ONCE by TMA into shared memory
+//   * FastVim-T/S: W is small (192 x 384 / 256 x 192 bf16): the CTA's column block of W is loaded ONCE by TMA into shared memory
 //     (128-byte swizzle, K-major; k-blocks interleaved with the first tile's A boxes) and stays resident; only A tiles
-//     stream from HBM (3-4 stage TMA ring of 128 x 64 boxes).
+//     stream from HBM (3-4 stage TMA ring of 128 x 64 boxes).  Large K (FastVim-B, patch embedding: K = 768 / 1536): the
+//     weight block does not fit, so W k-blocks stream through the same ring as A (L2-resident after the first tile).
 //   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread issues tcgen05.mma.cta_group::1.kind::f16,
 //     M = 128, N = BN, K = 16 per instruction; accumulators live in TMEM, double-buffered 2 x BN columns so the
 //     epilogue of tile i overlaps the MMAs of tile i+1), warps 2-5 = epilogue (tcgen05.ld 32x32b: one TMEM lane =
@@ -28,6 +29,9 @@ constexpr uint32_t GT_A_STAGE_BYTES = GT_BM * GT_BK * 2;  // 16 KB
 
 struct GemmArgs {
     int M, N, K, KB, nstage, ncstage, ntiles;
+    int stream_w;   // 0: the CTA's W block stays resident (small K*BN); 1: W k-blocks stream through the ring with A
+    int nblocks;    // column blocks of BN (stream mode: a tile is (row tile, column block), column block fastest)
+    const float* bias;  // (N) fp32 added before the bf16 rounding, or null
 };
 
 // ---- PTX wrappers ----------------------------------------------------------------------------------------------
@@ -87,7 +91,6 @@ __device__ __forceinline__ uint32_t gt_pack(uint32_t lo, uint32_t hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// MODE 0: C = bf16(acc).  MODE 1: res = acc + res_in; res_out = res; C = bf16(res * rsqrt(mean(res^2) + eps) * norm_w)
 // Epilogue staging: the four epilogue warps convert their TMEM rows to bf16 and write them into a (128 x 64) bf16
 // tile in shared memory with the TMA 128-byte swizzle (16-byte chunk index XOR row % 8: conflict-free 16-byte stores
 // although every thread owns a different row), then ONE thread hands the tile to the TMA engine
@@ -113,9 +116,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int KB = a.KB, NS = a.nstage, NC = a.ncstage;
     constexpr uint32_t W_BLK_BYTES = BN * GT_BK * 2;
 
+    // resident mode: [W: KB blocks][A ring: NS x 16 KB][C staging]; stream mode: [ring: NS x (A 16 KB + W block)][C staging]
+    const bool stream = a.stream_w != 0;
+    const uint32_t stage_bytes = stream ? GT_A_STAGE_BYTES + W_BLK_BYTES : GT_A_STAGE_BYTES;
     unsigned char* sW = smem;
-    unsigned char* sA = sW + (size_t)KB * W_BLK_BYTES;
-    unsigned char* sC = sA + (size_t)NS * GT_A_STAGE_BYTES;
+    unsigned char* sA = stream ? smem : sW + (size_t)KB * W_BLK_BYTES;
+    unsigned char* sC = sA + (size_t)NS * stage_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sC + (size_t)NC * GT_C_STAGE_BYTES);
     uint64_t* w_full = bars;            // [KB]: W k-block kb has landed (once per kernel)
     uint64_t* a_full = w_full + KB;
@@ -144,7 +150,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
-    const int n0 = blockIdx.y * BN;
+    const int nblk = a.nblocks;
+    // resident mode: this CTA's column block is blockIdx.y and a tile is a row tile; stream mode: tile = (row tile, block)
+#define GT_TILE_M(tile_) (stream ? (tile_) / nblk : (tile_))
+#define GT_TILE_N0(tile_) ((stream ? (tile_) % nblk : (int)blockIdx.y) * BN)
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -153,14 +162,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t ph = 0;
             bool first = true;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+                const int m0 = GT_TILE_M(tile) * GT_BM, n0 = GT_TILE_N0(tile);
                 for (int kb = 0; kb < KB; ++kb) {
-                    if (first) {  // W k-blocks are interleaved with the first tile's A boxes: the first MMAs start early
+                    if (!stream && first) {  // W k-blocks are interleaved with the first tile's A boxes: the first MMAs start early
                         mbar_arrive_expect_tx(&w_full[kb], W_BLK_BYTES);
                         gt_tma_2d(sW + (size_t)kb * W_BLK_BYTES, &tmW, kb * GT_BK, n0, &w_full[kb]);
                     }
                     gt_mbar_wait(&a_empty[st], ph ^ 1u);
-                    mbar_arrive_expect_tx(&a_full[st], GT_A_STAGE_BYTES);
-                    gt_tma_2d(sA + (size_t)st * GT_A_STAGE_BYTES, &tmA, kb * GT_BK, tile * GT_BM, &a_full[st]);
+                    unsigned char* stg = sA + (size_t)st * stage_bytes;
+                    mbar_arrive_expect_tx(&a_full[st], stage_bytes);
+                    gt_tma_2d(stg, &tmA, kb * GT_BK, m0, &a_full[st]);
+                    if (stream) gt_tma_2d(stg + GT_A_STAGE_BYTES, &tmW, kb * GT_BK, n0, &a_full[st]);
                     if (++st == NS) { st = 0; ph ^= 1u; }
                 }
                 first = false;
@@ -181,13 +193,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
                 for (int kb = 0; kb < KB; ++kb) {
-                    if (first) gt_mbar_wait(&w_full[kb], 0);
+                    if (!stream && first) gt_mbar_wait(&w_full[kb], 0);
                     gt_mbar_wait(&a_full[st], ph);
                     tc_fence_after();
+                    const uint32_t a_u = sA_u + (uint32_t)st * stage_bytes;
+                    const uint32_t b_u = stream ? a_u + GT_A_STAGE_BYTES : sW_u + (uint32_t)kb * W_BLK_BYTES;
 #pragma unroll
                     for (int k = 0; k < GT_BK / 16; ++k) {
-                        const uint64_t ad = tc_smem_desc(sA_u + (uint32_t)st * GT_A_STAGE_BYTES + k * 32);
-                        const uint64_t bd = tc_smem_desc(sW_u + (uint32_t)kb * W_BLK_BYTES + k * 32);
+                        const uint64_t ad = tc_smem_desc(a_u + k * 32);
+                        const uint64_t bd = tc_smem_desc(b_u + k * 32);
                         tc_mma(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     tc_commit(&a_empty[st]);  // frees the A stage once these MMAs have read it
@@ -211,6 +225,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             gt_mbar_wait(&acc_full[as], aph);
             tc_fence_after();
             const uint32_t t0 = lane_addr + (uint32_t)(as * BN);
+            const int m0 = GT_TILE_M(tile) * GT_BM, n0 = GT_TILE_N0(tile);
 #pragma unroll 1
             for (int c = 0; c < BN / GT_CCHUNK; ++c) {
                 unsigned char* stage = sC + (size_t)cs * GT_C_STAGE_BYTES;
@@ -226,6 +241,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint32_t r[32];
                     tc_ld32(t0 + c * GT_CCHUNK + h * 32, r);
                     tc_wait_ld();
+                    if (a.bias) {
+                        const float4* bp = reinterpret_cast<const float4*>(a.bias + n0 + c * GT_CCHUNK + h * 32);
+#pragma unroll
+                        for (int v = 0; v < 8; ++v) {
+                            const float4 bq = __ldg(bp + v);
+                            r[4 * v] = __float_as_uint(__uint_as_float(r[4 * v]) + bq.x);
+                            r[4 * v + 1] = __float_as_uint(__uint_as_float(r[4 * v + 1]) + bq.y);
+                            r[4 * v + 2] = __float_as_uint(__uint_as_float(r[4 * v + 2]) + bq.z);
+                            r[4 * v + 3] = __float_as_uint(__uint_as_float(r[4 * v + 3]) + bq.w);
+                        }
+                    }
 #pragma unroll
                     for (int v = 0; v < 4; ++v) {
                         uint4 o;
@@ -238,7 +264,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> TMA (async proxy) reads
                 gt_epi_barrier();
                 if (issuer) {
-                    gt_tma_store_2d(&tmC, stage, n0 + c * GT_CCHUNK, tile * GT_BM);
+                    gt_tma_store_2d(&tmC, stage, n0 + c * GT_CCHUNK, m0);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 if (++cs == NC) cs = 0;
@@ -252,6 +278,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     tc_fence_before();
     __syncthreads();
+#undef GT_TILE_M
+#undef GT_TILE_N0
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
@@ -315,14 +343,23 @@ static int pick_bn(int N) {
     return 0;
 }
 
-// W block resident + A stages (2..4) + C staging buffers (1..2) within 227 KB
-static bool plan_smem(int KB, int BN, int* ns, int* nc, size_t* bytes) {
-    const size_t wbytes = (size_t)KB * BN * GT_BK * 2, fixed = (size_t)(KB + 16) * 8 + 16 + 1024, cap = 227 * 1024;
+// Shared-memory plan within 227 KB.  Resident mode (small K x BN weight block): W + A ring (2..4) + C staging (1..2).
+// Stream mode (large K, e.g. FastVim-B and the patch embedding, K = 768 / 1536): ring of (A + W k-block) stages.
+static bool plan_smem(int KB, int BN, int* ns, int* nc, int* stream, size_t* bytes) {
+    const size_t wblk = (size_t)BN * GT_BK * 2, fixed = (size_t)(KB + 16) * 8 + 16 + 1024, cap = 227 * 1024;
     const int opts[5][2] = {{4, 2}, {3, 2}, {4, 1}, {3, 1}, {2, 1}};
     for (auto& o : opts) {
-        const size_t tot = wbytes + (size_t)o[0] * GT_A_STAGE_BYTES + (size_t)o[1] * GT_C_STAGE_BYTES + fixed;
+        const size_t tot = (size_t)KB * wblk + (size_t)o[0] * GT_A_STAGE_BYTES + (size_t)o[1] * GT_C_STAGE_BYTES + fixed;
+        if (tot <= cap && o[0] >= 3) {
+            *ns = o[0]; *nc = o[1]; *stream = 0; *bytes = tot;
+            return true;
+        }
+    }
+    const int sopts[4][2] = {{4, 2}, {4, 1}, {3, 2}, {3, 1}};
+    for (auto& o : sopts) {
+        const size_t tot = (size_t)o[0] * (GT_A_STAGE_BYTES + wblk) + (size_t)o[1] * GT_C_STAGE_BYTES + fixed;
         if (tot <= cap) {
-            *ns = o[0]; *nc = o[1]; *bytes = tot;
+            *ns = o[0]; *nc = o[1]; *stream = 1; *bytes = tot;
             return true;
         }
     }
@@ -334,10 +371,15 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUt
                        size_t smem, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     FV_REQUIRE(e == cudaSuccess, "fv_gemm: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
-    int gx = sm_count() / nblocks;
-    if (gx < 1) gx = 1;
-    if (gx > a.ntiles) gx = a.ntiles;
-    dim3 grid((unsigned)gx, (unsigned)nblocks);
+    dim3 grid;
+    if (a.stream_w) {
+        grid = dim3((unsigned)(a.ntiles < sm_count() ? a.ntiles : sm_count()), 1u);
+    } else {
+        int gx = sm_count() / nblocks;
+        if (gx < 1) gx = 1;
+        if (gx > a.ntiles) gx = a.ntiles;
+        grid = dim3((unsigned)gx, (unsigned)nblocks);
+    }
     gemm_tc_kernel<BN><<<grid, GT_THREADS, smem, st>>>(tmA, tmW, tmC, a);
     return finish_launch("gemm_tc");
 }
@@ -349,13 +391,13 @@ extern "C" int fv_gemm_supported(int64_t M, int N, int K) {
     if (M <= 0 || N <= 0 || K <= 0 || K % GT_BK != 0 || M >= (1ll << 31)) return 0;
     const int BN = pick_bn(N);
     if (!BN) return 0;
-    int ns, nc;
+    int ns, nc, stream;
     size_t bytes;
-    return plan_smem(K / GT_BK, BN, &ns, &nc, &bytes) ? 1 : 0;
+    return plan_smem(K / GT_BK, BN, &ns, &nc, &stream, &bytes) ? 1 : 0;
 }
 
-extern "C" int fv_gemm_bf16_tn(int64_t M, int N, int K, const void* A, int64_t lda, const void* W, int64_t ldw, void* C,
-                               int64_t ldc, void* stream) {
+extern "C" int fv_gemm_bf16_tn(int64_t M, int N, int K, const void* A, int64_t lda, const void* W, int64_t ldw,
+                               const float* bias, void* C, int64_t ldc, void* stream) {
     using namespace fv;
     FV_REQUIRE(A && W && C, "fv_gemm: null pointer");
     FV_REQUIRE(M > 0 && N > 0 && K > 0 && K % GT_BK == 0, "fv_gemm: K (%d) must be a positive multiple of 64", K);
@@ -365,10 +407,13 @@ extern "C" int fv_gemm_bf16_tn(int64_t M, int N, int K, const void* A, int64_t l
     const int BN = pick_bn(N);
     FV_REQUIRE(BN > 0, "fv_gemm: N (%d) must be a multiple of 64", N);
     GemmArgs a;
-    a.M = (int)M; a.N = N; a.K = K; a.KB = K / GT_BK;
+    a.M = (int)M; a.N = N; a.K = K; a.KB = K / GT_BK; a.bias = bias;
+    FV_REQUIRE(!bias || ((uintptr_t)bias % 16) == 0, "fv_gemm: bias must be 16-byte aligned");
     a.ntiles = (int)((M + GT_BM - 1) / GT_BM);
     size_t smem = 0;
-    FV_REQUIRE(plan_smem(a.KB, BN, &a.nstage, &a.ncstage, &smem), "fv_gemm: the %d x %d weight block does not fit shared memory", BN, K);
+    FV_REQUIRE(plan_smem(a.KB, BN, &a.nstage, &a.ncstage, &a.stream_w, &smem), "fv_gemm: no shared-memory plan for BN = %d, K = %d", BN, K);
+    a.nblocks = N / BN;
+    if (a.stream_w) a.ntiles *= a.nblocks;
     CUtensorMap tmA, tmW, tmC;
     if (int rc = get_tmap2d(&tmA, A, M, K, lda, GT_BM)) return rc;
     if (int rc = get_tmap2d(&tmW, W, N, K, ldw, BN)) return rc;

@@ -41,11 +41,11 @@ TC_GEMM = os.environ.get("FASTVIM_TC_GEMM", "1") != "0"
 
 def linear(x, w, b):
     """y = x @ w.T (+ b).  x (..., K), w (N, K)."""
-    if (TC_GEMM and b is None and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.is_cuda
-            and x.stride(-1) == 1 and ops.gemm_supported(x.numel() // x.shape[-1], w.shape[0], w.shape[1])):
+    if (TC_GEMM and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and x.is_cuda and x.stride(-1) == 1
+            and ops.gemm_supported(x.numel() // x.shape[-1], w.shape[0], w.shape[1])):
         x2 = x.reshape(-1, x.shape[-1])
         if x2.stride(0) % 8 == 0 and x2.data_ptr() % 16 == 0 and w.is_contiguous():
-            return ops.gemm_bf16_tn(x2, w).view(*x.shape[:-1], w.shape[0])
+            return ops.gemm_bf16_tn(x2, w, bias=b).view(*x.shape[:-1], w.shape[0])
     return F.linear(x, w, b)
 
 

@@ -239,8 +239,9 @@ def gemm_supported(M: int, N: int, K: int) -> bool:
     return bool(_lib.lib().fv_gemm_supported(int(M), int(N), int(K)))
 
 
-def gemm_bf16_tn(a: Tensor, w: Tensor, out: Optional[Tensor] = None) -> Tensor:
-    """a (..., K) bf16, w (N, K) bf16 -> (..., N) bf16 = a @ w.T on the tcgen05 tensor cores (fp32 accumulate)."""
+def gemm_bf16_tn(a: Tensor, w: Tensor, out: Optional[Tensor] = None, bias: Optional[Tensor] = None) -> Tensor:
+    """a (..., K) bf16, w (N, K) bf16 [, bias (N)] -> (..., N) bf16 = a @ w.T + bias on the tcgen05 tensor cores
+    (fp32 accumulate, bias added in fp32 before the bf16 rounding)."""
     _check_cuda(a, w)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and w.dim() == 2 and w.stride(1) == 1
     K = a.shape[-1]
@@ -249,7 +250,8 @@ def gemm_bf16_tn(a: Tensor, w: Tensor, out: Optional[Tensor] = None) -> Tensor:
         a2 = a2.contiguous()
     M, N = a2.shape[0], w.shape[0]
     c = out if out is not None else torch.empty((M, N), device=a.device, dtype=a.dtype)
-    _lib.call("fv_gemm_bf16_tn", M, N, K, _p(a2), a2.stride(0), _p(w), w.stride(0), _p(c), c.stride(0), _stream(a))
+    _lib.call("fv_gemm_bf16_tn", M, N, K, _p(a2), a2.stride(0), _p(w), w.stride(0), _p(_f32c(bias)), _p(c), c.stride(0),
+              _stream(a))
     return c.reshape(*a.shape[:-1], N)
 
 

@@ -23,6 +23,7 @@ import torch.nn.functional as F
 from torch import Tensor
 
 from .mixer import Mamba
+from .mixer import linear as _linear
 from .norm import RMSNorm, layer_norm_fn, rms_norm_fn
 
 
@@ -60,8 +61,14 @@ class PatchEmbed(nn.Module):
         gh, gw = H // p0, W // p1
         w = self.proj.weight
         cols = x.reshape(B, C, gh, p0, gw, p1).permute(0, 2, 4, 1, 3, 5).reshape(B * gh * gw, C * p0 * p1)
-        out = F.linear(cols, w.reshape(w.shape[0], -1).to(cols.dtype),
-                       None if self.proj.bias is None else self.proj.bias.to(cols.dtype))
+        if torch.is_autocast_enabled("cuda"):
+            cols = cols.to(torch.get_autocast_dtype("cuda"))
+        wmat = w.reshape(w.shape[0], -1).to(cols.dtype)
+        bias = None if self.proj.bias is None else self.proj.bias.to(cols.dtype)
+        if cols.is_cuda and not (torch.is_grad_enabled() and (w.requires_grad or x.requires_grad)):
+            out = _linear(cols, wmat, bias)     # tcgen05 GEMM (bf16) / cuBLAS
+        else:
+            out = F.linear(cols, wmat, bias)
         out = out.reshape(B, gh, gw, -1)
         if self.scanpath_type == "colwise":
             out = out.transpose(1, 2)

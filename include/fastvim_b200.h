@@ -153,13 +153,14 @@ int fv_selective_scan_fwd(int dtype, int batch, int dim, int64_t L, int dstate, 
 /* ---- tcgen05 / TMEM / TMA GEMMs for the projections -------------------------------------------
  * C (M x N) = A (M x K) . W (N x K)^T: bf16 operands (row-major, row strides lda / ldw / ldc elements,
  * 16-byte aligned, multiples of 8), fp32 accumulation in tensor memory, bf16 result.  Replaces the cuBLAS
- * calls of in_proj / out_proj (mamba_simple_faster.py:189-195, 442-444).  K % 64 == 0, N % 64 == 0, and the
- * CTA's (N-block x K) slice of W must fit shared memory (true for every FastVim in_proj / out_proj).
+ * calls of in_proj / out_proj (mamba_simple_faster.py:189-195, 442-444) and of the patch embedding
+ * (models/fastvim.py:67-103).  K % 64 == 0, N % 64 == 0.  When the CTA's (N-block x K) slice of W fits shared
+ * memory it stays resident (FastVim-T/S); otherwise W k-blocks stream with A (FastVim-B, patch embedding).
  * fv_gemm_supported() returns 1 when (M, N, K) qualifies; callers use cuBLAS otherwise.
  */
 int fv_gemm_supported(int64_t M, int N, int K);
-int fv_gemm_bf16_tn(int64_t M, int N, int K, const void* A, int64_t lda, const void* W, int64_t ldw, void* C,
-                    int64_t ldc, void* stream);
+int fv_gemm_bf16_tn(int64_t M, int N, int K, const void* A, int64_t lda, const void* W, int64_t ldw,
+                    const float* bias /* (N) fp32 or NULL */, void* C, int64_t ldc, void* stream);
 /* ---- operator API helpers on (batch, dim, L), L contiguous ---------------------------------
  * The reference's fused autograd functions (selective_scan_interface.py:208-330, 452-605) call, on
  * (B, D, L) tensors: causal_conv1d_cuda.causal_conv1d_fwd(x, w, bias, None, True) (:496-498; third-party

@@ -514,7 +514,8 @@ def test_fastvim_inner_fn_vs_oracle(dtype, Bt, Dm, rows, cols, sf):
 
 # ------------------------------------------------------------------ tcgen05 / TMEM GEMMs
 @pytest.mark.parametrize("M,N,K", [(50176, 192, 384), (50176, 768, 192), (1000, 192, 384), (128, 64, 64), (257, 256, 128),
-                                   (16384, 768, 192), (4097, 384, 256), (130, 1536, 256)])
+                                   (16384, 768, 192), (4097, 384, 256), (130, 1536, 256),
+                                   (50176, 192, 768), (25088, 768, 1536), (3000, 3072, 768), (129, 64, 2048)])
 def test_gemm_tcgen05_vs_torch(M, N, K):
     """C = A W^T on tcgen05 (fp32 accumulate in TMEM) against an fp64 matmul of the same bf16 operands."""
     from fastvim_b200 import ops
@@ -523,12 +524,16 @@ def test_gemm_tcgen05_vs_torch(M, N, K):
     a = (torch.randn(M, K) * 0.5).bfloat16().cuda()
     w = (torch.randn(N, K) * K ** -0.5).bfloat16().cuda()
     assert ops.gemm_supported(M, N, K)
-    assert not ops.gemm_supported(M, 384, 1536) and not ops.gemm_supported(M, N, 100)   # W block too large / K % 64
+    assert not ops.gemm_supported(M, N, 100) and not ops.gemm_supported(M, 100, K)   # K % 64, N % 64
     c = ops.gemm_bf16_tn(a, w)
     want = a.double() @ w.double().t()
     assert c.shape == (M, N) and c.dtype == torch.bfloat16
     err = (c.double() - want).abs().max().item() / want.abs().max().item()
     assert err < 4e-3, err          # one bf16 rounding of an fp32-accumulated result
+    bias = torch.randn(N).cuda()
+    cb = ops.gemm_bf16_tn(a, w, bias=bias)
+    errb = (cb.double() - (want + bias.double())).abs().max().item() / (want + bias.double()).abs().max().item()
+    assert errb < 4e-3, errb
     # strided A (the x half of an in_proj output) and a 3-D input
     az = torch.zeros(M, 2 * K, dtype=torch.bfloat16, device="cuda")
     az[:, :K] = a

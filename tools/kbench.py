@@ -122,6 +122,13 @@ def main():
             rep("in_proj(tcgen05)", t, Bt * L * (dm + 2 * D) * s)
             t = timeit(lambda i: ops.gemm_bf16_tn(y[i], w_out), nrot, a.iters)
             rep("out_proj(tcgen05)", t, Bt * L * (dm + D) * s)
+        pe_in = [torch.randn(Bt * L, 768, device=dev).to(dt) for _ in range(nrot)]
+        w_pe, b_pe = torch.randn(dm, 768, device=dev).to(dt), torch.randn(dm, device=dev)
+        t = timeit(lambda i: torch.nn.functional.linear(pe_in[i], w_pe, b_pe.to(dt)), nrot, a.iters)
+        rep("patch_embed(cublas)", t, Bt * L * (768 + dm) * s)
+        if dt == torch.bfloat16 and ops.gemm_supported(Bt * L, dm, 768):
+            t = timeit(lambda i: ops.gemm_bf16_tn(pe_in[i], w_pe, bias=b_pe), nrot, a.iters)
+            rep("patch_embed(tcgen05, streamed W)", t, Bt * L * (768 + dm) * s)
 
 
 if __name__ == "__main__":
