@@ -137,7 +137,7 @@ add_norm_bwd_kernel(int64_t rows, int cols, const T* __restrict__ dy, int64_t ld
             r[i] = make_float4((r[i].x - mean) * rstd, (r[i].y - mean) * rstd, (r[i].z - mean) * rstd, (r[i].w - mean) * rstd);
             if (lane + i * 32 >= nvec) r[i] = zero4();
             aw[i] = fma4(gy[i], r[i], aw[i]);
-            ab[i] = ab[i] + gy[i];
+            if (!RMS) ab[i] = ab[i] + gy[i];   // RMSNorm has no bias (ops/triton/layernorm.py:515-536)
             gy[i] = make_float4(gy[i].x * wv[i].x, gy[i].y * wv[i].y, gy[i].z * wv[i].z, gy[i].w * wv[i].w);
             c1 += (gy[i].x + gy[i].y) + (gy[i].z + gy[i].w);
             c2 += fmaf(gy[i].x, r[i].x, fmaf(gy[i].y, r[i].y, fmaf(gy[i].z, r[i].z, gy[i].w * r[i].w)));
@@ -156,15 +156,25 @@ add_norm_bwd_kernel(int64_t rows, int cols, const T* __restrict__ dy, int64_t ld
             }
         }
     }
+    // weight / bias gradients: sum the CTA's warps in shared memory first, then ONE atomic per CTA and column
+    // (per-warp atomics put ~9,000 serialized fp32 adds on each of the `cols` addresses)
+    __shared__ float4 red[NORM_WARPS][32];
+    const int wid = threadIdx.x >> 5;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-        const int v = lane + i * 32;
-        if (v < nvec) {
-            atomicAdd(dw + v * 4 + 0, aw[i].x); atomicAdd(dw + v * 4 + 1, aw[i].y);
-            atomicAdd(dw + v * 4 + 2, aw[i].z); atomicAdd(dw + v * 4 + 3, aw[i].w);
-            if (db) {
-                atomicAdd(db + v * 4 + 0, ab[i].x); atomicAdd(db + v * 4 + 1, ab[i].y);
-                atomicAdd(db + v * 4 + 2, ab[i].z); atomicAdd(db + v * 4 + 3, ab[i].w);
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1 && (RMS || !db)) break;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            __syncthreads();
+            red[wid][lane] = pass ? ab[i] : aw[i];
+            __syncthreads();
+            const int v = lane + i * 32;
+            if (wid == 0 && v < nvec) {
+                float4 t = red[0][lane];
+#pragma unroll
+                for (int k = 1; k < NORM_WARPS; ++k) t = t + red[k][lane];
+                float* dst = (pass ? db : dw) + v * 4;
+                atomicAdd(dst + 0, t.x); atomicAdd(dst + 1, t.y); atomicAdd(dst + 2, t.z); atomicAdd(dst + 3, t.w);
             }
         }
     }
@@ -187,7 +197,7 @@ static int launch_add_norm_bwd(int64_t rows, int cols, const T* dy, int64_t lddy
         else add_norm_bwd_kernel<T, NV_, false><<<grid, block, 0, st>>>(rows, cols, dy, lddy, dres_out, res_out, w, eps, dx, lddx, dres_in, dw, db);       \
         return finish_launch("add_norm_bwd");                                                                           \
     }
-    FV_NB_CASE(2) FV_NB_CASE(4) FV_NB_CASE(8) FV_NB_CASE(16)
+    FV_NB_CASE(2) FV_NB_CASE(3) FV_NB_CASE(4) FV_NB_CASE(6) FV_NB_CASE(8) FV_NB_CASE(12) FV_NB_CASE(16)
 #undef FV_NB_CASE
     return fail("fv_add_norm_bwd: cols %d > 2048 not supported", cols);
 }

@@ -268,6 +268,178 @@ scan_bwd_kernel(Geom g, int nplanes_ds, const T* __restrict__ u, const T* __rest
     }
 }
 
+// ---- short pooled sequences (Lp <= 16: every 224^2 model) ----------------------------------------------------------
+// The kernel above gives one thread a whole (channel, direction) chain and loops over the 16 states: 255 registers,
+// 8 warps per SM, 32-step dependent chains -- 1.76 ms per launch at FastVim-B (half of the training step).
+// Here a thread owns ONE state of one channel: 16 threads (a half-warp) per channel, 32 channels per CTA (512 threads).
+//   rows   half-warp lane i prepares pooled row i of its channel: u, dy (sum of the ds planes), delta = softplus(bias +
+//          W_dt . dt_i), shared with the other 15 lanes through shared memory (intra-warp: __syncwarp only);
+//   fwd    h_s = a_s h_{s-1} + delta u B_n, keeping a_s and h_s of the <= 16 steps in registers (no recompute, no checkpoints);
+//   rev    g_s = C_n dy + a_{s+1} g_{s+1}; per-step dB / dC are summed over the warp's two channels by one shuffle and
+//          parked per warp in shared memory, then summed over the 16 warps -> one plane per 32-channel CTA (deterministic);
+//          du / d(delta) partials are transposed through shared memory so that lane i sums the 16 states of row i;
+//   out    du, d(delta) staged per CTA and written as 64-byte row segments.
+constexpr int SBS_CH = 32, SBS_THREADS = SBS_CH * 16, SBS_LP = 16;
+
+template <typename T, int RT>
+__global__ void __launch_bounds__(SBS_THREADS, 2)
+scan_bwd_small_kernel(Geom g, int nplanes_ds, const T* __restrict__ u, const T* __restrict__ xdbl, int64_t ldxd, int R,
+                      const float* __restrict__ dtw, const float* __restrict__ dtb, const float* __restrict__ A,
+                      int a_is_log, const float* __restrict__ ds, T* __restrict__ du, T* __restrict__ ddelta,
+                      float* __restrict__ dbc_planes, float* __restrict__ dA, float* __restrict__ dbias) {
+    constexpr int N = 16, WROW = RT + 2 * N;
+    extern __shared__ __align__(16) float sbs[];
+    float* tile = sbs;                                   // [SBS_LP][WROW]      dt | B | C rows
+    float* rowd = tile + SBS_LP * WROW;                  // [SBS_CH][4][SBS_LP] per channel: delta, pre, u, dy
+    float* xch = rowd + SBS_CH * 4 * SBS_LP;             // [16 warps][2][SBS_LP][17]  per-warp exchange (du / ddelta partials)
+    float* part = xch + 16 * 2 * SBS_LP * 17;            // [16 warps][SBS_LP][32]     dB | dC partials of each warp
+    float* outs = part + 16 * SBS_LP * 32;               // [2][SBS_LP][SBS_CH]        staged du, ddelta
+    const int dir = blockIdx.z, b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = tid & 15, c = tid >> 4;                // state, channel within the CTA
+    const int hsel = (lane >> 4) & 1;                    // which of the warp's two channels
+    const int d = blockIdx.x * SBS_CH + c;
+    const bool live = d < g.D;
+    const int dd = live ? d : 0;
+    const int Lp = g.Lp;
+    const int64_t plane = (int64_t)g.B * Lp * g.D;
+    constexpr float LOG2E = 1.4426950408889634f;
+
+    const T* xd = xdbl + ((int64_t)dir * g.B + b) * Lp * ldxd;
+    for (int i = tid; i < Lp * WROW; i += SBS_THREADS) {
+        const int r = i / WROW, cc = i - r * WROW;
+        float v = 0.f;
+        if (cc < RT) {
+            if (cc < R) v = ld1(xd + (int64_t)r * ldxd + cc);
+        } else {
+            v = ld1(xd + (int64_t)r * ldxd + R + (cc - RT));
+        }
+        tile[i] = v;
+    }
+    const float a_raw = A[((int64_t)dir * g.D + dd) * N + n];
+    const float Anat = a_is_log ? -expf(a_raw) : a_raw, A2 = Anat * LOG2E;
+    __syncthreads();
+    // ---- row data of this channel: lane n prepares pooled row n
+    float* rd = rowd + c * 4 * SBS_LP;
+    {
+        float delta = 0.f, pre = 0.f, uv = 0.f, dyv = 0.f;
+        if (n < Lp) {
+            const float* row = tile + n * WROW;
+            const float* Wp = dtw + ((int64_t)dir * g.D + dd) * R;
+            pre = dtb[(int64_t)dir * g.D + dd];
+            for (int j = 0; j < R; ++j) pre = fmaf(__ldg(Wp + j), row[j], pre);
+            delta = softplus20(pre);
+            if (live) {
+                uv = ld1(u + dir * plane + ((int64_t)b * Lp + n) * g.D + dd);
+                const float* dsb = ds + ((int64_t)b * Lp + n) * g.D + dd;
+                for (int q = 0; q < nplanes_ds; ++q) dyv += dsb[q * plane];
+            }
+        }
+        rd[0 * SBS_LP + n] = delta;
+        rd[1 * SBS_LP + n] = pre;
+        rd[2 * SBS_LP + n] = uv;
+        rd[3 * SBS_LP + n] = dyv;
+    }
+    __syncwarp();
+    // ---- forward: states and decays of every step stay in registers
+    float hs[SBS_LP], as_[SBS_LP];
+    {
+        float h = 0.f;
+#pragma unroll
+        for (int s = 0; s < SBS_LP; ++s) {
+            hs[s] = 0.f;
+            as_[s] = 1.f;
+            if (s < Lp) {
+                const int i = dir ? Lp - 1 - s : s;
+                const float delta = rd[i];
+                as_[s] = ex2b(delta * A2);
+                h = fmaf(as_[s], h, delta * rd[2 * SBS_LP + i] * tile[i * WROW + RT + n]);
+                hs[s] = h;
+            }
+        }
+    }
+    // ---- reverse
+    float gn = 0.f, dAacc = 0.f;
+    float dul[SBS_LP], ddl[SBS_LP];
+    float* pw = part + warp * SBS_LP * 32;
+#pragma unroll
+    for (int s = SBS_LP - 1; s >= 0; --s) {
+        dul[s] = 0.f;
+        ddl[s] = 0.f;
+        if (s < Lp) {
+            const int i = dir ? Lp - 1 - s : s;
+            const float delta = rd[i], uv = rd[2 * SBS_LP + i], dyv = rd[3 * SBS_LP + i];
+            const float Bn = tile[i * WROW + RT + n], Cn = tile[i * WROW + RT + N + n];
+            const float gi = fmaf(Cn, dyv, gn);
+            const float hm1 = s > 0 ? hs[s - 1] : 0.f;
+            const float da_a = gi * hm1 * as_[s];
+            float dCv = dyv * hs[s], dBv = gi * delta * uv;
+            dul[s] = gi * delta * Bn;
+            ddl[s] = fmaf(gi * Bn, uv, da_a * Anat);
+            dAacc = fmaf(da_a, delta, dAacc);
+            gn = gi * as_[s];
+            dBv += __shfl_xor_sync(0xffffffffu, dBv, 16);   // the warp's two channels
+            dCv += __shfl_xor_sync(0xffffffffu, dCv, 16);
+            if (lane < 16) {
+                pw[i * 32 + n] = dBv;
+                pw[i * 32 + N + n] = dCv;
+            }
+        }
+    }
+    // ---- du / d(delta): sum over the 16 states of the channel (lane n ends up with row n)
+    float* xw = xch + (warp * 2 + hsel) * SBS_LP * 17;
+    float du_row = 0.f, dd_row = 0.f;
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll
+        for (int s = 0; s < SBS_LP; ++s) {
+            const int i = dir ? Lp - 1 - s : s;
+            if (s < Lp) xw[i * 17 + n] = pass ? ddl[s] : dul[s];
+        }
+        __syncwarp();
+        float acc = 0.f;
+        if (n < Lp) {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) acc += xw[n * 17 + k];
+        }
+        if (pass) dd_row = acc; else du_row = acc;
+        __syncwarp();
+    }
+    float dpre = 0.f;
+    if (n < Lp) {
+        const float pre = rd[1 * SBS_LP + n];
+        dpre = pre <= 20.f ? dd_row * sigmoidf_(pre) : dd_row;
+        outs[(0 * SBS_LP + n) * SBS_CH + c] = du_row;
+        outs[(1 * SBS_LP + n) * SBS_CH + c] = dpre;
+    }
+    // d(dt_bias) = sum over rows; dA (per state) over rows and images: fp32 atomics as in the reference (:467-477)
+    float bsum = dpre;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) bsum += __shfl_xor_sync(0xffffffffu, bsum, o);
+    if (live) {
+        atomicAdd(dA + ((int64_t)dir * g.D + d) * N + n, a_is_log ? dAacc * Anat : dAacc);
+        if (n == 0) atomicAdd(dbias + (int64_t)dir * g.D + d, bsum);
+    }
+    __syncthreads();
+    // ---- coalesced outputs
+    for (int t = tid; t < Lp * SBS_CH; t += SBS_THREADS) {
+        const int i = t / SBS_CH, cc = t - i * SBS_CH;
+        const int dch = blockIdx.x * SBS_CH + cc;
+        if (dch < g.D) {
+            const int64_t o = dir * plane + ((int64_t)b * Lp + i) * g.D + dch;
+            st1(du + o, outs[(0 * SBS_LP + i) * SBS_CH + cc]);
+            st1(ddelta + o, outs[(1 * SBS_LP + i) * SBS_CH + cc]);
+        }
+    }
+    float* outp = dbc_planes + (((int64_t)blockIdx.x * 2 + dir) * g.B + b) * Lp * 2 * N;
+    for (int t = tid; t < Lp * 32; t += SBS_THREADS) {
+        float acc = 0.f;
+#pragma unroll
+        for (int w = 0; w < 16; ++w) acc += part[w * SBS_LP * 32 + t];
+        outp[t] = acc;
+    }
+}
+
 // sums `nplanes` planes of `n` floats: out[i] = sum_p in[p*n + i] (adds to the cast when `accumulate`)
 template <typename TO>
 __global__ void reduce_planes_kernel(const float* __restrict__ in, int nplanes, int64_t n, TO* __restrict__ out) {
@@ -285,6 +457,23 @@ static int launch_scan_bwd(const Geom& g, int nplanes_ds, const T* u, const T* x
                            const float* dtw, const float* dtb, const float* A, int a_is_log, const float* ds, T* du,
                            T* ddelta, float* dbc, float* dA, float* dbias, cudaStream_t st) {
     FV_REQUIRE(N == 16, "fv_scan_bwd: d_state %d not supported (16)", N);
+    if (g.Lp <= SBS_LP) {  // short pooled sequences: one thread per (channel, state)
+        dim3 grid(ceil_div(g.D, SBS_CH), g.B, 2), block(SBS_THREADS);
+#define FV_SBS_CASE(RT_)                                                                                             \
+    if (R <= RT_) {                                                                                                  \
+        const size_t smem = sizeof(float) * ((size_t)SBS_LP * (RT_ + 32) + SBS_CH * 4 * SBS_LP + 16 * 2 * SBS_LP * 17 + \
+                                             16 * SBS_LP * 32 + 2 * SBS_LP * SBS_CH);                                \
+        auto kern = scan_bwd_small_kernel<T, RT_>;                                                                   \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+        FV_REQUIRE(e == cudaSuccess, "fv_scan_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));                \
+        kern<<<grid, block, smem, st>>>(g, nplanes_ds, u, xdbl, ldxd, R, dtw, dtb, A, a_is_log, ds, du, ddelta, dbc, \
+                                        dA, dbias);                                                                  \
+        return finish_launch("scan_bwd");                                                                            \
+    }
+        FV_SBS_CASE(12) FV_SBS_CASE(24) FV_SBS_CASE(48) FV_SBS_CASE(64)
+#undef FV_SBS_CASE
+        return fail("fv_scan_bwd: dt_rank %d > 64 not supported", R);
+    }
     const int nchunks = ceil_div(g.Lp, SB_LC);
     dim3 grid(ceil_div(g.D, SB_THREADS), g.B, 2), block(SB_THREADS);
 #define FV_SB_CASE(RT_)                                                                                              \
@@ -327,6 +516,13 @@ extern "C" int fv_scan_bwd(const fv_geom* g_, int dtype, int nplanes_ds, const v
         return launch_scan_bwd<bf16>(g, nplanes_ds, (const bf16*)u, (const bf16*)xdbl, ld_xdbl, dt_rank, dstate, dt_w,
                                      dt_bias, A, a_is_log, ds, (bf16*)du, (bf16*)ddelta, dbc_planes, dA, d_dt_bias, st);
     return fail("fv_scan_bwd: unsupported dtype %d", dtype);
+}
+
+/* number of [dB | dC] partial planes fv_scan_bwd writes for this geometry (the caller sizes dbc_planes with it) */
+extern "C" int fv_scan_bwd_planes(const fv_geom* g) {
+    if (!g || g->dim <= 0) return 0;
+    const int Lp = g->outer * g->inner;
+    return Lp <= fv::SBS_LP ? (g->dim + fv::SBS_CH - 1) / fv::SBS_CH : (g->dim + fv::SB_THREADS - 1) / fv::SB_THREADS;
 }
 
 extern "C" int fv_reduce_planes(int out_dtype, const float* in, int nplanes, int64_t n, void* out, void* stream) {

@@ -327,7 +327,8 @@ def scan_bwd(ds: Tensor, u: Tensor, xdbl: Tensor, geom: Geometry, dt_rank: int, 
     _check_cuda(ds, u, xdbl)
     _, B, Lp, D = u.shape
     assert u.is_contiguous() and ds.is_contiguous() and ds.dtype == torch.float32 and xdbl.stride(2) == 1
-    ncol = (D + 127) // 128
+    g = geom.c_struct(B, D)
+    ncol = int(_lib.lib().fv_scan_bwd_planes(C.byref(g)))
     du = torch.empty_like(u)
     ddelta = torch.empty_like(u)
     planes = torch.empty((ncol, 2, B * Lp, 2 * d_state), device=u.device, dtype=torch.float32)

@@ -199,9 +199,10 @@ int fv_gate_bwd(const fv_geom* g, int dtype, const void* x, const void* z, int64
 
 /* K2a-bwd.  ds (nplanes_ds, B, Lp, dim) fp32 (summed on load; the same gradient feeds both directions).
  * Outputs: du, ddelta (2, B, Lp, dim) dtype (ddelta = gradient of the dt_proj pre-activation);
- * dbc_planes (ceil(dim/128), 2, B*Lp, 2N) fp32 partial sums over 128-channel columns of [dB | dC]
- * (add them with fv_reduce_planes); dA (2, dim, N) (gradient of A_log if a_is_log), d_dt_bias (2, dim)
+ * dbc_planes (fv_scan_bwd_planes(g), 2, B*Lp, 2N) fp32 partial sums over channel columns of [dB | dC]
+ * (32-channel columns for Lp <= 16, 128-channel columns otherwise; add them with fv_reduce_planes); dA (2, dim, N) (gradient of A_log if a_is_log), d_dt_bias (2, dim)
  * fp32 accumulated. */
+int fv_scan_bwd_planes(const fv_geom* g);
 int fv_scan_bwd(const fv_geom* g, int dtype, int nplanes_ds, const void* u, const void* xdbl,
                 int64_t ld_xdbl, int dt_rank, int dstate, const float* dt_w, const float* dt_bias,
                 const float* A, int a_is_log, const float* ds, void* du, void* ddelta,
