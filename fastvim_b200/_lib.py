@@ -44,6 +44,11 @@ SIGNATURES = {
     "fv_causal_conv1d_fwd": [_I, _I, _I, _L, _P, _L, _L, _P, _P, _I, _P, _P],
     "fv_pool_bdl_fwd": [_I, _I, _I, _I, _I, _I, _P, _I, _F, _P, _P],
     "fv_bcast_skip_bdl_fwd": [_I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],
+    "fv_selective_scan_bwd_workspace_bytes": [_I, _I, _L, _I],
+    "fv_selective_scan_bwd": [_I, _I, _I, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P,
+                              _P, _P, _P, _L, _P],
+    "fv_causal_conv1d_bwd": [_I, _I, _I, _L, _P, _L, _L, _P, _P, _I, _P, _P, _L, _L, _P, _P, _P],
+    "fv_rowdot_bdl": [_I, _I, _I, _L, _P, _P, _P, _P],
     "fv_bwd_tiles_per_group": [_G, _I],
     "fv_gate_bwd": [_G, _I, _P, _P, _L, _L, _P, _L, _L, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P],
     "fv_scan_bwd_planes": [_G],

@@ -142,7 +142,106 @@ def add_norm_train(x, weight, bias, residual, eps, prenorm, residual_in_fp32, is
     return y, res_out
 
 
+# --------------------------------------------------------------------------- operator API on (batch, dim, L)
+class SelectiveScanFn(torch.autograd.Function):
+    """``SelectiveScanFn`` of the reference (``selective_scan_interface.py:12-102``) over fv_selective_scan_fwd/_bwd.
+    B, C arrive as (batch, groups, N, L); nothing but the inputs is saved (the backward re-runs the recurrence)."""
+
+    @staticmethod
+    def forward(ctx, u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state):
+        out, last = ops.selective_scan_fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus,
+                                           want_last_state=return_last_state)
+        ctx.save_for_backward(u, delta, A, B, C, D, z, delta_bias)
+        ctx.delta_softplus = delta_softplus
+        if return_last_state:
+            ctx.mark_non_differentiable(last)   # "the gradient of the last state is not considered" (:115-117)
+            return out, last
+        return out
+
+    @staticmethod
+    def backward(ctx, dout, *unused):
+        u, delta, A, B, C, D, z, delta_bias = ctx.saved_tensors
+        du, ddelta, dA, dB, dC, dD, dz, dbias = ops.selective_scan_bwd(
+            dout.to(u.dtype).contiguous(), u, delta, A, B, C, D, z, delta_bias, ctx.delta_softplus)
+        return du, ddelta, dA, dB, dC, dD, dz, dbias, None, None
+
+
+def _bc_4d(M, batch, dim, L, dt):
+    """B / C in any of the reference's shapes -> (batch, groups, N, L) contiguous, differentiably."""
+    if M.dim() == 2:      # (dim, N): constant over batch and time, one group per channel
+        return M.to(dt)[None, :, :, None].expand(batch, dim, M.shape[1], L).contiguous()
+    if M.dim() == 3:
+        M = M[:, None]
+    if M.dim() != 4:
+        raise ValueError(f"B / C must have 2, 3 or 4 dims, got {M.dim()}")
+    return M.to(dt).contiguous()
+
+
 def selective_scan_train(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state):
-    raise NotImplementedError(
-        "fastvim_b200: the backward of the (batch, dim, L) operator selective_scan_fn is not built yet; the "
-        "model training path goes through fastvim_b200.mixer.Mamba (MixerFn)")
+    """Differentiable ``selective_scan_fn``: dtype / layout preparation with ordinary torch ops, then SelectiveScanFn."""
+    batch, dim, L = u.shape
+    dt = u.dtype
+    f32 = torch.float32
+    return SelectiveScanFn.apply(
+        u.contiguous(), delta.to(dt).contiguous(), A.to(f32).contiguous(), _bc_4d(B, batch, dim, L, dt),
+        _bc_4d(C, batch, dim, L, dt), None if D is None else D.to(f32).contiguous(),
+        None if z is None else z.to(dt).contiguous(), None if delta_bias is None else delta_bias.to(f32).contiguous(),
+        bool(delta_softplus), bool(return_last_state))
+
+
+class CausalConv1dFn(torch.autograd.Function):
+    """Depthwise causal conv + SiLU on (batch, dim, L) (``causal_conv1d_fn``; call sites
+    ``selective_scan_interface.py:231-233, 496-498`` forward and ``:751-753`` backward)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, silu):
+        w = weight.reshape(weight.shape[0], -1)
+        ctx.save_for_backward(x, w, bias)
+        ctx.meta = (silu, weight.shape, weight.dtype, None if bias is None else bias.dtype)
+        return ops.causal_conv1d_fwd(x, w, bias, silu)
+
+    @staticmethod
+    def backward(ctx, dout):
+        x, w, bias = ctx.saved_tensors
+        silu, wshape, wdt, bdt = ctx.meta
+        dx, dw, db = ops.causal_conv1d_bwd(x, w, bias, dout.to(x.dtype).contiguous(), silu)
+        return dx, dw.reshape(wshape).to(wdt), (None if db is None else db.to(bdt)), None
+
+
+class PoolBdlFn(torch.autograd.Function):
+    """Mean pool (times scaling_factor) over the ``pool`` axis of a (batch, dim, outer*pool*inner) sequence
+    (``selective_scan_interface.py:503-508``); backward = broadcast of the pooled gradient (``:700-704``)."""
+
+    @staticmethod
+    def forward(ctx, xc, outer, pool, inner, scale):
+        ctx.meta = (outer, pool, inner, scale)
+        return ops.pool_bdl_fwd(xc, outer, pool, inner, "mean", scale)
+
+    @staticmethod
+    def backward(ctx, du):
+        outer, pool, inner, scale = ctx.meta
+        return ops.bcast_skip_bdl_fwd((du * (scale / pool)).contiguous(), None, None, outer, pool, inner), None, None, None, None
+
+
+class BcastSkipFn(torch.autograd.Function):
+    """out = repeat_interleave(s) + D * xc (``selective_scan_interface.py:570-571``); backward: ds = sum over the pool
+    axis of dout, dxc = D * dout, dD = sum dout * xc (``:636-642``)."""
+
+    @staticmethod
+    def forward(ctx, s, xc, Dskip, outer, pool, inner):
+        ctx.save_for_backward(xc, Dskip)
+        ctx.meta = (outer, pool, inner)
+        return ops.bcast_skip_bdl_fwd(s, xc, Dskip, outer, pool, inner)
+
+    @staticmethod
+    def backward(ctx, dout):
+        xc, Dskip = ctx.saved_tensors
+        outer, pool, inner = ctx.meta
+        dout = dout.contiguous()
+        ds = ops.pool_bdl_fwd(dout, outer, pool, inner, "mean", float(pool))   # mean * pool = sum
+        dxc = dD = None
+        if Dskip is not None:
+            zero_s = torch.zeros_like(ds)
+            dxc = ops.bcast_skip_bdl_fwd(zero_s, dout, Dskip, outer, pool, inner)   # D[d] * dout
+            dD = ops.rowdot_bdl(dout, xc).to(Dskip.dtype)
+        return ds, dxc, dD, None, None, None

@@ -132,6 +132,233 @@ selective_scan_fwd_kernel(int batch, int dim, int64_t L, int N, int groups, cons
     if (last_state && lane < N) last_state[((int64_t)b * dim + d) * N + lane] = carry;
 }
 
+
+// ---- backward ------------------------------------------------------------------------------------------------------
+// Replaces selective_scan_cuda.bwd (selective_scan.cpp:338-492, selective_scan_bwd_kernel.cuh:75-489) behind
+// SelectiveScanFn.backward (selective_scan_interface.py:59-102).  Same mapping as the forward: one warp per (b, d)
+// row, 128-step chunks of 32 lanes x 4 items.
+//   pass 1 (only when L > 128): forward sweep that records the state entering every chunk in `ws`
+//          (batch*dim, nchunks, N) fp32 -- the role of the reference's `x` checkpoint tensor, but written here, by
+//          the backward, so the inference forward never pays for it;
+//   pass 2: chunks in reverse.  Per state n the lane recomputes h over its 4 steps (forward warp scan of the affine
+//          maps, as in the forward), then runs the adjoint recurrence G_t = a_t (C_t dy_t + G_{t+1}) as a REVERSE
+//          warp scan (shfl_down) of the maps (a_t, a_t C_t dy_t); G_{t+1} entering the chunk from the right is the
+//          carry of state n in lane n.  With g_t = C_t dy_t + G_{t+1} (the gradient reaching h_t):
+//              d delta_t += g_t (h_{t-1} a_t A_n + B_t u_t)     dA_n += g_t h_{t-1} a_t delta_t
+//              dB_t[n]   += g_t delta_t u_t                     dC_t[n] += dy_t h_t
+//              du_t      += g_t delta_t B_t  (+ dy_t D)         dD += dy_t u_t
+//          and, with z: dy_t = dout_t silu(z_t), dz_t = dout_t y_t silu'(z_t) with y recomputed here (the reference
+//          saves `out` for this, selective_scan_interface.py:58).
+// dB / dC are summed over the channels of a group with fp32 vector atomics into caller-zeroed (batch, G, N, L)
+// buffers (the reference does the same, bwd_kernel.cuh:438-462); dA, dD, d(delta_bias) by one atomic per row.
+template <typename T>
+__global__ void __launch_bounds__(SS_WARPS * 32)
+selective_scan_bwd_kernel(int batch, int dim, int64_t L, int N, int groups, const T* __restrict__ u,
+                          const T* __restrict__ delta, const float* __restrict__ A, const T* __restrict__ Bm,
+                          const T* __restrict__ Cm, const float* __restrict__ Dp, const T* __restrict__ z,
+                          const float* __restrict__ dbias, int softplus, const T* __restrict__ dout,
+                          T* __restrict__ du, T* __restrict__ ddelta, float* __restrict__ dA, float* __restrict__ dB,
+                          float* __restrict__ dC, float* __restrict__ dD, T* __restrict__ dz,
+                          float* __restrict__ ddbias, float* __restrict__ ws) {
+    constexpr int CH = 32 * SS_ITEMS;
+    const int lane = threadIdx.x & 31;
+    const int d = blockIdx.x * SS_WARPS + (threadIdx.x >> 5);
+    const int b = blockIdx.y;
+    if (d >= dim) return;
+    const int grp = d / (dim / groups);
+    const int64_t rowi = (int64_t)b * dim + d, row = rowi * L;
+    const T* ur = u + row;
+    const T* dr = delta + row;
+    const T* zr = z ? z + row : nullptr;
+    const T* gr = dout + row;
+    const int64_t bc0 = ((int64_t)b * groups + grp) * N * L;
+    const T* Br = Bm + bc0;
+    const T* Cr = Cm + bc0;
+    const bool vec = (L % 4 == 0);
+    constexpr float LOG2E = 1.4426950408889634f;
+    const float Alane = lane < N ? A[(int64_t)d * N + lane] : 0.f;
+    const float A2lane = Alane * LOG2E;
+    const float bias = dbias ? dbias[d] : 0.f;
+    const float Dd = Dp ? Dp[d] : 0.f;
+    const int nchunks = (int)((L + CH - 1) / CH);
+    float* wsr = ws ? ws + rowi * nchunks * N : nullptr;
+
+    // ---- pass 1: state entering each chunk
+    if (nchunks > 1) {
+        float carry = 0.f;
+        for (int c = 0; c < nchunks - 1; ++c) {
+            if (lane < N) wsr[(int64_t)c * N + lane] = carry;
+            const int64_t t0 = (int64_t)c * CH + lane * SS_ITEMS;
+            float uv[SS_ITEMS], dv[SS_ITEMS];
+            load_items(ur, L, t0, vec, uv);
+            load_items(dr, L, t0, vec, dv);
+#pragma unroll
+            for (int k = 0; k < SS_ITEMS; ++k) {
+                float x = dv[k] + bias;
+                if (softplus) x = softplus20(x);
+                dv[k] = x;  // every chunk but the last is full
+            }
+            for (int n = 0; n < N; ++n) {
+                const float A2 = __shfl_sync(0xffffffffu, A2lane, n);
+                const float hin = __shfl_sync(0xffffffffu, carry, n);
+                float bv[SS_ITEMS];
+                load_items(Br + (int64_t)n * L, L, t0, vec, bv);
+                float P = 1.f, S = 0.f;
+#pragma unroll
+                for (int k = 0; k < SS_ITEMS; ++k) {
+                    const float a = ex2f_(dv[k] * A2);
+                    S = fmaf(a, S, dv[k] * bv[k] * uv[k]);
+                    P *= a;
+                }
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float Pp = __shfl_up_sync(0xffffffffu, P, o);
+                    const float Sp = __shfl_up_sync(0xffffffffu, S, o);
+                    if (lane >= o) {
+                        S = fmaf(P, Sp, S);
+                        P *= Pp;
+                    }
+                }
+                const float hlast = __shfl_sync(0xffffffffu, fmaf(P, hin, S), 31);
+                if (lane == n) carry = hlast;
+            }
+        }
+        if (lane < N) wsr[(int64_t)(nchunks - 1) * N + lane] = carry;
+        __syncwarp();
+    }
+
+    // ---- pass 2: chunks in reverse
+    float Gcarry = 0.f, dAacc = 0.f, dDacc = 0.f, dbacc = 0.f;
+    for (int c = nchunks - 1; c >= 0; --c) {
+        const int64_t t0 = (int64_t)c * CH + lane * SS_ITEMS;
+        const bool full4 = vec && t0 + SS_ITEMS <= L;
+        float uv[SS_ITEMS], dv[SS_ITEMS], raw[SS_ITEMS], gv[SS_ITEMS], zv[SS_ITEMS], dy[SS_ITEMS];
+        float ddl[SS_ITEMS], dul[SS_ITEMS], ys[SS_ITEMS];
+        load_items(ur, L, t0, vec, uv);
+        load_items(dr, L, t0, vec, raw);
+        load_items(gr, L, t0, vec, gv);
+        if (zr) load_items(zr, L, t0, vec, zv);
+#pragma unroll
+        for (int k = 0; k < SS_ITEMS; ++k) {
+            raw[k] += bias;
+            const float x = softplus ? softplus20(raw[k]) : raw[k];
+            dv[k] = (t0 + k < L) ? x : 0.f;
+            dy[k] = zr ? gv[k] * silu_exact(zv[k]) : gv[k];
+            ddl[k] = 0.f;
+            dul[k] = dy[k] * Dd;
+            ys[k] = 0.f;
+        }
+        const float cin = (nchunks > 1 && lane < N) ? wsr[(int64_t)c * N + lane] : 0.f;
+        for (int n = 0; n < N; ++n) {
+            const float A2 = __shfl_sync(0xffffffffu, A2lane, n);
+            const float An = __shfl_sync(0xffffffffu, Alane, n);
+            const float hin = __shfl_sync(0xffffffffu, cin, n);
+            const float Gin = __shfl_sync(0xffffffffu, Gcarry, n);
+            float bv[SS_ITEMS], cv[SS_ITEMS], a[SS_ITEMS], ck[SS_ITEMS], hm1[SS_ITEMS];
+            load_items(Br + (int64_t)n * L, L, t0, vec, bv);
+            load_items(Cr + (int64_t)n * L, L, t0, vec, cv);
+            // forward maps of the lane's steps, and the adjoint maps (reverse order)
+            float P = 1.f, S = 0.f;
+#pragma unroll
+            for (int k = 0; k < SS_ITEMS; ++k) {
+                a[k] = ex2f_(dv[k] * A2);
+                S = fmaf(a[k], S, dv[k] * bv[k] * uv[k]);
+                P *= a[k];
+                ck[k] = cv[k] * dy[k];
+            }
+            float Sr = 0.f;
+#pragma unroll
+            for (int k = SS_ITEMS - 1; k >= 0; --k) Sr = a[k] * (ck[k] + Sr);
+            float Pf = P, Sf = S, Pb = P, Sb = Sr;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float Pp = __shfl_up_sync(0xffffffffu, Pf, o);
+                const float Sp = __shfl_up_sync(0xffffffffu, Sf, o);
+                const float Pn = __shfl_down_sync(0xffffffffu, Pb, o);
+                const float Sn = __shfl_down_sync(0xffffffffu, Sb, o);
+                if (lane >= o) {
+                    Sf = fmaf(Pf, Sp, Sf);
+                    Pf *= Pp;
+                }
+                if (lane + o < 32) {
+                    Sb = fmaf(Pb, Sn, Sb);
+                    Pb *= Pn;
+                }
+            }
+            const float Pe = __shfl_up_sync(0xffffffffu, Pf, 1), Se = __shfl_up_sync(0xffffffffu, Sf, 1);
+            float h = lane == 0 ? hin : fmaf(Pe, hin, Se);            // state entering the lane's first step
+            const float Pq = __shfl_down_sync(0xffffffffu, Pb, 1), Sq = __shfl_down_sync(0xffffffffu, Sb, 1);
+            float G = lane == 31 ? Gin : fmaf(Pq, Gin, Sq);          // adjoint entering the lane's last step from the right
+            const float Gnew = __shfl_sync(0xffffffffu, fmaf(Pb, Gin, Sb), 0);
+            if (lane == n) Gcarry = Gnew;
+            float hk[SS_ITEMS];
+#pragma unroll
+            for (int k = 0; k < SS_ITEMS; ++k) {
+                hm1[k] = h;
+                h = fmaf(a[k], h, dv[k] * bv[k] * uv[k]);
+                hk[k] = h;
+                ys[k] = fmaf(cv[k], h, ys[k]);
+            }
+            float dAp = 0.f, dBk[SS_ITEMS], dCk[SS_ITEMS];
+#pragma unroll
+            for (int k = SS_ITEMS - 1; k >= 0; --k) {
+                const float g = ck[k] + G;
+                const float tmp = g * hm1[k] * a[k];
+                ddl[k] = fmaf(tmp, An, fmaf(g * bv[k], uv[k], ddl[k]));
+                dAp = fmaf(tmp, dv[k], dAp);
+                dBk[k] = g * dv[k] * uv[k];
+                dul[k] = fmaf(g * dv[k], bv[k], dul[k]);
+                dCk[k] = dy[k] * hk[k];
+                G = a[k] * g;
+            }
+            dAp = warp_sum(dAp);
+            if (lane == n) dAacc += dAp;
+            float* dBr = dB + bc0 + (int64_t)n * L + t0;
+            float* dCr = dC + bc0 + (int64_t)n * L + t0;
+            if (full4) {
+                atomicAdd(reinterpret_cast<float4*>(dBr), make_float4(dBk[0], dBk[1], dBk[2], dBk[3]));
+                atomicAdd(reinterpret_cast<float4*>(dCr), make_float4(dCk[0], dCk[1], dCk[2], dCk[3]));
+            } else {
+#pragma unroll
+                for (int k = 0; k < SS_ITEMS; ++k)
+                    if (t0 + k < L) {
+                        atomicAdd(dBr + k, dBk[k]);
+                        atomicAdd(dCr + k, dCk[k]);
+                    }
+            }
+        }
+        float dzv[SS_ITEMS];
+#pragma unroll
+        for (int k = 0; k < SS_ITEMS; ++k) {
+            const bool in = t0 + k < L;
+            if (zr) dzv[k] = gv[k] * fmaf(Dd, uv[k], ys[k]) * dsilu(zv[k]);
+            if (in) dDacc = fmaf(dy[k], uv[k], dDacc);
+            if (softplus && raw[k] <= 20.f) ddl[k] *= sigmoidf_(raw[k]);
+            if (in) dbacc += ddl[k];
+        }
+        if (full4) {
+            st4(du + row + t0, make_float4(dul[0], dul[1], dul[2], dul[3]));
+            st4(ddelta + row + t0, make_float4(ddl[0], ddl[1], ddl[2], ddl[3]));
+            if (zr) st4(dz + row + t0, make_float4(dzv[0], dzv[1], dzv[2], dzv[3]));
+        } else {
+#pragma unroll
+            for (int k = 0; k < SS_ITEMS; ++k)
+                if (t0 + k < L) {
+                    st1(du + row + t0 + k, dul[k]);
+                    st1(ddelta + row + t0 + k, ddl[k]);
+                    if (zr) st1(dz + row + t0 + k, dzv[k]);
+                }
+        }
+    }
+    if (lane < N) atomicAdd(dA + (int64_t)d * N + lane, dAacc);
+    dDacc = warp_sum(dDacc);
+    dbacc = warp_sum(dbacc);
+    if (lane == 0) {
+        if (dD) atomicAdd(dD + d, dDacc);
+        if (ddbias) atomicAdd(ddbias + d, dbacc);
+    }
+}
+
 }  // namespace fv
 
 extern "C" int fv_selective_scan_fwd(int dtype, int batch, int dim, int64_t L, int dstate, int groups,
@@ -154,4 +381,38 @@ extern "C" int fv_selective_scan_fwd(int dtype, int batch, int dim, int64_t L, i
     else
         return fail("fv_selective_scan_fwd: unsupported dtype %d", dtype);
     return finish_launch("selective_scan_fwd");
+}
+
+extern "C" int64_t fv_selective_scan_bwd_workspace_bytes(int batch, int dim, int64_t L, int dstate) {
+    if (batch <= 0 || dim <= 0 || L <= 0 || dstate <= 0) return 0;
+    const int64_t nchunks = (L + 32 * fv::SS_ITEMS - 1) / (32 * fv::SS_ITEMS);
+    return nchunks > 1 ? (int64_t)batch * dim * nchunks * dstate * 4 : 0;
+}
+
+extern "C" int fv_selective_scan_bwd(int dtype, int batch, int dim, int64_t L, int dstate, int groups,
+                                     const void* u, const void* delta, const float* A, const void* B,
+                                     const void* C, const float* D, const void* z, const float* delta_bias,
+                                     int delta_softplus, const void* dout, void* du, void* ddelta, float* dA,
+                                     float* dB, float* dC, float* dD, void* dz, float* ddelta_bias,
+                                     void* workspace, int64_t workspace_bytes, void* stream) {
+    using namespace fv;
+    FV_REQUIRE(u && delta && A && B && C && dout && du && ddelta && dA && dB && dC, "fv_selective_scan_bwd: null pointer");
+    FV_REQUIRE(batch > 0 && dim > 0 && L > 0, "fv_selective_scan_bwd: bad shape");
+    FV_REQUIRE(dstate >= 1 && dstate <= 32, "fv_selective_scan_bwd: d_state %d not in [1, 32]", dstate);
+    FV_REQUIRE(groups >= 1 && dim % groups == 0, "fv_selective_scan_bwd: dim %d not divisible by groups %d", dim, groups);
+    FV_REQUIRE(batch <= 65535, "fv_selective_scan_bwd: batch > 65535");
+    FV_REQUIRE((!D || dD) && (!z || dz) && (!delta_bias || ddelta_bias), "fv_selective_scan_bwd: missing gradient buffer");
+    const int64_t need = fv_selective_scan_bwd_workspace_bytes(batch, dim, L, dstate);
+    FV_REQUIRE(need == 0 || (workspace && workspace_bytes >= need), "fv_selective_scan_bwd: workspace of %lld bytes required",
+               (long long)need);
+    FV_REQUIRE(L % 4 != 0 || (((uintptr_t)dB | (uintptr_t)dC) % 16) == 0, "fv_selective_scan_bwd: dB / dC must be 16-byte aligned");
+    dim3 grid(ceil_div(dim, SS_WARPS), batch), block(SS_WARPS * 32);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == FV_F32)
+        selective_scan_bwd_kernel<float><<<grid, block, 0, st>>>(batch, dim, L, dstate, groups, (const float*)u, (const float*)delta, A, (const float*)B, (const float*)C, D, (const float*)z, delta_bias, delta_softplus, (const float*)dout, (float*)du, (float*)ddelta, dA, dB, dC, dD, (float*)dz, ddelta_bias, (float*)workspace);
+    else if (dtype == FV_BF16)
+        selective_scan_bwd_kernel<bf16><<<grid, block, 0, st>>>(batch, dim, L, dstate, groups, (const bf16*)u, (const bf16*)delta, A, (const bf16*)B, (const bf16*)C, D, (const bf16*)z, delta_bias, delta_softplus, (const bf16*)dout, (bf16*)du, (bf16*)ddelta, dA, dB, dC, dD, (bf16*)dz, ddelta_bias, (float*)workspace);
+    else
+        return fail("fv_selective_scan_bwd: unsupported dtype %d", dtype);
+    return finish_launch("selective_scan_bwd");
 }

@@ -5,7 +5,8 @@ Same names, argument meaning and error behaviour as the reference's public funct
 ``mamba_inner_fn_no_out_proj_withoutZ`` :1684-1713,
 ``FastVim_mamba_inner_fn_no_out_proj_withoutZ`` :1716-1753), operating on the reference's
 ``(batch, dim, seqlen)`` layout, so the reference's op-level tests read the same against this
-module.  Everything runs on ``libfastvim_b200.so``; there is no PyTorch fallback.
+module.  Everything runs on ``libfastvim_b200.so``; there is no PyTorch fallback.  All functions are
+differentiable (``fastvim_b200.autograd``: SelectiveScanFn and friends over the ``fv_*_bwd`` kernels).
 """
 from __future__ import annotations
 
@@ -50,14 +51,10 @@ def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_
     return (out, last) if return_last_state else out
 
 
-# --------------------------------------------------------------------------- fused "inner" functions (forward)
-def _no_grad_only(name, *tensors):
-    if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors):
-        raise NotImplementedError(
-            f"fastvim_b200.interface.{name}: forward only.  Training goes through fastvim_b200.mixer.Mamba "
-            "(autograd.MixerFn), which implements the backward of the live module branch")
-
-
+# --------------------------------------------------------------------------- fused "inner" functions
+# Differentiable: every kernel call below is a torch.autograd.Function over a forward / backward kernel pair
+# (autograd.CausalConv1dFn, PoolBdlFn, SelectiveScanFn, BcastSkipFn); the x_proj / dt_proj contractions are torch
+# matmuls (cuBLAS, as in the reference's backward, selective_scan_interface.py:698-737), differentiated by autograd.
 def _inner(x, z, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B, C, D, delta_bias,
            B_proj_bias, C_proj_bias, delta_softplus):
     """conv1d(+SiLU) -> x_proj -> dt_proj -> selective scan (u = conv output, D skip, z gate) on (batch, dim, L)
@@ -65,7 +62,7 @@ def _inner(x, z, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A
     batch, dim, L = x.shape
     R, N = delta_proj_weight.shape[1], A.shape[-1]
     act = x.dtype
-    xc = ops.causal_conv1d_fwd(x, conv1d_weight.reshape(dim, -1), conv1d_bias, True)            # :231-233
+    xc = fv_autograd.CausalConv1dFn.apply(x, conv1d_weight, conv1d_bias, True)                     # :231-233
     # x_proj / dt_proj are GEMMs (cuBLAS through torch), in the activation dtype as under autocast (:221-226)
     x_dbl = torch.nn.functional.linear(xc.transpose(1, 2).reshape(batch * L, dim), x_proj_weight.to(act))   # :237-239
     delta = (delta_proj_weight.to(act) @ x_dbl[:, :R].t()).reshape(dim, batch, L).permute(1, 0, 2).contiguous()  # :240-243
@@ -85,7 +82,6 @@ def _inner(x, z, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A
 def mamba_inner_fn_no_out_proj(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, B=None, C=None,
                                D=None, delta_bias=None, B_proj_bias=None, C_proj_bias=None, delta_softplus=True):
     """xz: (batch, 2*dim, L) -> (batch, dim, L).  Reference :1652-1681."""
-    _no_grad_only("mamba_inner_fn_no_out_proj", xz, conv1d_weight, x_proj_weight, delta_proj_weight, A, D)
     if A.is_complex():
         raise NotImplementedError("complex A is not used by any FastVim model and is not implemented")
     if xz.stride(-1) != 1:
@@ -99,7 +95,6 @@ def mamba_inner_fn_no_out_proj_withoutZ(x, conv1d_weight, conv1d_bias, x_proj_we
                                         C=None, D=None, delta_bias=None, B_proj_bias=None, C_proj_bias=None,
                                         delta_softplus=True):
     """x: (batch, dim, L) -> (batch, dim, L), no z gate.  Reference :1684-1713."""
-    _no_grad_only("mamba_inner_fn_no_out_proj_withoutZ", x, conv1d_weight, x_proj_weight, delta_proj_weight, A, D)
     if A.is_complex():
         raise NotImplementedError("complex A is not used by any FastVim model and is not implemented")
     if x.stride(-1) != 1:
@@ -115,7 +110,6 @@ def FastVim_mamba_inner_fn_no_out_proj_withoutZ(x, conv1d_weight, conv1d_bias, x
     """x: (batch, dim, L) -> (batch, dim, L): conv -> mean over ``num_of_col`` -> x_proj / dt_proj -> scan over the
     pooled sequence -> repeat_interleave + D * conv.  Reference :1716-1753, forward :452-603.  As in the reference
     (:503-508) only ``collapse_method="mean"`` is defined for this function."""
-    _no_grad_only("FastVim_mamba_inner_fn_no_out_proj_withoutZ", x, conv1d_weight, x_proj_weight, delta_proj_weight, A, D)
     if A.is_complex():
         raise NotImplementedError("complex A is not used by any FastVim model and is not implemented")
     if collapse_method != "mean":
@@ -133,8 +127,8 @@ def FastVim_mamba_inner_fn_no_out_proj_withoutZ(x, conv1d_weight, conv1d_bias, x
     rows = L // num_of_col
     R, N = delta_proj_weight.shape[1], A.shape[-1]
     act = x.dtype
-    xc = ops.causal_conv1d_fwd(x, conv1d_weight.reshape(dim, -1), conv1d_bias, True)            # :496-498
-    u = ops.pool_bdl_fwd(xc, rows, num_of_col, 1, "mean", float(scaling_factor))                # :503-508
+    xc = fv_autograd.CausalConv1dFn.apply(x, conv1d_weight, conv1d_bias, True)                     # :496-498
+    u = fv_autograd.PoolBdlFn.apply(xc, rows, num_of_col, 1, float(scaling_factor))                # :503-508
     x_dbl = torch.nn.functional.linear(u.transpose(1, 2).reshape(batch * rows, dim), x_proj_weight.to(act))  # :512-514
     delta = (delta_proj_weight.to(act) @ x_dbl[:, :R].t()).reshape(dim, batch, rows).permute(1, 0, 2).contiguous()
     Bm = x_dbl[:, R:R + N]
@@ -146,4 +140,4 @@ def FastVim_mamba_inner_fn_no_out_proj_withoutZ(x, conv1d_weight, conv1d_bias, x
     Bm = Bm.reshape(batch, rows, N).transpose(1, 2)[:, None].contiguous()
     Cm = Cm.reshape(batch, rows, N).transpose(1, 2)[:, None].contiguous()
     s = selective_scan_fn(u, delta, A, Bm, Cm, None, None, delta_bias, delta_softplus)          # :556-566
-    return ops.bcast_skip_bdl_fwd(s, xc, D, rows, num_of_col, 1)                                # :570-571
+    return fv_autograd.BcastSkipFn.apply(s, xc, D, rows, num_of_col, 1)                            # :570-571

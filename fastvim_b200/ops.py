@@ -290,6 +290,53 @@ def bcast_skip_bdl_fwd(s: Tensor, xc: Optional[Tensor], Dskip: Optional[Tensor],
     return out
 
 
+def selective_scan_bwd(dout: Tensor, u: Tensor, delta: Tensor, A: Tensor, B: Tensor, Cm: Tensor, D: Optional[Tensor],
+                       z: Optional[Tensor], delta_bias: Optional[Tensor], delta_softplus: bool):
+    """Backward of the operator-API scan.  Returns (du, ddelta, dA, dB, dC, dD, dz, ddelta_bias): du / ddelta / dz in the
+    input dtype, dA / dD / ddelta_bias fp32, dB / dC (batch, groups, N, L) in the input dtype after fp32 accumulation."""
+    _check_cuda(dout, u, delta, A, B, Cm)
+    batch, dim, L = u.shape
+    groups, N = B.shape[1], B.shape[2]
+    for t in (dout, u, delta, B, Cm, z):
+        assert t is None or (t.is_contiguous() and t.dtype == u.dtype)
+    f32 = dict(device=u.device, dtype=torch.float32)
+    du, ddelta = torch.empty_like(u), torch.empty_like(u)
+    dz = torch.empty_like(u) if z is not None else None
+    dA = torch.zeros((dim, N), **f32)
+    dB, dC = torch.zeros(B.shape, **f32), torch.zeros(B.shape, **f32)
+    dD = torch.zeros(dim, **f32) if D is not None else None
+    dbias = torch.zeros(dim, **f32) if delta_bias is not None else None
+    nbytes = int(_lib.lib().fv_selective_scan_bwd_workspace_bytes(batch, dim, L, N))
+    ws = torch.empty(max(nbytes, 4) // 4, **f32)
+    _lib.call("fv_selective_scan_bwd", _dt(u), batch, dim, L, N, groups, _p(u), _p(delta), _p(A), _p(B), _p(Cm), _p(D),
+              _p(z), _p(delta_bias), int(delta_softplus), _p(dout), _p(du), _p(ddelta), _p(dA), _p(dB), _p(dC), _p(dD),
+              _p(dz), _p(dbias), _p(ws), ws.numel() * 4, _stream(u))
+    return du, ddelta, dA, dB.to(u.dtype), dC.to(u.dtype), dD, dz, dbias
+
+
+def causal_conv1d_bwd(x: Tensor, weight: Tensor, bias: Optional[Tensor], dout: Tensor, silu: bool = True):
+    """x (B, D, L) unit stride along L, dout (B, D, L) contiguous -> dx (B, D, L) contiguous, dw (D, 4) fp32, db (D) fp32 | None."""
+    _check_cuda(x, weight, dout)
+    B, D, L = x.shape
+    assert x.stride(2) == 1 and weight.shape == (D, 4) and dout.is_contiguous() and dout.dtype == x.dtype
+    dx = torch.empty((B, D, L), device=x.device, dtype=x.dtype)
+    dw = torch.zeros((D, 4), device=x.device, dtype=torch.float32)
+    db = torch.zeros(D, device=x.device, dtype=torch.float32) if bias is not None else None
+    _lib.call("fv_causal_conv1d_bwd", _dt(x), B, D, L, _p(x), x.stride(0), x.stride(1), _p(_f32c(weight)), _p(_f32c(bias)),
+              int(silu), _p(dout), _p(dx), dx.stride(0), dx.stride(1), _p(dw), _p(db), _stream(x))
+    return dx, dw, db
+
+
+def rowdot_bdl(a: Tensor, c: Tensor) -> Tensor:
+    """(B, D, L) x (B, D, L) contiguous -> (D,) fp32: sum over batch and L of a * c."""
+    _check_cuda(a, c)
+    B, D, L = a.shape
+    assert a.is_contiguous() and c.is_contiguous() and a.dtype == c.dtype and a.shape == c.shape
+    out = torch.zeros(D, device=a.device, dtype=torch.float32)
+    _lib.call("fv_rowdot_bdl", _dt(a), B, D, L, _p(a), _p(c), _p(out), _stream(a))
+    return out
+
+
 # --------------------------------------------------------------------------- backward wrappers
 def bwd_tiles_per_group(geom: Geometry, batch: int, dim: int, dtype: torch.dtype) -> int:
     g = geom.c_struct(batch, dim)

@@ -177,6 +177,32 @@ int fv_pool_bdl_fwd(int dtype, int batch, int dim, int outer, int pool, int inne
 int fv_bcast_skip_bdl_fwd(int dtype, int batch, int dim, int outer, int pool, int inner, const void* s,
                           const void* xc, const float* Dskip, void* out, void* stream);
 
+/* ---- operator API, backward ------------------------------------------------------------------
+ * fv_selective_scan_bwd replaces selective_scan_cuda.bwd (selective_scan.cpp:338-492; kernel
+ * selective_scan_bwd_kernel.cuh:75-489) behind SelectiveScanFn.backward (selective_scan_interface.py:59-102).
+ * Same tensors as fv_selective_scan_fwd plus dout (batch, dim, L).  Outputs: du, ddelta, dz (batch, dim, L) dtype
+ * (dz NULL iff z NULL); dA (dim, N), dD (dim), d_delta_bias (dim) fp32 and dB, dC (batch, groups, N, L) FP32 --
+ * all five ACCUMULATED (caller zero-fills; the caller casts dB / dC to the input dtype as the reference does,
+ * selective_scan.cpp:470-472).  ddelta is the gradient of the delta INPUT (before bias and softplus).
+ * No forward checkpoint is needed: the kernel re-runs the recurrence and keeps the states entering each
+ * 128-step chunk in `workspace` (fv_selective_scan_bwd_workspace_bytes; 0 when L <= 128).
+ * fv_causal_conv1d_bwd replaces causal_conv1d_cuda.causal_conv1d_bwd (call site :751-753): dx strided like x,
+ * dw (dim, 4) / dbias (dim) fp32 accumulated.  fv_rowdot_bdl: out[d] += sum_{b,l} a[b,d,l] c[b,d,l] (the D-skip
+ * gradient of the fused functions, :640-642). */
+int64_t fv_selective_scan_bwd_workspace_bytes(int batch, int dim, int64_t L, int dstate);
+int fv_selective_scan_bwd(int dtype, int batch, int dim, int64_t L, int dstate, int groups,
+                          const void* u, const void* delta, const float* A, const void* B,
+                          const void* C, const float* D, const void* z, const float* delta_bias,
+                          int delta_softplus, const void* dout, void* du, void* ddelta, float* dA,
+                          float* dB, float* dC, float* dD, void* dz, float* d_delta_bias,
+                          void* workspace, int64_t workspace_bytes, void* stream);
+int fv_causal_conv1d_bwd(int dtype, int batch, int dim, int64_t L, const void* x, int64_t x_bstride,
+                         int64_t x_dstride, const float* w, const float* bias, int silu, const void* dout,
+                         void* dx, int64_t dx_bstride, int64_t dx_dstride, float* dw, float* dbias,
+                         void* stream);
+int fv_rowdot_bdl(int dtype, int batch, int dim, int64_t L, const void* a, const void* c, float* out,
+                  void* stream);
+
 /* ======================= backward (training) entry points ==============================
  * Replace SelectiveScanFn.backward / selective_scan_cuda.bwd (selective_scan_interface.py:59-102,
  * csrc/selective_scan/selective_scan.cpp:338-492), FastVim_MambaInnerFnNoOutProj_withoutZ.backward

@@ -43,7 +43,7 @@ def selective_scan_oracle(u, delta, A, B, C, D=None, z=None, delta_bias=None,
     u, delta, z: (Bt, Dm, L); A: (Dm, N); B, C: (Dm, N) | (Bt, N, L) | (Bt, G, N, L).
     """
     dtype_in = u.dtype
-    cd = compute_dtype
+    cd = torch.float64 if u.dtype == torch.float64 else compute_dtype   # fp64 inputs: fp64 gradient reference
     u_, delta_ = u.to(cd), delta.to(cd)
     if delta_bias is not None:
         delta_ = delta_ + delta_bias.to(cd)[..., None]

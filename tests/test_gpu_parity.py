@@ -484,9 +484,6 @@ def test_mamba_inner_fn_no_out_proj_vs_reference_golden():
     want_noz = O.mamba_inner_oracle(g["xz"][:, :Dm], g["conv_w"], g["conv_b"], g["x_proj_w"], g["dt_proj_w"], g["A"],
                                     None, None, g["D"], g["delta_bias"], True, has_z=False)
     assert_close(out_noz, want_noz, 1e-4, "mamba_inner_fn_no_out_proj_withoutZ")
-    with pytest.raises(NotImplementedError):
-        mamba_inner_fn_no_out_proj(c("xz").requires_grad_(), c("conv_w"), c("conv_b"), c("x_proj_w"), c("dt_proj_w"),
-                                   c("A"), None, None, c("D"), c("delta_bias"))
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
@@ -575,3 +572,142 @@ def test_channel_mixer_jumpcp_shape_vs_oracle(dtype, order):
     want = O.mixer_oracle(h, p, ts, layout=layout)
     assert out.dtype == dtype
     assert_close(out, want, TOL[dtype], f"channel mixer {order} {dtype}")
+
+
+# ------------------------------------------------------------------ operator API, backward
+@pytest.mark.parametrize("name", ["scan_L14_g1_full", "scan_L14_g2_full", "scan_L128_g1_full", "scan_L128_g2_full",
+                                  "scan_L300_g1_full", "scan_L300_g2_full", "scan_L64_plain", "scan_L64_constBC"])
+def test_selective_scan_fn_bwd_vs_reference_golden(name):
+    """Gradients of selective_scan_fn against the reference's own selective_scan_ref autograd (tests/golden), with the
+    tolerances of the reference's test (tests/ops/test_selective_scan.py:53-59, 170-190) and BASELINE's 1e-4 relative."""
+    from fastvim_b200.interface import selective_scan_fn
+
+    g = load_golden(name)
+    leaves = {k: (v.cuda().requires_grad_() if v is not None else None) for k, v in g["inputs"].items()}
+    out, last = selective_scan_fn(leaves["u"], leaves["delta"], leaves["A"], leaves["B"], leaves["C"], leaves["D"],
+                                  z=leaves["z"], delta_bias=leaves["delta_bias"], delta_softplus=g["delta_softplus"],
+                                  return_last_state=True)
+    assert not last.requires_grad
+    assert_close(out, g["out"], 1e-4, "out")
+    out.backward(g["dout"].cuda())
+    for k, want in g["grads"].items():
+        got = leaves[k].grad
+        assert got is not None and got.shape == want.shape and got.dtype == want.dtype, k
+        rtol, atol = (6e-4, 2e-3) if k in ("u", "delta", "z") else (1e-3, 2e-3)
+        assert torch.allclose(got.cpu(), want, rtol=rtol, atol=atol), f"d{k}: {(got.cpu() - want).abs().max()}"
+        assert_close(got, want, 1e-4, "d" + k)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("Bt,Dm,L,N,G,has_z,has_D,has_bias,softplus", [
+    (2, 4, 4096, 8, 1, True, True, True, True),       # the reference test's longest sequence (32 chunks)
+    (2, 8, 1031, 16, 2, False, True, True, True),     # ragged tail, groups
+    (3, 384, 14, 16, 1, False, False, True, True),    # FastVim-T pooled scan
+    (2, 96, 128, 16, 1, True, True, False, False),    # 2048^2 pooled length, exactly one chunk
+    (1, 12, 129, 4, 3, True, False, True, True),      # one element into the second chunk
+])
+def test_selective_scan_fn_bwd_vs_oracle(dtype, Bt, Dm, L, N, G, has_z, has_D, has_bias, softplus):
+    """du, ddelta, dA, dB, dC, dD, dz, ddelta_bias against fp64 autograd through the oracle on the same (rounded) inputs."""
+    from fastvim_b200.interface import selective_scan_fn
+
+    torch.manual_seed(0)
+    r = lambda *s: torch.randn(*s).to(dtype)
+    ins = dict(u=r(Bt, Dm, L), delta=(0.5 * torch.rand(Bt, Dm, L)).to(dtype), A=-0.5 * torch.rand(Dm, N) - 0.05,
+               B=r(Bt, G, N, L) if G > 1 else r(Bt, N, L), C=r(Bt, G, N, L) if G > 1 else r(Bt, N, L),
+               D=torch.randn(Dm) if has_D else None, z=r(Bt, Dm, L) if has_z else None,
+               delta_bias=0.5 * torch.rand(Dm) if has_bias else None)
+    dout = r(Bt, Dm, L)
+
+    def run(fn, conv):
+        lv = {k: (conv(v).requires_grad_() if v is not None else None) for k, v in ins.items()}
+        out = fn(lv["u"], lv["delta"], lv["A"], lv["B"], lv["C"], lv["D"], z=lv["z"], delta_bias=lv["delta_bias"],
+                 delta_softplus=softplus)
+        out.backward(conv(dout))
+        return out.detach(), {k: v.grad for k, v in lv.items() if v is not None}
+
+    out_w, gw = run(O.selective_scan_oracle, lambda t: t.double().clone())
+    out_g, gg = run(selective_scan_fn, lambda t: t.cuda())
+    assert_close(out_g, out_w, TOL[dtype], "out")
+    for k, want in gw.items():
+        assert gg[k].dtype == ins[k].dtype and gg[k].shape == want.shape, k
+        assert_close(gg[k], want, TOL[dtype], "d" + k)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("Bt,Dm,L", [(2, 16, 40), (3, 64, 196), (1, 8, 7), (2, 32, 1030)])
+@pytest.mark.parametrize("silu", [True, False])
+def test_causal_conv1d_bdl_backward(dtype, Bt, Dm, L, silu):
+    from fastvim_b200 import ops
+
+    torch.manual_seed(0)
+    xz = torch.randn(Bt, 2 * Dm, L).to(dtype)          # x is a strided view of xz, as in mamba_inner_fn
+    w, b, dout = torch.randn(Dm, 4) * 0.5, torch.randn(Dm) * 0.5, torch.randn(Bt, Dm, L).to(dtype)
+    x64 = xz[:, :Dm].double().requires_grad_()
+    w64, b64 = w.double().requires_grad_(), b.double().requires_grad_()
+    O.causal_conv1d_oracle(x64, w64, b64, activation="silu" if silu else None).backward(dout.double())
+    dx, dw, db = ops.causal_conv1d_bwd(xz.cuda()[:, :Dm], w.cuda(), b.cuda(), dout.cuda(), silu)
+    assert_close(dx, x64.grad, TOL[dtype], "dx")
+    assert_close(dw, w64.grad, TOL[dtype], "dw")
+    assert_close(db, b64.grad, TOL[dtype], "db")
+
+
+def _inner_grads(fn, tensors, dout, conv, names):
+    lv = [conv(t).requires_grad_() if t is not None else None for t in tensors]
+    out = fn(*lv)
+    out.backward(conv(dout))
+    return out.detach(), {n: v.grad for n, v in zip(names, lv) if v is not None}
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("has_z", [True, False])
+def test_mamba_inner_fn_backward_vs_oracle(dtype, has_z):
+    """mamba_inner_fn_no_out_proj[_withoutZ] gradients (MambaInnerFnNoOutProj.backward, selective_scan_interface.py:332-449)."""
+    from fastvim_b200 import interface as I
+
+    torch.manual_seed(0)
+    Bt, Dm, L, N = 2, 64, 77, 16
+    R = 4
+    xz = torch.randn(Bt, 2 * Dm if has_z else Dm, L).to(dtype)
+    cw, cb = torch.randn(Dm, 1, 4) * 0.5, torch.randn(Dm) * 0.5
+    xw, dw = torch.randn(R + 2 * N, Dm) * Dm ** -0.5, torch.randn(Dm, R) * R ** -0.5
+    A = -torch.exp(torch.log(torch.arange(1, N + 1).float()).repeat(Dm, 1))
+    Dp, dbias = torch.ones(Dm) + 0.1 * torch.randn(Dm), torch.rand(Dm) * 3.0 - 4.0
+    dout = torch.randn(Bt, Dm, L).to(dtype)
+    names = ["xz", "conv_w", "conv_b", "x_proj_w", "dt_proj_w", "A", "D", "delta_bias"]
+    tensors = [xz, cw, cb, xw, dw, A, Dp, dbias]
+    ours = I.mamba_inner_fn_no_out_proj if has_z else I.mamba_inner_fn_no_out_proj_withoutZ
+    f_o = lambda a, b, c, d, e, f, g, h: O.mamba_inner_oracle(a, b, c, d, e, f, None, None, g, h, True, has_z=has_z)
+    f_g = lambda a, b, c, d, e, f, g, h: ours(a, b, c, d, e, f, None, None, g, h, delta_softplus=True)
+    out_w, gw = _inner_grads(f_o, tensors, dout, lambda t: t.double().clone(), names)
+    out_g, gg = _inner_grads(f_g, tensors, dout, lambda t: t.cuda(), names)
+    assert_close(out_g, out_w, TOL[dtype], "out")
+    for k, want in gw.items():
+        assert gg[k].shape == want.shape, k
+        assert_close(gg[k], want, TOL[dtype] * (2 if dtype == torch.bfloat16 else 1), "d" + k)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("Bt,Dm,rows,cols,sf", [(2, 64, 14, 14, 1.0), (3, 32, 5, 9, 0.5)])
+def test_fastvim_inner_fn_backward_vs_oracle(dtype, Bt, Dm, rows, cols, sf):
+    """FastVim_mamba_inner_fn_no_out_proj_withoutZ gradients (selective_scan_interface.py:605-776)."""
+    from fastvim_b200.interface import FastVim_mamba_inner_fn_no_out_proj_withoutZ as fn
+
+    torch.manual_seed(0)
+    R, N, L = max(4, Dm // 16), 16, rows * cols
+    x = torch.randn(Bt, Dm, L).to(dtype)
+    cw, cb = torch.randn(Dm, 1, 4) * 0.5, torch.randn(Dm) * 0.5
+    xw, dw = torch.randn(R + 2 * N, Dm) * Dm ** -0.5, torch.randn(Dm, R) * R ** -0.5
+    A = -torch.exp(torch.log(torch.arange(1, N + 1).float()).repeat(Dm, 1))
+    Dp, dbias = torch.ones(Dm) + 0.1 * torch.randn(Dm), torch.rand(Dm) * 3.0 - 4.0
+    dout = torch.randn(Bt, Dm, L).to(dtype)
+    names = ["x", "conv_w", "conv_b", "x_proj_w", "dt_proj_w", "A", "D", "delta_bias"]
+    tensors = [x, cw, cb, xw, dw, A, Dp, dbias]
+    f_o = lambda a, b, c, d, e, f, g, h: O.fastvim_inner_oracle(a, b, c, d, e, f, g, h, cols, sf)
+    f_g = lambda a, b, c, d, e, f, g, h: fn(a, b, c, d, e, f, None, None, g, h, None, None, True, cols, "mean", sf,
+                                           (-1, Dm, rows, cols))
+    out_w, gw = _inner_grads(f_o, tensors, dout, lambda t: t.double().clone(), names)
+    out_g, gg = _inner_grads(f_g, tensors, dout, lambda t: t.cuda(), names)
+    assert_close(out_g, out_w, TOL[dtype], "out")
+    for k, want in gw.items():
+        assert gg[k].shape == want.shape, k
+        assert_close(gg[k], want, TOL[dtype] * (2 if dtype == torch.bfloat16 else 1), "d" + k)
