@@ -58,8 +58,12 @@ class Mamba(_SpatialMamba):
             from . import autograd as fv_autograd
 
             if geom.inner != 1:
-                raise NotImplementedError("fastvim_b200: the backward kernels cover plain (outer, pool, 1) layouts; "
-                                          "Channel-First training is not built (Spatial-First is)")
+                # Channel-First: (rows, cols, tpp) pooling, which the fused MixerFn backward kernels do not walk;
+                # run operator by operator (conv / pool / scan / broadcast kernels, each with its backward)
+                from . import composed
+
+                return composed.mixer_forward_composed(self, hidden_states, act_dtype, outer=geom.outer,
+                                                       pool=geom.pool, inner=geom.inner)
             out = fv_autograd.mixer_forward_train(self, hidden_states, geom, act_dtype)
         else:
             out = self._forward_inference(hidden_states.to(act_dtype), geom, act_dtype)

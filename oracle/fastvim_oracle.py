@@ -134,7 +134,7 @@ def broadcast_oracle(s, outer, pool, inner=1):
 def mixer_oracle(hidden, p: Dict[str, Tensor], token_size: Sequence[int], *,
                  d_state=16, dt_rank=None, use_norm_after_ssm=True,
                  collapse_method="mean", scaling_factor=1.0, ln_eps=1e-5,
-                 return_intermediates=False, layout=None):
+                 return_intermediates=False, layout=None, ids_keep=None):
     """FastVim ``Mamba.forward`` live branch, ``mamba_simple_faster.py:181-457``
     (the branch every shipped config takes, ``use_fast_path=False``, :269-453).
 
@@ -146,6 +146,12 @@ def mixer_oracle(hidden, p: Dict[str, Tensor], token_size: Sequence[int], *,
     """
     Bt, L, _ = hidden.shape
     rows, cols = token_size
+    if ids_keep is not None:
+        # FastMaskVim (``mamba_simple_masked_faster.py:167-325``): the sequence is the kept tokens; pooling is a
+        # scatter-add by ``ids_keep // cols`` divided by the constant ``cols`` (:208-215, 376-416); broadcast is a
+        # gather (:261-264).  The b-direction uses the SAME (un-flipped) row ids on the flipped sequence (:297-300).
+        assert layout is None and collapse_method == "mean" and scaling_factor == 1
+        return _masked_mixer_oracle(hidden, p, rows, cols, ids_keep, d_state, dt_rank, use_norm_after_ssm, ln_eps)
     # ``layout`` = (outer, pool, inner) generalises the pooling to the ChannelVim variants
     # (mamba_simple_channel_faster.py:225-256, 325-340): Channel-First (rows, cols, tpp), Spatial-First
     # (tpp*rows, cols, 1).  Default: FastVim (rows, cols, 1).  Below, ``rows`` = pooled length, ``cols`` = pool.
@@ -197,6 +203,47 @@ def mixer_oracle(hidden, p: Dict[str, Tensor], token_size: Sequence[int], *,
     if return_intermediates:
         inter.update(xz=xz, xc=xc, xc_b=xc_b, u=u, u_b=u_b, gated=g)
         return o, inter
+    return o
+
+
+def _masked_mixer_oracle(hidden, p, rows, cols, ids_keep, d_state, dt_rank, use_norm_after_ssm, ln_eps):
+    Bt, L, _ = hidden.shape
+    Dm = p["in_proj.weight"].shape[0] // 2
+    R = dt_rank if dt_rank is not None else p["dt_proj.weight"].shape[1]
+    N = d_state
+    cd = hidden.dtype if hidden.dtype == torch.float64 else torch.float32
+    xz = F.linear(hidden, p["in_proj.weight"], p.get("in_proj.bias")).transpose(1, 2)   # :175-182
+    x, z = xz.chunk(2, dim=1)                                                            # :194
+    x_flip = x.flip([-1])                                                                # :196
+    xc = causal_conv1d_oracle(x, p["conv1d.weight"][:, 0], p.get("conv1d.bias"))         # :198-203
+    xc_b = causal_conv1d_oracle(x_flip, p["conv1d_b.weight"][:, 0], p.get("conv1d_b.bias"))  # :204-209
+    rid = ids_keep // cols                                                               # :211
+
+    def row_means(t):                                                                    # :376-416
+        sums = torch.zeros(Bt, rows, Dm, dtype=cd)
+        sums = sums.scatter_add(1, rid[:, :, None].expand(-1, -1, Dm), t.transpose(1, 2).to(cd))
+        return (sums / cols).transpose(1, 2).to(t.dtype)
+
+    def direction(t, tag):
+        u_c = row_means(t)
+        x_dbl = F.linear(u_c.transpose(1, 2).reshape(Bt * rows, Dm), p[f"x_proj{tag}.weight"])  # :232-234
+        dt, Bm, Cm = torch.split(x_dbl, [R, N, N], dim=-1)
+        dt = (p[f"dt_proj{tag}.weight"] @ dt.t()).reshape(Dm, Bt, rows).permute(1, 0, 2)        # :239-241
+        Bm = Bm.reshape(Bt, rows, N).transpose(1, 2)
+        Cm = Cm.reshape(Bt, rows, N).transpose(1, 2)
+        A = -torch.exp(p["A_log" if tag == "" else "A_b_log"].float().to(hidden.dtype))
+        s = selective_scan_oracle(u_c, dt, A, Bm, Cm, D=None, z=None, delta_bias=p[f"dt_proj{tag}.bias"].float(),
+                                  delta_softplus=True, compute_dtype=cd)                          # :249-260
+        y = torch.gather(s, 2, rid[:, None, :].expand(-1, Dm, -1))                                # :261-263
+        return y + p["D" + tag].float().to(y.dtype)[None, :, None] * t                            # :264
+
+    out, out_b = direction(xc, ""), direction(xc_b, "_b")
+    y = (out + out_b.flip([-1])).transpose(1, 2) / 2                                     # :306
+    if use_norm_after_ssm:
+        y = F.layer_norm(y, (Dm,), p["layernorm.weight"], p["layernorm.bias"], ln_eps)   # :305
+    o = F.linear(y * F.silu(z.transpose(1, 2)), p["out_proj.weight"], p.get("out_proj.bias"))
+    if "gamma" in p:
+        o = o * p["gamma"]
     return o
 
 

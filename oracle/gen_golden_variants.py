@@ -1,0 +1,100 @@
+"""TEST INFRASTRUCTURE ONLY -- golden vectors for the FastMaskVim and Channel-First FastChannelVim mixers.
+
+Run in the build container (needs /root/reference):  python oracle/gen_golden_variants.py
+
+Imports the UNMODIFIED reference modules ``mamba_simple_masked_faster{,_v2}.Mamba_masked`` and
+``mamba_simple_channel_faster.Mamba`` (through ``oracle/ref_loader.py``), runs them forward AND backward on CPU on
+seeded inputs, asserts that ``oracle/fastvim_oracle.py`` reproduces outputs and every gradient, and writes
+``tests/golden/mmixer_*.pt`` / ``cmixer_*_grads.pt`` (kept separate from gen_golden.py so the earlier vectors are
+not rewritten).
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import fastvim_oracle as O  # noqa: E402
+from ref_loader import load_reference  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+
+
+def relerr(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+def detrivialise(m):
+    with torch.no_grad():
+        for k, v in m.named_parameters():
+            if k in ("D", "D_b", "layernorm.weight", "A_log", "A_b_log", "layernorm.bias"):
+                v.add_(0.1 * torch.randn_like(v))
+
+
+def run_case(module, oracle_fn, h, extra):
+    h = h.clone().requires_grad_()
+    out = module(h, extra)
+    torch.manual_seed(1)
+    g = torch.randn_like(out)
+    out.backward(g)
+    params = {k: v.detach().clone() for k, v in module.named_parameters()}
+    grads = {k: v.grad.detach().clone() for k, v in module.named_parameters()}
+    p2 = {k: v.clone().requires_grad_() for k, v in params.items()}
+    h2 = h.detach().clone().requires_grad_()
+    out_o = oracle_fn(h2, p2)
+    out_o.backward(g)
+    errs = {"out": relerr(out_o, out), "dh": relerr(h2.grad, h.grad)}
+    errs.update({"d" + k: relerr(p2[k].grad, grads[k]) for k in grads})
+    worst = max(errs, key=errs.get)
+    assert errs[worst] < 5e-5, (worst, errs[worst])
+    return dict(params=params, hidden=h.detach(), dout=g, out=out.detach(), dhidden=h.grad.detach(), grads=grads), errs[worst]
+
+
+def main():
+    ref = load_reference()
+    manifest_path = os.path.join(GOLD, "manifest.json")
+    manifest = json.load(open(manifest_path))
+
+    print("[m] FastMaskVim mixer (mamba_simple_masked_faster.py:167-325 and _v2)")
+    for name, mod, d_model, ts, keep, norm in (("mmixer_d32_4x6_keep10", ref.msmf, 32, (4, 6), 10, True),
+                                               ("mmixer_d32_6x4_keep24_full", ref.msmf, 32, (6, 4), 24, True),
+                                               ("mmixer_v2_d48_14x14_keep49_nonorm", ref.msmf2, 48, (14, 14), 49, False)):
+        torch.manual_seed(0)
+        m = mod.Mamba_masked(d_model, token_size=list(ts), layer_idx=0, use_norm_after_ssm=norm)
+        detrivialise(m)
+        Bt, Ltot = 2, ts[0] * ts[1]
+        # kept ids sorted ascending, as random_masking produces them (models/mae/..._v2.py:740-774)
+        ids = torch.stack([torch.randperm(Ltot)[:keep].sort().values for _ in range(Bt)])
+        h = torch.randn(Bt, keep, d_model)
+        case, e = run_case(m, lambda hh, pp: O.mixer_oracle(hh, pp, ts, use_norm_after_ssm=norm, ids_keep=ids), h, ids)
+        case.update(token_size=ts, ids_keep=ids, use_norm_after_ssm=norm)
+        path = os.path.join(GOLD, name + ".pt")
+        torch.save(case, path)
+        manifest[name] = dict(oracle_vs_ref=e, bytes=os.path.getsize(path))
+        print(f"  {name}: oracle_vs_ref {e:.2e}")
+
+    print("[c] FastChannelVim mixer with gradients (mamba_simple_channel_faster.py:176-420)")
+    for name, d_model, ts, tpp, order in (("cmixer_d32_4x6_t3_channel_first_grads", 32, (4, 6), 3, "Channel-First"),
+                                          ("cmixer_d32_6x4_t2_spatial_first_grads", 32, (6, 4), 2, "Spatial-First")):
+        torch.manual_seed(0)
+        m = ref.mscf.Mamba(d_model, token_size=list(ts), layer_idx=0, scan_order=order)
+        detrivialise(m)
+        h = torch.randn(2, ts[0] * ts[1] * tpp, d_model)
+        layout = (ts[0], ts[1], tpp) if order == "Channel-First" else (tpp * ts[0], ts[1], 1)
+        case, e = run_case(m, lambda hh, pp: O.mixer_oracle(hh, pp, ts, layout=layout), h, tpp)
+        case.update(token_size=ts, tokens_per_patch=tpp, scan_order=order)
+        path = os.path.join(GOLD, name + ".pt")
+        torch.save(case, path)
+        manifest[name] = dict(oracle_vs_ref=e, bytes=os.path.getsize(path))
+        print(f"  {name}: oracle_vs_ref {e:.2e}")
+
+    with open(manifest_path, "w") as f:
+        json.dump(manifest, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

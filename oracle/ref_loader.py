@@ -177,7 +177,10 @@ def load_reference():
 
     import mamba_ssm.modules.mamba_simple_channel_faster as mscf  # noqa: E402  (FastChannelVim mixer)
 
-    ns = types.SimpleNamespace(ssi=ssi, msf=msf, mscf=mscf, ln=ln, fastvim=fastvim)
+    import mamba_ssm.modules.mamba_simple_masked_faster as msmf  # noqa: E402  (FastMaskVim encoder mixer)
+    import mamba_ssm.modules.mamba_simple_masked_faster_v2 as msmf2  # noqa: E402
+
+    ns = types.SimpleNamespace(ssi=ssi, msf=msf, mscf=mscf, msmf=msmf, msmf2=msmf2, ln=ln, fastvim=fastvim)
     _loaded = ns
     return ns
 

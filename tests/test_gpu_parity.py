@@ -711,3 +711,74 @@ def test_fastvim_inner_fn_backward_vs_oracle(dtype, Bt, Dm, rows, cols, sf):
     for k, want in gw.items():
         assert gg[k].shape == want.shape, k
         assert_close(gg[k], want, TOL[dtype] * (2 if dtype == torch.bfloat16 else 1), "d" + k)
+
+
+# ------------------------------------------------------------------ FastMaskVim mixer, Channel-First training
+@pytest.mark.parametrize("name", ["mmixer_d32_4x6_keep10", "mmixer_d32_6x4_keep24_full", "mmixer_v2_d48_14x14_keep49_nonorm"])
+def test_masked_mixer_fwd_bwd_vs_reference_golden_fp32(name):
+    """Mamba_masked (kept-token sequences, scatter pooling by ids_keep // cols) forward and every gradient against the
+    reference's own module (tests/golden, oracle/gen_golden_variants.py)."""
+    from fastvim_b200.mixer_masked import Mamba_masked
+
+    g = load_golden(name)
+    m = Mamba_masked(g["params"]["in_proj.weight"].shape[1], token_size=list(g["token_size"]), layer_idx=0,
+                     use_norm_after_ssm=g["use_norm_after_ssm"])
+    m.load_state_dict(g["params"], strict=True)
+    m = m.cuda().train()
+    h = g["hidden"].cuda().requires_grad_()
+    out = m(h, g["ids_keep"].cuda())
+    out.backward(g["dout"].cuda())
+    assert_close(out, g["out"], 1e-4, "out")
+    assert_close(h.grad, g["dhidden"], 1e-4, "dhidden")
+    got = dict(m.named_parameters())
+    for k, want in g["grads"].items():
+        assert_close(got[k].grad, want, 1e-4, "d" + k)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_masked_mixer_mae_shape_vs_oracle(dtype):
+    """FastMaskVim-B-like encoder mixer at MAE shape: 14 x 14 grid, 75 % masked (49 kept tokens), batch 4."""
+    from fastvim_b200.mixer_masked import Mamba_masked
+
+    d_model, ts, keep, Bt = 192, (14, 14), 49, 4
+    p = O.random_mixer_params(d_model, seed=3)
+    torch.manual_seed(0)
+    ids = torch.stack([torch.randperm(ts[0] * ts[1])[:keep].sort().values for _ in range(Bt)])
+    h, dout = torch.randn(Bt, keep, d_model), torch.randn(Bt, keep, d_model)
+    m = Mamba_masked(d_model, token_size=list(ts), layer_idx=0)
+    m.load_state_dict(p, strict=True)
+    m = m.cuda().train()
+    hc = h.cuda().requires_grad_()
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        out = m(hc, ids.cuda())
+    out.backward(dout.cuda().to(out.dtype))
+    p64 = {k: v.clone().double().requires_grad_() for k, v in p.items()}
+    h64 = h.double().requires_grad_()
+    want = O.mixer_oracle(h64, p64, ts, ids_keep=ids)
+    want.backward(dout.double())
+    tol = TOL[dtype]
+    assert_close(out, want, tol, "out")
+    assert_close(hc.grad, h64.grad, tol, "dhidden")
+    got = dict(m.named_parameters())
+    for k, v in p64.items():
+        assert_close(got[k].grad, v.grad, tol if dtype == torch.float32 else 2 * tol, "d" + k)
+
+
+@pytest.mark.parametrize("name", ["cmixer_d32_4x6_t3_channel_first_grads", "cmixer_d32_6x4_t2_spatial_first_grads"])
+def test_channel_mixer_training_vs_reference_golden_fp32(name):
+    """FastChannelVim mixer gradients (Channel-First runs operator by operator, Spatial-First through MixerFn)."""
+    from fastvim_b200.mixer_channel import Mamba
+
+    g = load_golden(name)
+    m = Mamba(g["params"]["in_proj.weight"].shape[1], token_size=list(g["token_size"]), layer_idx=0,
+              scan_order=g["scan_order"])
+    m.load_state_dict(g["params"], strict=True)
+    m = m.cuda().train()
+    h = g["hidden"].cuda().requires_grad_()
+    out = m(h, g["tokens_per_patch"])
+    out.backward(g["dout"].cuda())
+    assert_close(out, g["out"], 1e-4, "out")
+    assert_close(h.grad, g["dhidden"], 1e-4, "dhidden")
+    got = dict(m.named_parameters())
+    for k, want in g["grads"].items():
+        assert_close(got[k].grad, want, 1e-4, "d" + k)

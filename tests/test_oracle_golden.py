@@ -8,7 +8,7 @@ import pytest
 import torch
 
 import fastvim_oracle as O
-from util import GOLDEN, load_golden, relerr
+from util import GOLDEN, assert_close, load_golden, relerr
 
 SCAN_CASES = ["scan_L14_g1_full", "scan_L14_g2_full", "scan_L128_g1_full", "scan_L128_g2_full",
               "scan_L300_g1_full", "scan_L300_g2_full", "scan_L64_plain", "scan_L64_constBC"]
@@ -103,3 +103,45 @@ def test_channel_mixer_oracle_matches_reference_vector(name):
     layout = (ts[0], ts[1], tpp) if g["scan_order"] == "Channel-First" else (tpp * ts[0], ts[1], 1)
     out = O.mixer_oracle(g["hidden"], g["params"], ts, layout=layout)
     assert relerr(out, g["out"]) < 2e-5
+
+
+MASKED = ["mmixer_d32_4x6_keep10", "mmixer_d32_6x4_keep24_full", "mmixer_v2_d48_14x14_keep49_nonorm"]
+
+
+def _oracle_grads(g, **kw):
+    p = {k: v.clone().requires_grad_() for k, v in g["params"].items()}
+    h = g["hidden"].clone().requires_grad_()
+    out = O.mixer_oracle(h, p, g["token_size"], **kw)
+    out.backward(g["dout"])
+    return out.detach(), h.grad, {k: v.grad for k, v in p.items()}
+
+
+@pytest.mark.parametrize("name", MASKED)
+def test_masked_mixer_oracle_matches_reference_vectors(name):
+    """FastMaskVim: oracle forward + every gradient against the reference's own Mamba_masked (v1 and v2 modules)."""
+    g = load_golden(name)
+    out, dh, grads = _oracle_grads(g, use_norm_after_ssm=g["use_norm_after_ssm"], ids_keep=g["ids_keep"])
+    assert_close(out, g["out"], 5e-5, "out")
+    assert_close(dh, g["dhidden"], 5e-5, "dhidden")
+    for k, want in g["grads"].items():
+        assert_close(grads[k], want, 5e-5, "d" + k)
+
+
+def test_masked_mixer_with_all_tokens_kept_equals_fastvim_mixer():
+    """the masked definition coincides with the FastVim mixer when nothing is masked."""
+    g = load_golden("mmixer_d32_6x4_keep24_full")
+    assert torch.equal(g["ids_keep"], torch.arange(24)[None].expand(2, -1))
+    plain = O.mixer_oracle(g["hidden"], g["params"], g["token_size"])
+    assert_close(plain, g["out"], 5e-5, "masked(all kept) vs plain")
+
+
+@pytest.mark.parametrize("name", ["cmixer_d32_4x6_t3_channel_first_grads", "cmixer_d32_6x4_t2_spatial_first_grads"])
+def test_channel_mixer_oracle_gradients_match_reference_vectors(name):
+    g = load_golden(name)
+    tpp, ts = g["tokens_per_patch"], g["token_size"]
+    layout = (ts[0], ts[1], tpp) if g["scan_order"] == "Channel-First" else (tpp * ts[0], ts[1], 1)
+    out, dh, grads = _oracle_grads(g, layout=layout)
+    assert_close(out, g["out"], 5e-5, "out")
+    assert_close(dh, g["dhidden"], 5e-5, "dhidden")
+    for k, want in g["grads"].items():
+        assert_close(grads[k], want, 5e-5, "d" + k)
