@@ -17,6 +17,8 @@
 // TT <= 8 tokens of one pooled group, all channels (4 per thread); x and e rows (+3 halo rows each side)
 // staged with cp.async; G_f / G_b live in thread-private shared-memory columns (no barrier between the
 // two passes); weight / bias gradients accumulate in registers and leave with one atomicAdd per CTA.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tiles.cuh"
 
@@ -144,6 +146,217 @@ conv_pool_bwd_kernel(Geom g, int64_t ntiles, int tiles_per_img, int tiles_per_gr
     }
 }
 
+// ---- streaming variant (default) -------------------------------------------------------------------------------------
+// The tiled kernel above stages TT + 6 token rows of ALL channels per tile: at dim 1536 that is 184 KB of shared memory
+// for TT = 4 -- one 384-thread CTA per SM, 2.5x halo re-reads and a full stage -> wait -> compute serialisation
+// (465 us per launch at FastVim-B, 12x its HBM time).  But the conv only couples tokens, never channels, so a thread
+// that owns TWO channels can simply walk a run of consecutive tokens with everything in registers:
+//   at front position f (x[f], e[f] just arrived) it forms G_f[f] from x[f-3..f], G_b[f-3] from the SAME four x rows,
+//   dx[f-3] from G_f[f-3..f] and G_b[f-6..f-3], and the weight-gradient products of both -- four 4-deep register windows
+//   (x, dxc_b, G_f, G_b), statically indexed by unrolling the walk by 4; no shared-memory data, no barrier in the walk.
+// Loads run 4 tokens ahead of their use through a register queue (8 independent 4-byte loads in flight per thread).
+// A CTA (<= 256 channel pairs) walks runs of <= 56 tokens (3-token halo each side: ~12 % extra L2 reads and SiLU
+// derivatives; the walk itself is branch-free, ownership of halo positions is applied with selects) and keeps the conv weight / bias gradient partials in registers across all its runs: one atomic per CTA
+// and parameter at the end.  The only shared memory is the run's row table (token -> memory row, pooled index).
+template <typename T> struct Pair;
+template <> struct Pair<bf16> {
+    typedef uint32_t type;
+    static __device__ __forceinline__ type ld(const bf16* p) { return __ldg(reinterpret_cast<const unsigned int*>(p)); }
+    static __device__ __forceinline__ type zero() { return 0u; }
+    static __device__ __forceinline__ float2 up(type v) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v)); }
+    static __device__ __forceinline__ void st(bf16* p, float2 v) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y); }
+};
+template <> struct Pair<float> {
+    typedef float2 type;
+    static __device__ __forceinline__ type ld(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+    static __device__ __forceinline__ type zero() { return make_float2(0.f, 0.f); }
+    static __device__ __forceinline__ float2 up(type v) { return v; }
+    static __device__ __forceinline__ void st(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
+};
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+// d silu / dx; FAST (bf16 I/O): sigmoid through one tanh.approx MUFU op
+template <bool FAST>
+__device__ __forceinline__ float dsilu_sel(float x) {
+    if (FAST) {
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+        const float s = fmaf(0.5f, t, 0.5f);
+        return s * fmaf(x, 1.f - s, 1.f);
+    }
+    return dsilu(x);
+}
+
+constexpr int CBS_MAXRUN = 64;   // longest token run of one work item (row table size - 8)
+
+// d silu / dx of a pair (see dsilu_sel), on the packed f32x2 pipe except for the two MUFU ops
+template <bool FAST>
+__device__ __forceinline__ float2 dsilu2(float2 x) {
+    if (FAST) {
+        const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+        float tx, ty;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(tx) : "f"(h.x));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(ty) : "f"(h.y));
+        const float2 s = __ffma2_rn(make_float2(tx, ty), make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+        const float2 oms = __ffma2_rn(s, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+        return __fmul2_rn(s, __ffma2_rn(x, oms, make_float2(1.f, 1.f)));
+    }
+    return make_float2(dsilu(x.x), dsilu(x.y));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256, 2)
+conv_pool_bwd_stream_kernel(Geom g, int nseg, int seg_len, int64_t nitems, int nslots, int chunks,
+                            const T* __restrict__ x, int64_t ldx, int64_t xbs, const T* __restrict__ e,
+                            const T* __restrict__ du, const float* __restrict__ cw, const float* __restrict__ cb,
+                            const float* __restrict__ Dskip, float scale, T* __restrict__ dx,
+                            float* __restrict__ dcw, float* __restrict__ dcb) {
+    typedef Pair<T> P;
+    typedef typename P::type PT;
+    constexpr bool FAST = is_fast<T>::value;
+    // per-run tables, padded by 8 entries so the unrolled walk never indexes past them:
+    // element offset of the token's row in x / dx and in e (-1: outside the image), pooled index
+    __shared__ int xoff[CBS_MAXRUN + 16], eoff[CBS_MAXRUN + 16], jtab[CBS_MAXRUN + 16];
+    const int D = g.D;
+    const int slot = blockIdx.x / chunks, chunk = blockIdx.x - slot * chunks;
+    const int d0 = (chunk * blockDim.x + threadIdx.x) * 2;
+    const int64_t uplane = (int64_t)g.B * g.Lp * D;
+    const float pscale = scale / (float)g.pool;
+    const float2 ps2 = make_float2(pscale, pscale);
+    float2 wf[4], wb[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        wf[k] = make_float2(cw[(int64_t)d0 * 4 + k], cw[(int64_t)(d0 + 1) * 4 + k]);
+        wb[k] = make_float2(cw[((int64_t)D + d0) * 4 + k], cw[((int64_t)D + d0 + 1) * 4 + k]);
+    }
+    const float2 bf_ = cb ? make_float2(cb[d0], cb[d0 + 1]) : make_float2(0.f, 0.f);
+    const float2 bb_ = cb ? make_float2(cb[D + d0], cb[D + d0 + 1]) : make_float2(0.f, 0.f);
+    const float2 Df = make_float2(Dskip[d0], Dskip[d0 + 1]), Db = make_float2(Dskip[D + d0], Dskip[D + d0 + 1]);
+    const float2 z2 = make_float2(0.f, 0.f);
+    float2 awf[4] = {z2, z2, z2, z2}, awb[4] = {z2, z2, z2, z2}, abf = z2, abb = z2;
+
+    for (int64_t item = slot; item < nitems; item += nslots) {
+        const int b = (int)(item / nseg), sgi = (int)(item - (int64_t)b * nseg);
+        const int t0 = sgi * seg_len, n = min(seg_len, g.L - t0), n6 = n + 6;
+        __syncthreads();  // the previous run's tables are no longer read
+        for (int i = threadIdx.x; i < n6 + 8; i += blockDim.x) {
+            const int t = t0 - 3 + i;
+            const bool in = i < n6 && t >= 0 && t < g.L;
+            const int row = in ? (int)seq_to_row(g, t) : 0;
+            xoff[i] = in ? row * (int)ldx : -1;
+            eoff[i] = in ? row * D : -1;
+            jtab[i] = min(max(t, 0), g.L - 1) / g.pool;   // clamped: no spurious du reload outside the image
+        }
+        __syncthreads();
+        const T* xb = x + (int64_t)b * xbs + d0;
+        const T* eb = e + (int64_t)b * g.L * D + d0;
+        T* dxb = dx + (int64_t)b * xbs + d0;
+        const T* duf_b = du + (int64_t)b * g.Lp * D + d0;
+        PT qx[4], qe[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ox = xoff[k], oe = eoff[k];
+            qx[k] = ox >= 0 ? P::ld(xb + ox) : P::zero();
+            qe[k] = oe >= 0 ? P::ld(eb + oe) : P::zero();
+        }
+        float2 xw[4] = {z2, z2, z2, z2}, cbw[4] = {z2, z2, z2, z2}, gfw[4] = {z2, z2, z2, z2}, gbw[4] = {z2, z2, z2, z2};
+        float2 duf = z2, dub = z2;
+        int jcur = -1;
+        for (int base = 0; base < n6; base += 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = base + k;                                  // may run up to 3 past n6: tables are padded
+                const PT px = qx[k], pe = qe[k];
+                {
+                    const int ox = xoff[i + 4], oe = eoff[i + 4];
+                    qx[k] = ox >= 0 ? P::ld(xb + ox) : P::zero();
+                    qe[k] = oe >= 0 ? P::ld(eb + oe) : P::zero();
+                }
+                const bool inr = xoff[i] >= 0;
+                const float2 ev = P::up(pe);
+                xw[k] = P::up(px);                                       // x[f]; x[f-m] sits in slot (k - m) & 3
+                const int j = jtab[i];
+                if (j != jcur) {
+                    jcur = j;
+                    duf = __fmul2_rn(P::up(P::ld(duf_b + (int64_t)j * D)), ps2);
+                    dub = __fmul2_rn(P::up(P::ld(duf_b + uplane + (int64_t)j * D)), ps2);
+                }
+                const float2 cbv = __ffma2_rn(ev, Db, dub);
+                cbw[k] = inr ? cbv : z2;                                 // dxc_b[f]
+                const float2 x3 = xw[(k + 1) & 3], x2 = xw[(k + 2) & 3], x1 = xw[(k + 3) & 3], x0 = xw[k];  // x[f-3..f]
+                const float2 cf = __ffma2_rn(wf[3], x0, __ffma2_rn(wf[2], x1, __ffma2_rn(wf[1], x2, __ffma2_rn(wf[0], x3, bf_))));
+                const float2 cbk = __ffma2_rn(wb[3], x3, __ffma2_rn(wb[2], x2, __ffma2_rn(wb[1], x1, __ffma2_rn(wb[0], x0, bb_))));
+                float2 Gf = __fmul2_rn(__ffma2_rn(ev, Df, duf), dsilu2<FAST>(cf));        // G_f[f]
+                if (!inr) Gf = z2;
+                const float2 Gb = __fmul2_rn(cbw[(k + 1) & 3], dsilu2<FAST>(cbk));         // G_b[f-3] (0 outside)
+                gfw[k] = Gf;
+                gbw[k] = Gb;
+                // ownership: G_f[f] for f in [t0, t0+n) <=> 3 <= i < n+3;  token t = f-3 (dx, G_b) <=> 6 <= i < n+6
+                const float2 Gfo = (i >= 3 && i < n + 3) ? Gf : z2;
+                const bool own = i >= 6 && i < n6;
+                const float2 Gbo = own ? Gb : z2;
+                awf[0] = __ffma2_rn(Gfo, x3, awf[0]); awf[1] = __ffma2_rn(Gfo, x2, awf[1]);
+                awf[2] = __ffma2_rn(Gfo, x1, awf[2]); awf[3] = __ffma2_rn(Gfo, x0, awf[3]);
+                abf = __fadd2_rn(abf, Gfo);
+                awb[0] = __ffma2_rn(Gbo, x0, awb[0]); awb[1] = __ffma2_rn(Gbo, x1, awb[1]);
+                awb[2] = __ffma2_rn(Gbo, x2, awb[2]); awb[3] = __ffma2_rn(Gbo, x3, awb[3]);
+                abb = __fadd2_rn(abb, Gbo);
+                float2 acc = __fmul2_rn(wf[0], gfw[k]);
+                acc = __ffma2_rn(wf[1], gfw[(k + 3) & 3], acc);
+                acc = __ffma2_rn(wf[2], gfw[(k + 2) & 3], acc);
+                acc = __ffma2_rn(wf[3], gfw[(k + 1) & 3], acc);
+                acc = __ffma2_rn(wb[3], gbw[k], acc);
+                acc = __ffma2_rn(wb[2], gbw[(k + 3) & 3], acc);
+                acc = __ffma2_rn(wb[1], gbw[(k + 2) & 3], acc);
+                acc = __ffma2_rn(wb[0], gbw[(k + 1) & 3], acc);
+                if (own) P::st(dxb + xoff[i - 3], acc);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        atomicAdd(dcw + (int64_t)d0 * 4 + k, awf[k].x);
+        atomicAdd(dcw + (int64_t)(d0 + 1) * 4 + k, awf[k].y);
+        atomicAdd(dcw + ((int64_t)D + d0) * 4 + k, awb[k].x);
+        atomicAdd(dcw + ((int64_t)D + d0 + 1) * 4 + k, awb[k].y);
+    }
+    if (dcb) {
+        atomicAdd(dcb + d0, abf.x); atomicAdd(dcb + d0 + 1, abf.y);
+        atomicAdd(dcb + D + d0, abb.x); atomicAdd(dcb + D + d0 + 1, abb.y);
+    }
+}
+
+// block size for the streaming kernel: the largest multiple of 32 that is <= 256 and divides dim / 2 (0: none)
+static int stream_block(int D) {
+    if (D % 64 != 0) return 0;
+    const int pairs = D / 2;
+    for (int t = 256; t >= 32; t -= 32)
+        if (pairs % t == 0) return t;
+    return 0;
+}
+
+template <typename T>
+static int launch_conv_bwd_stream(const Geom& g, const T* x, int64_t ldx, int64_t xbs, const T* e, const T* du,
+                                  const float* cw, const float* cb, const float* Dskip, float scale, T* dx, float* dcw,
+                                  float* dcb, cudaStream_t st) {
+    const int threads = stream_block(g.D), chunks = (g.D / 2) / threads;
+    const int nseg = ceil_div(g.L, 56), seg_len = ceil_div(g.L, nseg);   // equal runs of <= 56 tokens
+    const int64_t nitems = (int64_t)g.B * nseg;
+    auto kern = conv_pool_bwd_stream_kernel<T>;
+    int occ = 0;
+    cudaError_t er = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0);
+    FV_REQUIRE(er == cudaSuccess && occ > 0, "fv_conv_pool_bwd: occupancy query failed (%s)", cudaGetErrorString(er));
+    int64_t nslots = ((int64_t)sm_count() * occ) / chunks;
+    if (nslots < 1) nslots = 1;
+    if (nslots > nitems) nslots = nitems;
+    // even number of runs per slot where possible (no ragged last round)
+    const int64_t rounds = (nitems + nslots - 1) / nslots;
+    nslots = (nitems + rounds - 1) / rounds;
+    kern<<<(unsigned)(nslots * chunks), threads, 0, st>>>(g, nseg, seg_len, nitems, (int)nslots, chunks, x, ldx, xbs, e, du, cw,
+                                                          cb, Dskip, scale, dx, dcw, dcb);
+    return finish_launch("conv_pool_bwd");
+}
+
 int check_geom(const fv_geom* g, const char* who);
 
 template <typename T, int TT>
@@ -195,13 +408,23 @@ extern "C" int fv_conv_pool_bwd(const fv_geom* g_, int dtype, const void* x, int
     FV_REQUIRE(ldx % 4 == 0 && x_bstride % 4 == 0, "fv_conv_pool_bwd: strides must be multiples of 4 elements");
     FV_REQUIRE(g_->dim <= 4096 && g_->batch <= 65535, "fv_conv_pool_bwd: dim > 4096 or batch > 65535");
     Geom g = make_geom(g_);
+    cudaStream_t st = (cudaStream_t)stream;
+    static const bool tiled_only = getenv("FASTVIM_CONV_BWD_TILED") != nullptr;   // A/B switch for tools/kbench.py
+    if (!tiled_only && stream_block(g.D) > 0 && ldx % 2 == 0 && x_bstride % 2 == 0) {
+        if (dtype == FV_F32)
+            return launch_conv_bwd_stream<float>(g, (const float*)x, ldx, x_bstride, (const float*)e, (const float*)du, conv_w,
+                                                 conv_b, Dskip, scale, (float*)dx, dconv_w, dconv_b, st);
+        if (dtype == FV_BF16)
+            return launch_conv_bwd_stream<bf16>(g, (const bf16*)x, ldx, x_bstride, (const bf16*)e, (const bf16*)du, conv_w,
+                                                conv_b, Dskip, scale, (bf16*)dx, dconv_w, dconv_b, st);
+        return fail("fv_conv_pool_bwd: unsupported dtype %d", dtype);
+    }
     const size_t budget = 200 * 1024;
     int maxlen = 8;
     if ((dtype == FV_F32 ? conv_bwd_smem<float, 8>(g.D) : conv_bwd_smem<bf16, 8>(g.D)) > budget) maxlen = 4;
     if (maxlen == 4 && (dtype == FV_F32 ? conv_bwd_smem<float, 4>(g.D) : conv_bwd_smem<bf16, 4>(g.D)) > budget) maxlen = 2;
     const int tpg = (g.pool + maxlen - 1) / maxlen;
     const int tile_len = (g.pool + tpg - 1) / tpg;
-    cudaStream_t st = (cudaStream_t)stream;
 #define FV_CB(T_)                                                                                                      \
     do {                                                                                                               \
         if (tile_len <= 2)                                                                                             \

@@ -87,7 +87,7 @@ def main():
     def rep(name, t, nbytes):
         print(json.dumps({"kernel": name, "shape": a.shape, "dtype": a.dtype, "us": round(t * 1e6, 2),
                           "alg_MB": round(nbytes / 1e6, 2), "GBps": round(nbytes / t / 1e9, 1),
-                          "env": {k: v for k, v in os.environ.items() if k.startswith("FV_")}}), flush=True)
+                          "env": {k: v for k, v in os.environ.items() if k.startswith(("FV_", "FASTVIM_"))}}), flush=True)
 
     if not only or "conv_pool" in only:
         t = timeit(lambda i: ops.conv_pool_fwd(xz[i][..., :D], geom, cw, cb), nrot, a.iters)
@@ -106,6 +106,20 @@ def main():
         t = timeit(lambda i: ops.block_fwd(xz[i][..., :D], xz[i][..., D:], geom, cw, cb, xw, dtwa, dt_b, A_log, Dk,
                                            lw, lb, 1e-5, 1.0, R, N, True, xproj_w_packed=xwp), nrot, a.iters)
         rep("block_fwd", t, 3 * Bt * L * D * s)
+    if only and "bwd" in only:   # backward kernels of the training path (MixerFn.backward)
+        dxz = [torch.empty(Bt, L, 2 * D, device=dev, dtype=dt) for _ in range(2)]
+        dy = [torch.randn(Bt, L, D, device=dev).to(dt) for _ in range(nrot)]
+        e_ = [torch.randn(Bt, L, D, device=dev).to(dt) for _ in range(nrot)]
+        t = timeit(lambda i: ops.gate_bwd(xz[i][..., :D], xz[i][..., D:], dy[i], sv[i], geom, cw, cb, Dk, lw, lb, 1e-5,
+                                          dxz[i & 1][..., D:]), nrot, a.iters)
+        rep("gate_bwd", t, 5 * Bt * L * D * s + 3 * Bt * Lp * D * 4)
+        tpg = ops.bwd_tiles_per_group(geom, Bt, D, dt)
+        dsp = [torch.randn(tpg, Bt, Lp, D, device=dev) for _ in range(2)]
+        t = timeit(lambda i: ops.scan_bwd(dsp[i & 1], u[i], xdbl[i], geom, R, N, dt_w, dt_b, A_log, True), nrot, a.iters)
+        rep("scan_bwd(+reduce_planes)", t, (tpg * 4 + 6 * s) * Bt * Lp * D + 2 * Bt * Lp * (R + 4 * N) * s)
+        t = timeit(lambda i: ops.conv_pool_bwd(xz[i][..., :D], e_[i], u[i], geom, cw, cb, Dk, 1.0, dxz[i & 1][..., :D]),
+                   nrot, a.iters)
+        rep("conv_pool_bwd", t, 3 * Bt * L * D * s + 2 * Bt * Lp * D * s)
     if not only or "add_norm" in only:
         t = timeit(lambda i: ops.add_norm_fwd(hs[i], res[i], nw, None, 1e-5, True), nrot, a.iters)
         rep("add_norm_fwd", t, Bt * L * dm * (s + 4) * 2)
