@@ -52,6 +52,8 @@ SIGNATURES = {
     "fv_bwd_tiles_per_group": [_G, _I],
     "fv_gate_bwd": [_G, _I, _P, _P, _L, _L, _P, _L, _L, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P],
     "fv_scan_bwd_planes": [_G],
+    "fv_scan_bwd_short_supported": [_G, _I],
+    "fv_scan_bwd_short": [_G, _I, _I, _P, _P, _L, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P],
     "fv_scan_bwd": [_G, _I, _I, _P, _P, _L, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P],
     "fv_reduce_planes": [_I, _P, _I, _L, _P, _P],
     "fv_conv_pool_bwd": [_G, _I, _P, _L, _L, _P, _P, _P, _P, _P, _F, _I, _P, _P, _P, _P],

@@ -440,6 +440,218 @@ scan_bwd_small_kernel(Geom g, int nplanes_ds, const T* __restrict__ u, const T* 
     }
 }
 
+// ---- short pooled sequences, v2: two states per thread, dt_proj pre-activation supplied by the caller ----------------
+// scan_bwd_small_kernel spends ~860 instructions per thread with 16 threads per (channel, direction): a third of them
+// re-deriving delta (a 48-term dot product per row), the rest mostly shared-memory traffic -- 550 us per launch at
+// FastVim-B.  Here
+//   * the caller passes delta_pre = dt_bias + W_dt . dt (2, B, Lp, dim) fp32 -- the dt_proj GEMM, which the reference also
+//     runs as a GEMM (mamba_simple_faster.py:328-334) -- so the kernel does no projection;
+//   * a thread owns TWO states of one channel (8 threads per channel, 32 channels per 256-thread CTA) and all of its
+//     recurrence arithmetic runs on the packed f32x2 pipe;
+//   * per step a thread reads exactly two 16-byte shared-memory words: the channel's row record {delta, delta*u, dy, u}
+//     and the state pair's {B, B', C, C'};
+//   * h and the decays of the <= 16 steps stay in registers between the forward and the reverse sweep (no recompute);
+//   * dB / dC partials go to shared memory as one 16-byte store per step and are summed over the CTA's 32 channels at
+//     the end (one plane per CTA, deterministic); du / d(delta) partials are summed over a channel's 8 threads through
+//     a warp-private shared-memory transpose.
+// softplus in the form the forward kernels use (scan_pooled.cu softplus_fast / block_fwd.cu bk_softplus): 2 SFU ops
+__device__ __forceinline__ float s2_softplus(float x) {
+    constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+    const float e = ex2b(x * LOG2E);
+    float l;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.f + e));
+    const float sp = x < -5.f ? e * fmaf(e, fmaf(e, 0.33333334f, -0.5f), 1.f) : LN2 * l;
+    return x <= 20.f ? sp : x;
+}
+
+constexpr int S2_CH = 32, S2_THREADS = S2_CH * 8, S2_LP = 16;
+
+// dynamic shared memory, sized by the actual Lp (104 KB at Lp = 14: two CTAs per SM):
+//   bc   [Lp][8] float4            per row, state pair: {B_2p, B_2p+1, C_2p, C_2p+1}
+//   rowd [S2_CH][Lp] float4        per channel, row: {delta, delta*u, dy, u}
+//   part [S2_CH][Lp][8] float4     per channel, row, state pair: {dB_2p, dB_2p+1, dC_2p, dC_2p+1}
+//   xch  [S2_CH][Lp][9] float2     per channel, row, thread-of-channel: {du partial, d(delta) partial} (+1 pad)
+//   prer [S2_CH][Lp] float         dt_proj pre-activation (for the softplus derivative)
+//   outs [2][Lp][S2_CH] float      staged du, d(delta_pre)
+static inline size_t s2_smem_bytes(int Lp) {
+    return (size_t)Lp * (8 * 16 + S2_CH * 16 + S2_CH * 8 * 16 + S2_CH * 9 * 8 + S2_CH * 4 + 2 * S2_CH * 4);
+}
+
+// LPT: compile-time pooled length (14: every 224^2 model; 0: run-time g.Lp <= 16).  DIR: scan direction.  With both
+// static every shared-memory address of the unrolled sweeps is base + constant (no index arithmetic, no guards).
+template <typename T, int LPT, int DIR>
+__device__ __forceinline__ void
+scan_bwd_short_body(const Geom& g, int nplanes_ds, const T* __restrict__ u, const T* __restrict__ xdbl, int64_t ldxd, int R,
+                    const float* __restrict__ pre, const float* __restrict__ A, int a_is_log,
+                    const float* __restrict__ ds, T* __restrict__ du, T* __restrict__ ddelta,
+                    float* __restrict__ dbc_planes, float* __restrict__ dA, float* __restrict__ dbias) {
+    constexpr int N = 16;
+    extern __shared__ __align__(16) unsigned char s2_raw[];
+    const int Lp = LPT ? LPT : g.Lp;
+    float4* s_bc = reinterpret_cast<float4*>(s2_raw);
+    float4* s_rowd = s_bc + Lp * 8;
+    float4* s_part = s_rowd + S2_CH * Lp;
+    float2* s_xch = reinterpret_cast<float2*>(s_part + S2_CH * Lp * 8);
+    float* s_prer = reinterpret_cast<float*>(s_xch + S2_CH * Lp * 9);
+    float* s_outs = s_prer + S2_CH * Lp;
+    constexpr int dir = DIR;
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x, c = tid >> 3, p = tid & 7;   // channel within the CTA, state pair
+    const int d = blockIdx.x * S2_CH + c;
+    const bool live = d < g.D;
+    const int dd = live ? d : 0;
+    const int64_t plane = (int64_t)g.B * Lp * g.D;
+    constexpr float LOG2E = 1.4426950408889634f;
+    const float2 araw = *reinterpret_cast<const float2*>(A + ((int64_t)dir * g.D + dd) * N + 2 * p);   // latency hidden below
+
+    // ---- B / C of the image's pooled rows
+    const T* xd = xdbl + ((int64_t)dir * g.B + b) * Lp * ldxd + R;
+    for (int i = tid; i < Lp * 8; i += S2_THREADS) {
+        const int r = i >> 3, pp = i & 7;
+        const T* row = xd + (int64_t)r * ldxd;
+        s_bc[r * 8 + pp] = make_float4(ld1(row + 2 * pp), ld1(row + 2 * pp + 1), ld1(row + N + 2 * pp), ld1(row + N + 2 * pp + 1));
+    }
+    // row records: (row, channel) pairs spread over the CTA with the channel fastest -- 128-byte coalesced row segments
+    for (int i = tid; i < Lp * S2_CH; i += S2_THREADS) {
+        const int r = i >> 5, cc = i & 31;
+        const int dch = blockIdx.x * S2_CH + cc;
+        float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
+        float pv = 0.f;
+        if (dch < g.D) {
+            const int64_t o = ((int64_t)b * Lp + r) * g.D + dch;
+            pv = pre[dir * plane + o];
+            const float uv = ld1(u + dir * plane + o);
+            float dyv = 0.f;
+            for (int q0 = 0; q0 < nplanes_ds; q0 += 4) {   // the planes' loads are independent: issue four at a time
+                float v[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v[q] = q0 + q < nplanes_ds ? ds[(q0 + q) * plane + o] : 0.f;
+                dyv += (v[0] + v[1]) + (v[2] + v[3]);
+            }
+            const float delta = s2_softplus(pv);
+            rec = make_float4(delta, delta * uv, dyv, uv);
+        }
+        s_rowd[cc * Lp + r] = rec;
+        s_prer[cc * Lp + r] = pv;
+    }
+    const float2 Anat = a_is_log ? make_float2(-expf(araw.x), -expf(araw.y)) : araw;
+    const float2 A2 = make_float2(Anat.x * LOG2E, Anat.y * LOG2E);
+    __syncthreads();
+
+    // ---- forward sweep: states and decays of every step stay in registers
+    const int i0 = DIR ? Lp - 1 : 0;
+    constexpr int istep = DIR ? -1 : 1;
+    float2 hs[S2_LP], as_[S2_LP];
+    {
+        float2 h = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int s = 0; s < S2_LP; ++s) {
+            hs[s] = make_float2(0.f, 0.f);
+            as_[s] = make_float2(1.f, 1.f);
+            if (s < Lp) {
+                const int i = i0 + s * istep;
+                const float4 rd = s_rowd[c * Lp + i];
+                const float4 bcv = s_bc[i * 8 + p];
+                const float2 ea = __fmul2_rn(make_float2(rd.x, rd.x), A2);
+                as_[s] = make_float2(ex2b(ea.x), ex2b(ea.y));
+                h = __ffma2_rn(as_[s], h, __fmul2_rn(make_float2(rd.y, rd.y), make_float2(bcv.x, bcv.y)));
+                hs[s] = h;
+            }
+        }
+    }
+    // ---- reverse sweep
+    float2 G = make_float2(0.f, 0.f), dAacc = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int s = S2_LP - 1; s >= 0; --s) {
+        if (s < Lp) {
+            const int i = i0 + s * istep;
+            const float4 rd = s_rowd[c * Lp + i];      // delta, delta*u, dy, u
+            const float4 bcv = s_bc[i * 8 + p];        // B, B', C, C'
+            const float2 dy2 = make_float2(rd.z, rd.z);
+            const float2 gi = __ffma2_rn(make_float2(bcv.z, bcv.w), dy2, G);
+            const float2 hm1 = s > 0 ? hs[s > 0 ? s - 1 : 0] : make_float2(0.f, 0.f);
+            const float2 daa = __fmul2_rn(__fmul2_rn(gi, hm1), as_[s]);
+            const float2 dC = __fmul2_rn(dy2, hs[s]);
+            const float2 dB = __fmul2_rn(gi, make_float2(rd.y, rd.y));
+            const float2 gB = __fmul2_rn(gi, make_float2(bcv.x, bcv.y));
+            const float2 dul = __fmul2_rn(gB, make_float2(rd.x, rd.x));
+            const float2 ddl = __ffma2_rn(gB, make_float2(rd.w, rd.w), __fmul2_rn(daa, Anat));
+            dAacc = __ffma2_rn(daa, make_float2(rd.x, rd.x), dAacc);
+            G = __fmul2_rn(gi, as_[s]);
+            s_part[(c * Lp + i) * 8 + p] = make_float4(dB.x, dB.y, dC.x, dC.y);
+            s_xch[(c * Lp + i) * 9 + p] = make_float2(dul.x + dul.y, ddl.x + ddl.y);
+        }
+    }
+    __syncwarp();   // a channel's 8 threads sit in one warp
+    // ---- du / d(delta): thread p sums the 8 partials of rows p and p + 8
+    float bsum = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int r = p + 8 * h;
+        if (r < Lp) {
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float2 v = s_xch[(c * Lp + r) * 9 + k];
+                a0 += v.x;
+                a1 += v.y;
+            }
+            const float pv = s_prer[c * Lp + r];
+            const float dpre = pv <= 20.f ? a1 * sigmoidf_(pv) : a1;
+            s_outs[r * S2_CH + c] = a0;
+            s_outs[(Lp + r) * S2_CH + c] = dpre;
+            bsum += dpre;
+        }
+    }
+    // d(dt_bias) = sum over rows; dA per state over rows and images: fp32 atomics as in the reference (bwd_kernel.cuh:467-477)
+    bsum += __shfl_xor_sync(0xffffffffu, bsum, 1);
+    bsum += __shfl_xor_sync(0xffffffffu, bsum, 2);
+    bsum += __shfl_xor_sync(0xffffffffu, bsum, 4);
+    if (live) {
+        float* dAp = dA + ((int64_t)dir * g.D + d) * N + 2 * p;
+        atomicAdd(dAp, a_is_log ? dAacc.x * Anat.x : dAacc.x);
+        atomicAdd(dAp + 1, a_is_log ? dAacc.y * Anat.y : dAacc.y);
+        if (p == 0) atomicAdd(dbias + (int64_t)dir * g.D + d, bsum);
+    }
+    __syncthreads();
+    // ---- coalesced outputs: du, d(delta_pre) as 32-channel row segments; [dB | dC] summed over the CTA's channels
+    for (int t = tid; t < Lp * S2_CH; t += S2_THREADS) {
+        const int i = t / S2_CH, cc = t - i * S2_CH;
+        const int dch = blockIdx.x * S2_CH + cc;
+        if (dch < g.D) {
+            const int64_t o = dir * plane + ((int64_t)b * Lp + i) * g.D + dch;
+            st1(du + o, s_outs[i * S2_CH + cc]);
+            st1(ddelta + o, s_outs[(Lp + i) * S2_CH + cc]);
+        }
+    }
+    // one thread per (row, state pair): 32 x LDS.128 + packed adds, then the plane's [dB | dC] row layout
+    float* outp = dbc_planes + (((int64_t)blockIdx.x * 2 + dir) * g.B + b) * Lp * 2 * N;
+    for (int t = tid; t < Lp * 8; t += S2_THREADS) {
+        float2 accB = make_float2(0.f, 0.f), accC = make_float2(0.f, 0.f);
+#pragma unroll 8
+        for (int ch = 0; ch < S2_CH; ++ch) {
+            const float4 v = s_part[ch * (Lp * 8) + t];
+            accB = __fadd2_rn(accB, make_float2(v.x, v.y));
+            accC = __fadd2_rn(accC, make_float2(v.z, v.w));
+        }
+        const int i = t >> 3, pp = t & 7;
+        *reinterpret_cast<float2*>(outp + i * 32 + 2 * pp) = accB;
+        *reinterpret_cast<float2*>(outp + i * 32 + N + 2 * pp) = accC;
+    }
+}
+
+template <typename T, int LPT>
+__global__ void __launch_bounds__(S2_THREADS, 2)
+scan_bwd_short_kernel(Geom g, int nplanes_ds, const T* __restrict__ u, const T* __restrict__ xdbl, int64_t ldxd, int R,
+                      const float* __restrict__ pre, const float* __restrict__ A, int a_is_log,
+                      const float* __restrict__ ds, T* __restrict__ du, T* __restrict__ ddelta,
+                      float* __restrict__ dbc_planes, float* __restrict__ dA, float* __restrict__ dbias) {
+    if (blockIdx.z)
+        scan_bwd_short_body<T, LPT, 1>(g, nplanes_ds, u, xdbl, ldxd, R, pre, A, a_is_log, ds, du, ddelta, dbc_planes, dA, dbias);
+    else
+        scan_bwd_short_body<T, LPT, 0>(g, nplanes_ds, u, xdbl, ldxd, R, pre, A, a_is_log, ds, du, ddelta, dbc_planes, dA, dbias);
+}
+
 // sums `nplanes` planes of `n` floats: out[i] = sum_p in[p*n + i] (adds to the cast when `accumulate`)
 template <typename TO>
 __global__ void reduce_planes_kernel(const float* __restrict__ in, int nplanes, int64_t n, TO* __restrict__ out) {
@@ -534,4 +746,44 @@ extern "C" int fv_reduce_planes(int out_dtype, const float* in, int nplanes, int
     else if (out_dtype == FV_BF16) reduce_planes_kernel<bf16><<<grid, block, 0, st>>>(in, nplanes, n, (bf16*)out);
     else return fail("fv_reduce_planes: unsupported dtype %d", out_dtype);
     return finish_launch("reduce_planes");
+}
+
+/* Short pooled sequences (Lp <= 16) with the dt_proj pre-activation supplied: see scan_bwd_short_kernel. */
+extern "C" int fv_scan_bwd_short_supported(const fv_geom* g, int dstate) {
+    return g && g->dim > 0 && g->outer > 0 && g->inner > 0 && g->outer * g->inner <= fv::S2_LP && dstate == 16;
+}
+
+extern "C" int fv_scan_bwd_short(const fv_geom* g_, int dtype, int nplanes_ds, const void* u, const void* xdbl,
+                                 int64_t ld_xdbl, int dt_rank, int dstate, const float* delta_pre, const float* A,
+                                 int a_is_log, const float* ds, void* du, void* ddelta, float* dbc_planes, float* dA,
+                                 float* d_dt_bias, void* stream) {
+    using namespace fv;
+    if (int rc = check_geom(g_, "fv_scan_bwd_short")) return rc;
+    FV_REQUIRE(u && xdbl && delta_pre && A && ds && du && ddelta && dbc_planes && dA && d_dt_bias,
+               "fv_scan_bwd_short: null pointer");
+    FV_REQUIRE(fv_scan_bwd_short_supported(g_, dstate), "fv_scan_bwd_short: needs Lp <= 16 and d_state 16");
+    FV_REQUIRE(dt_rank > 0 && ld_xdbl >= dt_rank + 2 * dstate, "fv_scan_bwd_short: ld_xdbl %lld < R+2N", (long long)ld_xdbl);
+    FV_REQUIRE(g_->batch <= 65535 && nplanes_ds >= 1, "fv_scan_bwd_short: bad batch / plane count");
+    FV_REQUIRE(((uintptr_t)A % 8) == 0 && ((uintptr_t)dbc_planes % 8) == 0, "fv_scan_bwd_short: A / dbc_planes must be 8-byte aligned");
+    Geom g = make_geom(g_);
+    cudaStream_t st = (cudaStream_t)stream;
+    dim3 grid(ceil_div(g.D, S2_CH), g.B, 2), block(S2_THREADS);
+    const size_t smem = s2_smem_bytes(g.Lp);
+    if (dtype == FV_F32) {
+        auto kern = g.Lp == 14 ? scan_bwd_short_kernel<float, 14> : scan_bwd_short_kernel<float, 0>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        FV_REQUIRE(e == cudaSuccess, "fv_scan_bwd_short: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        kern<<<grid, block, smem, st>>>(g, nplanes_ds, (const float*)u, (const float*)xdbl, ld_xdbl, dt_rank, delta_pre, A, a_is_log,
+                                        ds, (float*)du, (float*)ddelta, dbc_planes, dA, d_dt_bias);
+        return finish_launch("scan_bwd_short");
+    }
+    if (dtype == FV_BF16) {
+        auto kern = g.Lp == 14 ? scan_bwd_short_kernel<bf16, 14> : scan_bwd_short_kernel<bf16, 0>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        FV_REQUIRE(e == cudaSuccess, "fv_scan_bwd_short: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        kern<<<grid, block, smem, st>>>(g, nplanes_ds, (const bf16*)u, (const bf16*)xdbl, ld_xdbl, dt_rank, delta_pre, A, a_is_log,
+                                        ds, (bf16*)du, (bf16*)ddelta, dbc_planes, dA, d_dt_bias);
+        return finish_launch("scan_bwd_short");
+    }
+    return fail("fv_scan_bwd_short: unsupported dtype %d", dtype);
 }

@@ -7,6 +7,7 @@ happens in Python.  Layout is token-major ``(B, L, D)`` (see include/fastvim_b20
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -16,6 +17,9 @@ from . import _lib
 from ._lib import FV_BF16, FV_F32, FV_POOL_MAX, FV_POOL_MEAN, fv_geom
 
 Tensor = torch.Tensor
+
+# short pooled sequences (Lp <= 16): fv_scan_bwd_short (two states per thread, dt_proj by GEMM); "0" = previous kernel
+SCAN_BWD_SHORT = os.environ.get("FASTVIM_SCAN_BWD_SHORT", "1") != "0"
 
 
 @dataclass(frozen=True)
@@ -382,9 +386,15 @@ def scan_bwd(ds: Tensor, u: Tensor, xdbl: Tensor, geom: Geometry, dt_rank: int, 
     dA = torch.zeros((2, D, d_state), device=u.device, dtype=torch.float32)
     dbias = torch.zeros((2, D), device=u.device, dtype=torch.float32)
     g = geom.c_struct(B, D)
-    _lib.call("fv_scan_bwd", C.byref(g), _dt(u), ds.shape[0], _p(u), _p(xdbl), xdbl.stride(1), dt_rank, d_state,
-              _p(dt_w), _p(dt_bias), _p(A), int(a_is_log), _p(ds), _p(du), _p(ddelta), _p(planes), _p(dA), _p(dbias),
-              _stream(u))
+    if SCAN_BWD_SHORT and _lib.lib().fv_scan_bwd_short_supported(C.byref(g), d_state):
+        # dt_proj as a GEMM (fp32, cuBLAS): delta_pre = dt_bias + dt . W_dt^T, (2, B*Lp, D)
+        pre = torch.baddbmm(dt_bias.float()[:, None, :], xdbl[..., :dt_rank].float(), dt_w.float().transpose(1, 2))
+        _lib.call("fv_scan_bwd_short", C.byref(g), _dt(u), ds.shape[0], _p(u), _p(xdbl), xdbl.stride(1), dt_rank, d_state,
+                  _p(pre), _p(A), int(a_is_log), _p(ds), _p(du), _p(ddelta), _p(planes), _p(dA), _p(dbias), _stream(u))
+    else:
+        _lib.call("fv_scan_bwd", C.byref(g), _dt(u), ds.shape[0], _p(u), _p(xdbl), xdbl.stride(1), dt_rank, d_state,
+                  _p(dt_w), _p(dt_bias), _p(A), int(a_is_log), _p(ds), _p(du), _p(ddelta), _p(planes), _p(dA), _p(dbias),
+                  _stream(u))
     dbc = torch.empty((2, B * Lp, 2 * d_state), device=u.device, dtype=u.dtype)
     _lib.call("fv_reduce_planes", _dt(u), _p(planes), ncol, dbc.numel(), _p(dbc), _stream(u))
     return du, ddelta, dbc, dA, dbias

@@ -229,6 +229,15 @@ int fv_gate_bwd(const fv_geom* g, int dtype, const void* x, const void* z, int64
  * (32-channel columns for Lp <= 16, 128-channel columns otherwise; add them with fv_reduce_planes); dA (2, dim, N) (gradient of A_log if a_is_log), d_dt_bias (2, dim)
  * fp32 accumulated. */
 int fv_scan_bwd_planes(const fv_geom* g);
+/* Same outputs for short pooled sequences (Lp <= 16: every 224^2 model), with the dt_proj GEMM done by the caller:
+ * delta_pre (2, B, Lp, dim) fp32 = dt_bias + W_dt . dt  (the reference runs this projection as a GEMM too,
+ * mamba_simple_faster.py:328-334).  Two states per thread, packed f32x2 arithmetic; dbc_planes has
+ * fv_scan_bwd_planes(g) planes. */
+int fv_scan_bwd_short_supported(const fv_geom* g, int dstate);
+int fv_scan_bwd_short(const fv_geom* g, int dtype, int nplanes_ds, const void* u, const void* xdbl,
+                      int64_t ld_xdbl, int dt_rank, int dstate, const float* delta_pre, const float* A,
+                      int a_is_log, const float* ds, void* du, void* ddelta, float* dbc_planes, float* dA,
+                      float* d_dt_bias, void* stream);
 int fv_scan_bwd(const fv_geom* g, int dtype, int nplanes_ds, const void* u, const void* xdbl,
                 int64_t ld_xdbl, int dt_rank, int dstate, const float* dt_w, const float* dt_bias,
                 const float* A, int a_is_log, const float* ds, void* du, void* ddelta,
