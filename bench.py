@@ -427,26 +427,79 @@ def run_train(a, model, w, Bt, dev, rank, world, local):
 
     img = w["img"]
     model.train()
-    net = model
-    if world > 1:
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
-                                                        static_graph=True, bucket_cap_mb=100)
-    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=0.05, fused=True)
     g = torch.Generator(device="cpu").manual_seed(100 + rank)
     host_imgs = [torch.randn(Bt, 3, img, img, generator=g).pin_memory() for _ in range(2)]
     host_tgt = [torch.softmax(torch.randn(Bt, 1000, generator=g) * 3, -1).pin_memory() for _ in range(2)]
     dev_imgs = [t.to(dev) for t in host_imgs]
     dev_tgt = [t.to(dev) for t in host_tgt]
     host_loss = torch.zeros(1).pin_memory()
+    params = [p for p in model.parameters() if p.requires_grad]
 
-    def step(x, t):
+    def fwd_bwd(net, x, t):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             logits = net(x)
         loss = torch.sum(-t * F.log_softmax(logits.float(), dim=-1), dim=-1).mean()   # SoftTargetCrossEntropy
         loss.backward()
-        opt.step()
-        opt.zero_grad(set_to_none=True)
         return loss
+
+    # ---- launch mode.  "graph" (default): the step is launch-bound on the host (~3,000 kernel launches; FastVim-T's
+    # kernels are shorter than their launches), so forward + backward and the optimizer are captured in two CUDA graphs
+    # over static input buffers.  With N > 1 the gradients are flattened inside the first graph, all-reduced with ONE
+    # NCCL call between the graphs and scattered back inside the second (392 MB for FastVim-B: ~1 ms over NVLink, no
+    # need to overlap it with a 45 ms backward).  "eager": torch DDP (bucketed all-reduce overlapped with backward).
+    mode = "eager" if a.no_graph else "graph"
+    step = None
+    if mode == "graph":
+        try:
+            opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=0.05, fused=True, capturable=True)
+            static_x, static_t = dev_imgs[0].clone(), dev_tgt[0].clone()
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    opt.zero_grad(set_to_none=True)
+                    fwd_bwd(model, static_x, static_t)
+                    opt.step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            opt.zero_grad(set_to_none=True)
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            _lib.reset_launch_count()
+            with torch.cuda.graph(g1):
+                static_loss = fwd_bwd(model, static_x, static_t)
+                grads = [p.grad for p in params]
+                flat = torch.cat([gr.reshape(-1) for gr in grads]) if world > 1 else None
+            launches = _lib.launch_count()
+            with torch.cuda.graph(g2, pool=g1.pool()):
+                if world > 1:
+                    torch._foreach_copy_(grads, [c.view_as(gr) for c, gr in zip(flat.split([gr.numel() for gr in grads]), grads)])
+                opt.step()
+
+            def step(x, t):
+                static_x.copy_(x, non_blocking=True)
+                static_t.copy_(t, non_blocking=True)
+                g1.replay()
+                if world > 1:
+                    dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+                g2.replay()
+                return static_loss
+        except Exception as ex:  # capture not possible: fall back to the eager step
+            sys.stderr.write(f"[bench] training-step graph capture failed ({type(ex).__name__}: {ex}); running eagerly\n")
+            mode, step = "eager", None
+            torch.cuda.synchronize()
+            model.zero_grad(set_to_none=True)
+    if step is None:
+        net = model
+        if world > 1:
+            net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True,
+                                                            static_graph=True, bucket_cap_mb=100)
+        opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=0.05, fused=True)
+
+        def step(x, t):
+            loss = fwd_bwd(net, x, t)
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            return loss
 
     def barrier():
         if world > 1:
@@ -462,9 +515,10 @@ def run_train(a, model, w, Bt, dev, rank, world, local):
 
     for _ in range(max(a.warmup, 3)):
         step(dev_imgs[0], dev_tgt[0])
-    _lib.reset_launch_count()
-    step(dev_imgs[0], dev_tgt[0])
-    launches = _lib.launch_count()
+    if mode == "eager":
+        _lib.reset_launch_count()
+        step(dev_imgs[0], dev_tgt[0])
+        launches = _lib.launch_count()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -499,8 +553,11 @@ def run_train(a, model, w, Bt, dev, rank, world, local):
                 "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": round(ms_total / a.steps, 4),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": a.workload, "desc": w["desc"], "batch_per_gpu": Bt, "global_batch": Bt * world,
-                           "sharding": f"batch-sharded DDP x{world}, NCCL gradient all-reduce overlapped with backward",
-                           "optimizer": "AdamW fused, lr 1e-3, wd 0.05, fp32 master weights", "launch": "eager",
+                           "sharding": (f"batch-sharded x{world}, one NCCL all-reduce (AVG) of the flattened gradients between the "
+                                        "forward+backward graph and the optimizer graph") if mode == "graph" else
+                                       f"batch-sharded DDP x{world}, NCCL gradient all-reduce overlapped with backward",
+                           "optimizer": "AdamW fused, lr 1e-3, wd 0.05, fp32 master weights",
+                           "launch": "cuda_graph (fwd+bwd | optimizer)" if mode == "graph" else "eager",
                            "l2": "activations of one step exceed the 126 MB L2; no flush"},
                 "e2e": {"value": round(world * Bt * a.steps / t_e2e, 1), "unit": "images/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": 4, "ms_per_step": round(t_e2e / a.steps * 1e3, 4)},
