@@ -96,5 +96,48 @@ def main():
         json.dump(manifest, f, indent=1, sort_keys=True)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--channel-model" not in sys.argv:
     main()
+
+
+def gen_channel_model():
+    """FastChannelVim model wrapper (models/channel_wise_tokenization/models_channel_mamba_faster.py:458-683):
+    the reference's own VisionMamba on CPU, eval mode (HCS off), 3-channel 32x64 images -> 2 x 4 patches x 3 channels
+    = 24 tokens, 4 blocks (two of them with the odd-layer token transposition), both scan orders; logits and the
+    gradient of every parameter."""
+    import importlib
+
+    load_reference()
+    cm = importlib.import_module("models.channel_wise_tokenization.models_channel_mamba_faster")
+    manifest_path = os.path.join(GOLD, "manifest.json")
+    manifest = json.load(open(manifest_path))
+    for name, order in (("channelvim_small_cf", "Channel-First"), ("channelvim_small_sf", "Spatial-First")):
+        torch.manual_seed(0)
+        model = cm.VisionMamba(img_size=(32, 64), patch_size=16, stride=16, depth=4, embed_dim=32, channels=3,
+                               num_classes=7, rms_norm=True, residual_in_fp32=True, fused_add_norm=False,
+                               final_pool_type="mean", if_abs_pos_embed=True, drop_path_rate=0.0, scan_order=order,
+                               hcs=False).eval()
+        with torch.no_grad():
+            for k, v in model.named_parameters():
+                if k.endswith(("mixer.D", "mixer.D_b", "norm.weight", "layernorm.weight", "layernorm.bias", "A_log",
+                               "A_b_log", "head.bias", "norm_f.weight")):
+                    v.add_(0.1 * torch.randn_like(v))
+        imgs = torch.randn(2, 3, 32, 64)
+        logits = model(imgs)
+        torch.manual_seed(1)
+        g = torch.randn_like(logits)
+        logits.backward(g)
+        sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+        gr = {k: v.grad.detach().clone() for k, v in model.named_parameters()}
+        path = os.path.join(GOLD, name + ".pt")
+        torch.save(dict(state_dict=sd, images=imgs, scan_order=order, dlogits=g, logits=logits.detach(), grads=gr,
+                        kwargs=dict(img_size=(32, 64), depth=4, embed_dim=32, channels=3, num_classes=7)), path)
+        manifest[name] = dict(bytes=os.path.getsize(path), note="reference model output (no oracle restatement: the "
+                              "CUDA model is compared with these vectors directly)")
+        print(f"  {name}: logits {tuple(logits.shape)}, {len(gr)} gradients, {os.path.getsize(path)} bytes")
+    with open(manifest_path, "w") as f:
+        json.dump(manifest, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__" and "--channel-model" in sys.argv:
+    gen_channel_model()

@@ -782,3 +782,48 @@ def test_channel_mixer_training_vs_reference_golden_fp32(name):
     got = dict(m.named_parameters())
     for k, want in g["grads"].items():
         assert_close(got[k].grad, want, 1e-4, "d" + k)
+
+
+# ------------------------------------------------------------------ FastChannelVim model (BASELINE.json configs[3])
+def _channel_model(g, **extra):
+    from fastvim_b200.vision_channel import VisionMamba
+
+    m = VisionMamba(**g["kwargs"], rms_norm=True, residual_in_fp32=True, fused_add_norm=True, final_pool_type="mean",
+                    if_abs_pos_embed=True, drop_path_rate=0.0, scan_order=g["scan_order"], hcs=False, **extra)
+    m.load_state_dict(g["state_dict"], strict=True)
+    return m.cuda()
+
+
+@pytest.mark.parametrize("name", ["channelvim_small_cf", "channelvim_small_sf"])
+def test_channel_model_fwd_bwd_vs_reference_golden_fp32(name):
+    """4-block FastChannelVim (per-channel patch embedding, channel embeddings, odd-layer transposition) against the
+    reference's own VisionMamba (models_channel_mamba_faster.py:458-683): logits and every parameter gradient."""
+    g = load_golden(name)
+    m = _channel_model(g).eval()
+    with torch.no_grad():
+        assert_close(m(g["images"].cuda()), g["logits"], 1e-4, "logits (inference kernels)")
+    m.train()
+    logits = m(g["images"].cuda())
+    assert_close(logits, g["logits"], 1e-4, "logits (training path)")
+    logits.backward(g["dlogits"].cuda())
+    for k, v in m.named_parameters():
+        assert v.grad is not None, k
+        assert_close(v.grad, g["grads"][k], 2e-4, f"d {k}")
+
+
+@pytest.mark.parametrize("order", ["Channel-First", "Spatial-First"])
+def test_channel_model_jumpcp_shape_bf16(order):
+    """FastChannelVim-S/16 on 8-channel 224 x 224 JUMP-CP-shape synthetic images (1568 tokens; 2 of the 24 blocks):
+    bf16 autocast logits against the same model in fp32."""
+    from fastvim_b200.vision_channel import VisionMamba
+
+    torch.manual_seed(0)
+    m = VisionMamba(img_size=224, depth=2, embed_dim=384, channels=8, num_classes=161, rms_norm=True,
+                    residual_in_fp32=True, fused_add_norm=True, drop_path_rate=0.0, scan_order=order, hcs=False).cuda().eval()
+    imgs = torch.randn(2, 8, 224, 224, device="cuda")
+    with torch.no_grad():
+        want = m(imgs)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            got = m(imgs)
+    assert got.shape == (2, 161)
+    assert_close(got, want, 2e-2, "bf16 vs fp32 logits")

@@ -145,3 +145,25 @@ def test_channel_mixer_oracle_gradients_match_reference_vectors(name):
     assert_close(dh, g["dhidden"], 5e-5, "dhidden")
     for k, want in g["grads"].items():
         assert_close(grads[k], want, 5e-5, "d" + k)
+
+
+@pytest.mark.parametrize("name", ["channelvim_small_cf", "channelvim_small_sf"])
+def test_channel_model_state_dict_is_reference_compatible(name):
+    """The FastChannelVim wrapper keeps the reference's parameter names and shapes (strict load of a state dict written by
+    the reference's own VisionMamba); construction needs no GPU."""
+    from fastvim_b200.vision_channel import VisionMamba
+
+    g = load_golden(name)
+    m = VisionMamba(**g["kwargs"], rms_norm=True, residual_in_fp32=True, fused_add_norm=True, final_pool_type="mean",
+                    if_abs_pos_embed=True, drop_path_rate=0.0, scan_order=g["scan_order"], hcs=False)
+    m.load_state_dict(g["state_dict"], strict=True)
+    assert set(g["grads"]) == {k for k, _ in m.named_parameters()}
+    # tokenisation order of the per-channel patch embedding is a pure index map (bit-exact against a Conv3d)
+    x = torch.randn(2, 3, 32, 64)
+    with torch.no_grad():
+        ours, tpp, _, _, chans = m.patch_embed(x)
+        ref = m.patch_embed.proj(x.unsqueeze(1)) + m.patch_embed.channel_embed.weight.t()[None, :, :, None, None]
+    ref = ref.permute(0, 1, 3, 4, 2) if g["scan_order"] == "Channel-First" else ref
+    ref = ref.flatten(2).transpose(1, 2)
+    assert tpp == 3 and chans == [0, 1, 2] and ours.shape == ref.shape
+    assert torch.allclose(ours, ref, atol=1e-5)
