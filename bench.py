@@ -42,6 +42,9 @@ WORKLOADS = {
     "fastvim_s_224": dict(embed_dim=384, img=224, batch=256, desc="FastVim-S patch16 d384 24 blocks, 224x224 inference"),
     "fastvim_b_224": dict(embed_dim=768, img=224, batch=128, desc="FastVim-B patch16 d768 24 blocks, 224x224 inference"),
     "fastvim_t_2048": dict(embed_dim=192, img=2048, batch=1, desc="FastVim-T patch16 d192 24 blocks, 2048x2048 inference"),
+    # BASELINE.json configs[3]: FastChannelVim-S/16, 8-channel JUMP-CP-shape images, 14 x 14 patches x 8 channels = 1568 tokens
+    "fastchannelvim_s_224": dict(embed_dim=384, img=224, batch=32, channels=8, classes=161, model="channel",
+                                 desc="FastChannelVim-S/16 d384 24 blocks, 8-channel 224x224 inference, Channel-First"),
     # BASELINE.json configs[2]: supervised training step, batch-sharded DDP, 128 images per GPU
     "fastvim_b_224_train": dict(embed_dim=768, img=224, batch=128, train=True,
                                 desc="FastVim-B patch16 d768 24 blocks, 224x224 training step (fwd+bwd+AdamW), bf16 autocast"),
@@ -217,8 +220,16 @@ def run_ours(a):
     img, E = w["img"], w["embed_dim"]
 
     torch.manual_seed(0)
-    model = VisionMamba(img_size=img, embed_dim=E, depth=24, rms_norm=True, residual_in_fp32=True, fused_add_norm=True,
-                        final_pool_type="mean", drop_path_rate=0.0).eval().to(dev)
+    C_in, n_cls, tpp = w.get("channels", 3), w.get("classes", 1000), 1
+    if w.get("model") == "channel":
+        from fastvim_b200.vision_channel import VisionMamba as ChannelVisionMamba
+        model = ChannelVisionMamba(img_size=img, embed_dim=E, depth=24, channels=C_in, num_classes=n_cls, rms_norm=True,
+                                   residual_in_fp32=True, fused_add_norm=True, final_pool_type="mean", drop_path_rate=0.0,
+                                   scan_order="Channel-First", hcs=False).eval().to(dev)
+        tpp = C_in
+    else:
+        model = VisionMamba(img_size=img, embed_dim=E, depth=24, rms_norm=True, residual_in_fp32=True, fused_add_norm=True,
+                            final_pool_type="mean", drop_path_rate=0.0).eval().to(dev)
     if w.get("train"):
         return run_train(a, model, w, Bt, dev, rank, world, local)
     # one very large image: d_inner channels sharded over the ranks (strong scaling), same image on every rank
@@ -228,8 +239,8 @@ def run_ours(a):
         shard_model_channels(model, None, a.out_mode)
     n_img_step = Bt if sharded else Bt * n_gpus
     g = torch.Generator(device="cpu").manual_seed(100 + (0 if sharded else rank))
-    host_imgs = [torch.randn(Bt, 3, img, img, generator=g).pin_memory() for _ in range(2)]
-    host_out = [torch.empty(Bt, 1000).pin_memory() for _ in range(2)]
+    host_imgs = [torch.randn(Bt, C_in, img, img, generator=g).pin_memory() for _ in range(2)]
+    host_out = [torch.empty(Bt, n_cls).pin_memory() for _ in range(2)]
 
     def fwd(x):
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
@@ -361,8 +372,8 @@ def run_ours(a):
         m0 = model.layers[0].mixer
         m0 = getattr(m0, "mixer", m0)          # channel-sharded wrapper
         D_loc = m0.d_inner // (world if sharded else 1)
-        L = (img // 16) ** 2
-        Lp = img // 16
+        L = (img // 16) ** 2 * tpp
+        Lp = img // 16 * tpp
         peaks, peak_src = load_peaks()
         for name, (tot, cnt) in agg.items():
             ab = algorithmic_bytes(name, Bt, L, Lp, D_loc, E, m0.dt_rank, m0.d_state, 2)
@@ -380,7 +391,7 @@ def run_ours(a):
 
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------
     cpu = None
-    if rank == 0 and world == 1 and not a.no_cpu:
+    if rank == 0 and world == 1 and not a.no_cpu and w.get("model") != "channel":
         cores = os.cpu_count() or 1
         v, ms, sb = cpu_reference_throughput(a.workload, a.cpu_budget, 2, 1, cores)
         cpu = {"value": round(v, 3), "unit": "images/s", "cores": cores, "kind": "port",

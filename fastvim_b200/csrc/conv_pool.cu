@@ -72,10 +72,23 @@ conv_pool_fwd_kernel(Geom g, const T* __restrict__ x, int64_t ldx, int64_t xbs,
             }
         }
     } else {
+        // channel layouts (inner > 1).  Channel-First FastChannelVim keeps the sequence in memory order (row = t):
+        // then the 7-row window needs no index arithmetic at all; other stride sets take the generic map.
+        const bool natural = g.si == 1 && g.sp == g.inner && g.so == (int64_t)g.pool * g.inner;
+        const int o = j / g.inner, i = j - o * g.inner;
+        const T* xd = xb + d0;
         for (int p = 0; p < g.pool; ++p) {
-            const int c = pooled_to_seq(g, j, p);
+            const int c = (o * g.pool + p) * g.inner + i;   // = pooled_to_seq(g, j, p)
+            if (natural) {
 #pragma unroll
-            for (int k = 0; k < 7; ++k) w[k] = load_row4(g, xb, ldx, d0, c - 3 + k);
+                for (int k = 0; k < 7; ++k) {
+                    const int t = c - 3 + k;
+                    w[k] = (t >= 0 && t < g.L) ? ld4(xd + (int64_t)t * ldx) : zero4();
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 7; ++k) w[k] = load_row4(g, xb, ldx, d0, c - 3 + k);
+            }
             float4 xf, xr;
             conv_both<FAST>(w, tf, tb, xf, xr);
             accf = MAXPOOL ? max4(accf, xf) : accf + xf;
