@@ -96,7 +96,7 @@ def main():
         json.dump(manifest, f, indent=1, sort_keys=True)
 
 
-if __name__ == "__main__" and "--channel-model" not in sys.argv:
+if __name__ == "__main__" and "--channel-model" not in sys.argv and "--2dcompress" not in sys.argv:
     main()
 
 
@@ -141,3 +141,32 @@ def gen_channel_model():
 
 if __name__ == "__main__" and "--channel-model" in sys.argv:
     gen_channel_model()
+
+
+def gen_2dcompress():
+    """FastChannelVim 2dcompress mixer (mamba_simple_channel_faster_2dcompress.py:176-425): both layer kinds, fwd + grads."""
+    import importlib
+
+    load_reference()
+    mod = importlib.import_module("mamba_ssm.modules.mamba_simple_channel_faster_2dcompress")
+    manifest_path = os.path.join(GOLD, "manifest.json")
+    manifest = json.load(open(manifest_path))
+    for name, layer_idx in (("cmixer2d_d32_4x6_t3_layer0_rows", 0), ("cmixer2d_d32_4x6_t3_layer2_channels", 2)):
+        torch.manual_seed(0)
+        ts, tpp, d_model = (4, 6), 3, 32
+        m = mod.Mamba(d_model, token_size=list(ts), layer_idx=layer_idx, scan_order="Channel-First")
+        detrivialise(m)
+        h = torch.randn(2, ts[0] * ts[1] * tpp, d_model)
+        layout = (1, ts[0] * ts[1], tpp) if (layer_idx + 1) % 3 == 0 else (ts[0], ts[1] * tpp, 1)
+        case, e = run_case(m, lambda hh, pp: O.mixer_oracle(hh, pp, ts, layout=layout), h, tpp)
+        case.update(token_size=ts, tokens_per_patch=tpp, layer_idx=layer_idx, layout=layout)
+        path = os.path.join(GOLD, name + ".pt")
+        torch.save(case, path)
+        manifest[name] = dict(oracle_vs_ref=e, bytes=os.path.getsize(path))
+        print(f"  {name}: oracle_vs_ref {e:.2e}")
+    with open(manifest_path, "w") as f:
+        json.dump(manifest, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__" and "--2dcompress" in sys.argv:
+    gen_2dcompress()

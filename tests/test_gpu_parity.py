@@ -827,3 +827,26 @@ def test_channel_model_jumpcp_shape_bf16(order):
             got = m(imgs)
     assert got.shape == (2, 161)
     assert_close(got, want, 2e-2, "bf16 vs fp32 logits")
+
+
+@pytest.mark.parametrize("name", ["cmixer2d_d32_4x6_t3_layer0_rows", "cmixer2d_d32_4x6_t3_layer2_channels"])
+def test_2dcompress_mixer_vs_reference_golden_fp32(name):
+    """2dcompress mixer: inference kernels and the training path (forward + every gradient) against the reference module."""
+    from fastvim_b200.mixer_channel_2dcompress import Mamba
+
+    g = load_golden(name)
+    m = Mamba(g["params"]["in_proj.weight"].shape[1], token_size=list(g["token_size"]), layer_idx=g["layer_idx"],
+              scan_order="Channel-First")
+    m.load_state_dict(g["params"], strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        assert_close(m(g["hidden"].cuda(), g["tokens_per_patch"]), g["out"], 1e-4, "out (inference kernels)")
+    m.train()
+    h = g["hidden"].cuda().requires_grad_()
+    out = m(h, g["tokens_per_patch"])
+    out.backward(g["dout"].cuda())
+    assert_close(out, g["out"], 1e-4, "out (training path)")
+    assert_close(h.grad, g["dhidden"], 1e-4, "dhidden")
+    got = dict(m.named_parameters())
+    for k, want in g["grads"].items():
+        assert_close(got[k].grad, want, 1e-4, "d" + k)

@@ -167,3 +167,15 @@ def test_channel_model_state_dict_is_reference_compatible(name):
     ref = ref.flatten(2).transpose(1, 2)
     assert tpp == 3 and chans == [0, 1, 2] and ours.shape == ref.shape
     assert torch.allclose(ours, ref, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["cmixer2d_d32_4x6_t3_layer0_rows", "cmixer2d_d32_4x6_t3_layer2_channels"])
+def test_2dcompress_mixer_oracle_matches_reference_vectors(name):
+    """FastChannelVim 2dcompress mixer (mamba_simple_channel_faster_2dcompress.py): both layer kinds are (outer, pool, inner)
+    layouts of the same oracle; forward and every gradient against the reference's own module."""
+    g = load_golden(name)
+    out, dh, grads = _oracle_grads(g, layout=g["layout"])
+    assert_close(out, g["out"], 5e-5, "out")
+    assert_close(dh, g["dhidden"], 5e-5, "dhidden")
+    for k, want in g["grads"].items():
+        assert_close(grads[k], want, 5e-5, "d" + k)
