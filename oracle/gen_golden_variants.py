@@ -96,7 +96,7 @@ def main():
         json.dump(manifest, f, indent=1, sort_keys=True)
 
 
-if __name__ == "__main__" and "--channel-model" not in sys.argv and "--2dcompress" not in sys.argv:
+if __name__ == "__main__" and "--channel-model" not in sys.argv and "--2dcompress" not in sys.argv and "--masked-blocks" not in sys.argv:
     main()
 
 
@@ -170,3 +170,49 @@ def gen_2dcompress():
 
 if __name__ == "__main__" and "--2dcompress" in sys.argv:
     gen_2dcompress()
+
+
+def gen_masked_blocks():
+    """FastMaskVim encoder blocks (models/mae/models_mamba_faster_mae_vimdecoder_v2.py:279-466): a stack of three
+    reference ``Block_masked`` (layer 1 takes the odd-layer id rotation) + the final add + RMSNorm, on 10 kept tokens of
+    a 4 x 6 grid; outputs and every gradient."""
+    import importlib
+
+    ref = load_reference()
+    mm = importlib.import_module("models.mae.models_mamba_faster_mae_vimdecoder_v2")
+    manifest_path = os.path.join(GOLD, "manifest.json")
+    manifest = json.load(open(manifest_path))
+    torch.manual_seed(0)
+    ts, d_model, keep, Bt, depth = (4, 6), 32, 10, 2, 3
+    layers = torch.nn.ModuleList([mm.create_block_masked(d_model, rms_norm=True, residual_in_fp32=True, fused_add_norm=False,
+                                                         layer_idx=i, token_size=ts) for i in range(depth)])
+    norm_f = ref.ln.RMSNorm(d_model, eps=1e-5)
+    with torch.no_grad():
+        for k, v in list(layers.named_parameters()) + list(norm_f.named_parameters()):
+            if k.endswith(("mixer.D", "mixer.D_b", "norm.weight", "layernorm.weight", "layernorm.bias", "A_log", "A_b_log",
+                           "weight")) and v.dim() == 1 or k.endswith(("A_log", "A_b_log")):
+                v.add_(0.1 * torch.randn_like(v))
+    ids = torch.stack([torch.randperm(ts[0] * ts[1])[:keep].sort().values for _ in range(Bt)])
+    h = torch.randn(Bt, keep, d_model, requires_grad=True)
+    hidden, residual = h, None
+    for layer in layers:
+        hidden, residual = layer(hidden, residual, ids.clone())
+    out = ref.ln.rms_norm_ref(hidden, norm_f.weight, None, residual=residual, eps=1e-5, prenorm=False, upcast=True)
+    torch.manual_seed(1)
+    g = torch.randn_like(out)
+    out.backward(g)
+    sd = {"layers." + k: v.detach().clone() for k, v in layers.state_dict().items()}
+    sd["norm_f.weight"] = norm_f.weight.detach().clone()
+    grads = {"layers." + k: v.grad.detach().clone() for k, v in layers.named_parameters()}
+    grads["norm_f.weight"] = norm_f.weight.grad.detach().clone()
+    path = os.path.join(GOLD, "mblocks_d32_4x6_keep10.pt")
+    torch.save(dict(state_dict=sd, hidden=h.detach(), ids_keep=ids, token_size=ts, depth=depth, dout=g, out=out.detach(),
+                    dhidden=h.grad.detach(), grads=grads), path)
+    manifest["mblocks_d32_4x6_keep10"] = dict(bytes=os.path.getsize(path), note="reference Block_masked stack output")
+    print("  mblocks_d32_4x6_keep10:", tuple(out.shape), len(grads), "gradients")
+    with open(manifest_path, "w") as f:
+        json.dump(manifest, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__" and "--masked-blocks" in sys.argv:
+    gen_masked_blocks()

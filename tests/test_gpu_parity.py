@@ -850,3 +850,53 @@ def test_2dcompress_mixer_vs_reference_golden_fp32(name):
     got = dict(m.named_parameters())
     for k, want in g["grads"].items():
         assert_close(got[k].grad, want, 1e-4, "d" + k)
+
+
+def test_masked_block_stack_vs_reference_golden_fp32():
+    """Three FastMaskVim encoder blocks (the middle one with the odd-layer id rotation) + final add + RMSNorm against the
+    reference's own Block_masked stack: output, input gradient and every parameter gradient."""
+    from fastvim_b200.norm import RMSNorm, layer_norm_fn
+    from fastvim_b200.vision_masked import create_block_masked
+
+    g = load_golden("mblocks_d32_4x6_keep10")
+    layers = torch.nn.ModuleList([create_block_masked(32, rms_norm=True, residual_in_fp32=True, fused_add_norm=True,
+                                                      layer_idx=i, token_size=g["token_size"]) for i in range(g["depth"])])
+    norm_f = RMSNorm(32, eps=1e-5)
+    layers.load_state_dict({k[len("layers."):]: v for k, v in g["state_dict"].items() if k.startswith("layers.")}, strict=True)
+    norm_f.load_state_dict({"weight": g["state_dict"]["norm_f.weight"]})
+    layers, norm_f = layers.cuda().train(), norm_f.cuda()
+    h = g["hidden"].cuda().requires_grad_()
+    ids = g["ids_keep"].cuda()
+    hidden, residual = h, None
+    for layer in layers:
+        hidden, residual = layer(hidden, residual, ids.clone())
+    out = layer_norm_fn(hidden, norm_f.weight, None, eps=1e-5, residual=residual, prenorm=False, residual_in_fp32=True,
+                        is_rms_norm=True)
+    out.backward(g["dout"].cuda())
+    assert_close(out, g["out"], 1e-4, "out")
+    assert_close(h.grad, g["dhidden"], 2e-4, "dhidden")
+    got = {"layers." + k: v for k, v in layers.named_parameters()}
+    got["norm_f.weight"] = norm_f.weight
+    for k, want in g["grads"].items():
+        assert_close(got[k].grad, want, 2e-4, "d " + k)
+
+
+def test_masked_encoder_runs_mae_shape_bf16():
+    """FastMaskVim-T-shaped encoder, 75 % masking (49 of 196 tokens), bf16 autocast forward + backward: finite outputs and
+    gradients, kept ids sorted (random_masking, reference :740-774)."""
+    from fastvim_b200.vision_masked import MaskedEncoder, random_masking
+
+    torch.manual_seed(0)
+    x = torch.randn(3, 196, 8, device="cuda")
+    xm, mask, ids_restore, ids_keep = random_masking(x, 0.75)
+    assert xm.shape == (3, 49, 8) and int(mask.sum()) == 3 * 147
+    assert torch.equal(ids_keep, ids_keep.sort(dim=1).values)
+    assert torch.equal(xm, torch.gather(x, 1, ids_keep[..., None].expand(-1, -1, 8)))
+    enc = MaskedEncoder(img_size=224, depth=2, embed_dim=192).cuda().train()
+    imgs = torch.randn(3, 3, 224, 224, device="cuda")
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        latent, mask, ids_restore = enc(imgs, 0.75)
+    assert latent.shape == (3, 49, 192) and torch.isfinite(latent.float()).all()
+    latent.float().square().mean().backward()
+    for k, v in enc.named_parameters():
+        assert v.grad is not None and torch.isfinite(v.grad).all(), k

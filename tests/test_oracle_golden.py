@@ -179,3 +179,21 @@ def test_2dcompress_mixer_oracle_matches_reference_vectors(name):
     assert_close(dh, g["dhidden"], 5e-5, "dhidden")
     for k, want in g["grads"].items():
         assert_close(grads[k], want, 5e-5, "d" + k)
+
+
+def test_masked_block_rotate_indices_and_state_dict():
+    """Block_masked: the id rotation table equals the reference's double loop (models_mamba_faster_mae_vimdecoder_v2.py
+    :320-328) and the block stack loads a state dict written by the reference's own blocks."""
+    from fastvim_b200.vision_masked import Block_masked, create_block_masked
+
+    H, W = 4, 6
+    want = torch.zeros(H * W, dtype=torch.long)
+    for i in range(H):
+        for j in range(W):
+            want[i * W + j] = j * H + i
+    assert torch.equal(Block_masked.compute_rotate_indices(H, W), want)
+    g = load_golden("mblocks_d32_4x6_keep10")
+    layers = torch.nn.ModuleList([create_block_masked(32, rms_norm=True, residual_in_fp32=True, fused_add_norm=True,
+                                                      layer_idx=i, token_size=g["token_size"]) for i in range(g["depth"])])
+    sd = {k[len("layers."):]: v for k, v in g["state_dict"].items() if k.startswith("layers.")}
+    layers.load_state_dict(sd, strict=True)
