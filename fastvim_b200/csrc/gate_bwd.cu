@@ -17,6 +17,8 @@
 //                                                                   -> register accumulators, one atomicAdd per CTA
 // Persistent grid; tiles and row tables as in the forward kernel (tiles.cuh); x (+3 halo rows each side),
 // z and dy rows are staged with cp.async.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tiles.cuh"
 
@@ -271,6 +273,11 @@ extern "C" int fv_bwd_tiles_per_group(const fv_geom* g_, int dtype) {
     if (need8 > budget) maxlen = 4;
     const size_t need4 = dtype == FV_F32 ? gate_bwd_smem<float, 4>(g_->dim, threads) : gate_bwd_smem<bf16, 4>(g_->dim, threads);
     if (maxlen == 4 && need4 > budget) maxlen = 2;
+    static const char* force = getenv("FASTVIM_BWD_MAXLEN");   // tuning switch (tools/kbench.py): cap the tile length
+    if (force) {
+        const int f = atoi(force);
+        if (f >= 1 && f < maxlen) maxlen = f;
+    }
     return (g_->pool + maxlen - 1) / maxlen;
 }
 
