@@ -434,7 +434,7 @@ def run_train(a, model, w, Bt, dev, rank, world, local):
     import torch.distributed as dist
     import torch.nn.functional as F
 
-    from fastvim_b200 import _lib
+    from fastvim_b200 import _lib, parallel
 
     img = w["img"]
     model.train()
@@ -479,11 +479,11 @@ def run_train(a, model, w, Bt, dev, rank, world, local):
             with torch.cuda.graph(g1):
                 static_loss = fwd_bwd(model, static_x, static_t)
                 grads = [p.grad for p in params]
-                flat = torch.cat([gr.reshape(-1) for gr in grads]) if world > 1 else None
+                flat = parallel.flatten_grads(grads) if world > 1 else None
             launches = _lib.launch_count()
             with torch.cuda.graph(g2, pool=g1.pool()):
                 if world > 1:
-                    torch._foreach_copy_(grads, [c.view_as(gr) for c, gr in zip(flat.split([gr.numel() for gr in grads]), grads)])
+                    parallel.scatter_mean_grads_(grads, flat, world)
                 opt.step()
 
             def step(x, t):
@@ -491,7 +491,7 @@ def run_train(a, model, w, Bt, dev, rank, world, local):
                 static_t.copy_(t, non_blocking=True)
                 g1.replay()
                 if world > 1:
-                    dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+                    parallel.allreduce_sum_(flat)
                 g2.replay()
                 return static_loss
         except Exception as ex:  # capture not possible: fall back to the eager step
@@ -564,7 +564,7 @@ def run_train(a, model, w, Bt, dev, rank, world, local):
                 "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": round(ms_total / a.steps, 4),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": a.workload, "desc": w["desc"], "batch_per_gpu": Bt, "global_batch": Bt * world,
-                           "sharding": (f"batch-sharded x{world}, one NCCL all-reduce (AVG) of the flattened gradients between the "
+                           "sharding": (f"batch-sharded x{world}, one NCCL all-reduce of the flattened gradients (fastvim_b200.parallel) between the "
                                         "forward+backward graph and the optimizer graph") if mode == "graph" else
                                        f"batch-sharded DDP x{world}, NCCL gradient all-reduce overlapped with backward",
                            "optimizer": "AdamW fused, lr 1e-3, wd 0.05, fp32 master weights",

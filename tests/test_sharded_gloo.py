@@ -105,3 +105,38 @@ def test_shard_ranges_cover_all_channels():
         assert all(spans[i][1] == spans[i + 1][0] for i in range(G - 1))
     with pytest.raises(ValueError):
         shard_range(100, 0, 8)
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fastvim_b200 import parallel
+
+    torch.manual_seed(0)
+    shapes = [(7, 3), (5,), (2, 4, 6), (1,)]
+    base = [torch.randn(*s) for s in shapes]                      # identical on every rank
+    grads = [b * (rank + 1) for b in base]                        # rank-dependent "local" gradients
+    flat = parallel.flatten_grads(grads)
+    assert flat.shape == (sum(b.numel() for b in base),)
+    parallel.allreduce_sum_(flat)
+    parallel.scatter_mean_grads_(grads, flat, world)
+    want_scale = sum(range(1, world + 1)) / world                 # mean over ranks of (rank + 1)
+    err = max(float((g - b * want_scale).abs().max()) for g, b in zip(grads, base))
+    if rank == 0:
+        q.put(err)
+    dist.destroy_process_group()
+
+
+def test_batch_sharded_gradient_exchange_world2_gloo():
+    """The N > 1 training path: gradients flattened, summed with ONE collective, scaled by 1/world while scattered back."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29950 + os.getpid() % 40
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert err < 1e-6, err
