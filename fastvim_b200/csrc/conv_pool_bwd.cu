@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "tiles.cuh"
+#include "stream.cuh"
 
 namespace fv {
 
@@ -158,23 +159,6 @@ conv_pool_bwd_kernel(Geom g, int64_t ntiles, int tiles_per_img, int tiles_per_gr
 // A CTA (<= 256 channel pairs) walks runs of <= 56 tokens (3-token halo each side: ~12 % extra L2 reads and SiLU
 // derivatives; the walk itself is branch-free, ownership of halo positions is applied with selects) and keeps the conv weight / bias gradient partials in registers across all its runs: one atomic per CTA
 // and parameter at the end.  The only shared memory is the run's row table (token -> memory row, pooled index).
-template <typename T> struct Pair;
-template <> struct Pair<bf16> {
-    typedef uint32_t type;
-    static __device__ __forceinline__ type ld(const bf16* p) { return __ldg(reinterpret_cast<const unsigned int*>(p)); }
-    static __device__ __forceinline__ type zero() { return 0u; }
-    static __device__ __forceinline__ float2 up(type v) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v)); }
-    static __device__ __forceinline__ void st(bf16* p, float2 v) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v.x, v.y); }
-};
-template <> struct Pair<float> {
-    typedef float2 type;
-    static __device__ __forceinline__ type ld(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
-    static __device__ __forceinline__ type zero() { return make_float2(0.f, 0.f); }
-    static __device__ __forceinline__ float2 up(type v) { return v; }
-    static __device__ __forceinline__ void st(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
-};
-__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
-__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
 // d silu / dx; FAST (bf16 I/O): sigmoid through one tanh.approx MUFU op
 template <bool FAST>
 __device__ __forceinline__ float dsilu_sel(float x) {
@@ -324,15 +308,6 @@ conv_pool_bwd_stream_kernel(Geom g, int nseg, int seg_len, int64_t nitems, int n
         atomicAdd(dcb + d0, abf.x); atomicAdd(dcb + d0 + 1, abf.y);
         atomicAdd(dcb + D + d0, abb.x); atomicAdd(dcb + D + d0 + 1, abb.y);
     }
-}
-
-// block size for the streaming kernel: the largest multiple of 32 that is <= 256 and divides dim / 2 (0: none)
-static int stream_block(int D) {
-    if (D % 64 != 0) return 0;
-    const int pairs = D / 2;
-    for (int t = 256; t >= 32; t -= 32)
-        if (pairs % t == 0) return t;
-    return 0;
 }
 
 template <typename T>
