@@ -51,6 +51,8 @@ SIGNATURES = {
     "fv_rowdot_bdl": [_I, _I, _I, _L, _P, _P, _P, _P],
     "fv_bwd_tiles_per_group": [_G, _I],
     "fv_gate_bwd": [_G, _I, _P, _P, _L, _L, _P, _L, _L, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P],
+    "fv_gate_bwd_stream_supported": [_G, _L, _L],
+    "fv_gate_bwd_stream": [_G, _I, _P, _P, _L, _L, _P, _L, _L, _P, _P, _P, _P, _P, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P],
     "fv_scan_bwd_planes": [_G],
     "fv_scan_bwd_short_supported": [_G, _I],
     "fv_scan_bwd_short": [_G, _I, _I, _P, _P, _L, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P],

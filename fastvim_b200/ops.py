@@ -18,6 +18,8 @@ from ._lib import FV_BF16, FV_F32, FV_POOL_MAX, FV_POOL_MEAN, fv_geom
 
 Tensor = torch.Tensor
 
+# streaming gate backward (statistics pass + apply pass, csrc/gate_bwd_stream.cu); "0" = the tiled kernel
+GATE_BWD_STREAM = os.environ.get("FASTVIM_GATE_BWD_STREAM", "1") != "0"
 # short pooled sequences (Lp <= 16): fv_scan_bwd_short (two states per thread, dt_proj by GEMM); "0" = previous kernel
 SCAN_BWD_SHORT = os.environ.get("FASTVIM_SCAN_BWD_SHORT", "1") != "0"
 
@@ -359,6 +361,19 @@ def gate_bwd(x: Tensor, z: Tensor, dy: Tensor, s: Tensor, geom: Geometry, conv_w
     ldx, bs = _tokmajor(x, "x")
     assert _tokmajor(z, "z") == (ldx, bs) and _tokmajor(dz, "dz") == (ldx, bs)
     lddy, dybs = _tokmajor(dy, "dy")
+    g = geom.c_struct(B, D)
+    if GATE_BWD_STREAM and geom.inner == 1 and _lib.lib().fv_gate_bwd_stream_supported(C.byref(g), ldx, lddy):
+        f32 = dict(device=x.device, dtype=torch.float32)
+        e = torch.empty((B, L, D), device=x.device, dtype=x.dtype)
+        ds = torch.zeros((1, B, geom.Lp, D), **f32)
+        dD = torch.zeros((2, D), **f32)
+        dlw = torch.zeros(D, **f32) if ln_w is not None else None
+        dlb = torch.zeros(D, **f32) if ln_w is not None else None
+        stats = torch.zeros((B, L, 4), **f32) if ln_w is not None else None
+        _lib.call("fv_gate_bwd_stream", C.byref(g), _dt(x), _p(x), _p(z), ldx, bs, _p(dy), lddy, dybs, _p(s), _p(conv_w),
+                  _p(conv_b), _p(Dskip), _p(ln_w), _p(ln_b), float(eps), _p(stats), _p(dz), _p(e), _p(ds), _p(dD), _p(dlw),
+                  _p(dlb), _stream(x))
+        return e, ds, dD, dlw, dlb
     tpg = bwd_tiles_per_group(geom, B, D, x.dtype)
     e = torch.empty((B, L, D), device=x.device, dtype=x.dtype)
     ds = torch.empty((tpg, B, geom.Lp, D), device=x.device, dtype=torch.float32)

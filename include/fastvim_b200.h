@@ -223,6 +223,17 @@ int fv_gate_bwd(const fv_geom* g, int dtype, const void* x, const void* z, int64
                 void* dz, void* e_out, float* ds_planes, float* dDskip, float* dln_w, float* dln_b,
                 void* stream);
 
+/* K2b-bwd, streaming form (csrc/gate_bwd_stream.cu): same inputs and outputs as fv_gate_bwd, but LayerNorm's coupling of
+ * the channels is carried by four per-token sums in `stats` (B, L, 4) fp32 (caller zero-fills; NULL without LayerNorm), so
+ * both passes are channel-local and stream (two channels per thread, register windows).  `ds` is ONE plane (B, Lp, dim)
+ * fp32, ACCUMULATED (caller zero-fills).  fv_gate_bwd_stream_supported: plain geometry, dim % 64 == 0, even strides. */
+int fv_gate_bwd_stream_supported(const fv_geom* g, int64_t ldxz, int64_t lddy);
+int fv_gate_bwd_stream(const fv_geom* g, int dtype, const void* x, const void* z, int64_t ldxz, int64_t xz_bstride,
+                       const void* dy, int64_t lddy, int64_t dy_bstride, const float* s, const float* conv_w,
+                       const float* conv_b, const float* Dskip, const float* ln_w, const float* ln_b, float eps,
+                       float* stats, void* dz, void* e_out, float* ds, float* dDskip, float* dln_w, float* dln_b,
+                       void* stream);
+
 /* K2a-bwd.  ds (nplanes_ds, B, Lp, dim) fp32 (summed on load; the same gradient feeds both directions).
  * Outputs: du, ddelta (2, B, Lp, dim) dtype (ddelta = gradient of the dt_proj pre-activation);
  * dbc_planes (fv_scan_bwd_planes(g), 2, B*Lp, 2N) fp32 partial sums over channel columns of [dB | dC]
