@@ -18,8 +18,9 @@ from ._lib import FV_BF16, FV_F32, FV_POOL_MAX, FV_POOL_MEAN, fv_geom
 
 Tensor = torch.Tensor
 
-# streaming gate backward (statistics pass + apply pass, csrc/gate_bwd_stream.cu); "0" = the tiled kernel
-GATE_BWD_STREAM = os.environ.get("FASTVIM_GATE_BWD_STREAM", "1") != "0"
+# streaming gate backward (statistics pass + apply pass, csrc/gate_bwd_stream.cu).  Parity-green but measured SLOWER than
+# the tiled kernel (408 vs 386 us at FastVim-B, 260 vs 191 us at FastVim-T: DESIGN.md 3b), so it is opt-in ("1").
+GATE_BWD_STREAM = os.environ.get("FASTVIM_GATE_BWD_STREAM", "0") == "1"
 # short pooled sequences (Lp <= 16): fv_scan_bwd_short (two states per thread, dt_proj by GEMM); "0" = previous kernel
 SCAN_BWD_SHORT = os.environ.get("FASTVIM_SCAN_BWD_SHORT", "1") != "0"
 

@@ -900,3 +900,30 @@ def test_masked_encoder_runs_mae_shape_bf16():
     latent.float().square().mean().backward()
     for k, v in enc.named_parameters():
         assert v.grad is not None and torch.isfinite(v.grad).all(), k
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("d_model,ts,norm", [(192, (14, 14), True), (64, (5, 9), True), (64, (20, 2), False), (768, (14, 14), True)])
+def test_mixer_backward_streaming_gate_bwd_vs_oracle(dtype, d_model, ts, norm, monkeypatch):
+    """The opt-in two-pass streaming gate backward (fv_gate_bwd_stream: per-token LayerNorm sums, then a channel-local
+    apply pass) gives the same gradients as the oracle."""
+    from fastvim_b200 import ops
+
+    monkeypatch.setattr(ops, "GATE_BWD_STREAM", True)
+    p = O.random_mixer_params(d_model, seed=5)
+    if not norm:
+        p = {k: v for k, v in p.items() if not k.startswith("layernorm")}
+    torch.manual_seed(1)
+    h = torch.randn(2, ts[0] * ts[1], d_model)
+    dout = torch.randn(2, ts[0] * ts[1], d_model)
+    m = _mixer_from_params(p, ts, use_norm_after_ssm=norm).train()
+    hc = h.cuda().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        out = m(hc)
+    out.backward(dout.cuda().to(out.dtype))
+    want_out, want_dh, want = _oracle_mixer_grads(h, p, ts, dout, use_norm_after_ssm=norm)
+    tol = TOL[dtype]
+    assert_close(hc.grad, want_dh, tol, "d hidden")
+    got = dict(m.named_parameters())
+    for k, g in want.items():
+        assert_close(got[k].grad, g, tol if dtype == torch.float32 else 2 * tol, f"d {k}")
