@@ -1,0 +1,106 @@
+"""CPU, build container only: the UNMODIFIED reference model files run on top of the import shims.
+
+With ``fastvim_b200/compat`` ahead of the reference tree on ``sys.path``, the reference's own ``models/fastvim.py``,
+``models/channel_wise_tokenization/models_channel_mamba_faster{,_2dcompress}.py`` and
+``models/mae/models_mamba_faster_mae_vimdecoder_v2.py`` import ``mamba_ssm.modules.*`` / ``mamba_ssm.ops.*`` and get the
+B200 mixers, norm and operator functions -- no source change.  Construction and state-dict
+layout are checked here; the arithmetic is covered by the GPU parity tests.  Skipped where /root/reference does not
+exist (the GPU box)."""
+import importlib
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "models")), reason="reference tree not present")
+
+
+@pytest.fixture()
+def shimmed():
+    """sys.path = [compat, repo, reference]; third-party imports of the reference (timm, mmdet, ...) stubbed by the oracle's
+    loader; every mamba_ssm / models module imported during the test is dropped again afterwards."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_loader
+
+    def purge():
+        for k in [k for k in sys.modules if k.split(".")[0] in ("mamba_ssm", "models")]:
+            del sys.modules[k]
+
+    saved = {k: v for k, v in sys.modules.items() if k.split(".")[0] in ("mamba_ssm", "models")}
+    purge()
+    ref_loader._install_shims()
+    paths = [os.path.join(ROOT, "fastvim_b200", "compat"), ROOT, REF]
+    for p in reversed(paths):
+        sys.path.insert(0, p)
+    try:
+        yield
+    finally:
+        for p in paths:
+            sys.path.remove(p)
+        purge()
+        sys.modules.update(saved)
+
+
+def test_reference_fastvim_model_builds_on_the_b200_mixer(shimmed):
+    from fastvim_b200 import mixer, norm, vision
+
+    fv = importlib.import_module("models.fastvim")
+    assert fv.__file__.startswith(REF) and fv.Mamba is mixer.Mamba and fv.RMSNorm is norm.RMSNorm
+    torch.manual_seed(0)
+    ref_model = fv.VisionMamba(img_size=(64, 96), patch_size=16, stride=16, embed_dim=32, depth=3, num_classes=10,
+                               rms_norm=True, residual_in_fp32=True, fused_add_norm=True, final_pool_type="mean",
+                               if_abs_pos_embed=True, drop_path_rate=0.0)
+    assert all(isinstance(l.mixer, mixer.Mamba) for l in ref_model.layers)
+    assert ref_model.layers[1].mixer.num_of_rows == 6 and ref_model.layers[1].mixer.num_of_col == 4   # odd layer: swapped
+    ours = vision.VisionMamba(img_size=(64, 96), embed_dim=32, depth=3, num_classes=10, rms_norm=True,
+                              residual_in_fp32=True, fused_add_norm=True, final_pool_type="mean", drop_path_rate=0.0)
+    ours.load_state_dict(ref_model.state_dict(), strict=True)        # same parameter names and shapes, both directions
+    ref_model.load_state_dict(ours.state_dict(), strict=True)
+
+
+def test_reference_channel_models_build_on_the_b200_mixers(shimmed):
+    from fastvim_b200 import mixer_channel, mixer_channel_2dcompress, vision_channel
+
+    cm = importlib.import_module("models.channel_wise_tokenization.models_channel_mamba_faster")
+    assert cm.__file__.startswith(REF) and cm.Mamba is mixer_channel.Mamba
+    kw = dict(img_size=(32, 64), patch_size=16, stride=16, depth=3, embed_dim=32, channels=3, num_classes=7, rms_norm=True,
+              residual_in_fp32=True, fused_add_norm=True, drop_path_rate=0.0, scan_order="Channel-First", hcs=False)
+    ref_model = cm.VisionMamba(**kw)
+    assert all(isinstance(l.mixer, mixer_channel.Mamba) for l in ref_model.layers)
+    ours = vision_channel.VisionMamba(**kw)
+    ours.load_state_dict(ref_model.state_dict(), strict=True)
+    ref_model.load_state_dict(ours.state_dict(), strict=True)
+    c2 = importlib.import_module("models.channel_wise_tokenization.models_channel_mamba_faster_2dcompress")
+    assert c2.Mamba is mixer_channel_2dcompress.Mamba
+    # the reference's own 2dcompress MODEL file cannot be constructed: its create_block passes max_tokens_per_patch to a
+    # Block.__init__ that does not take it (models_channel_mamba_faster_2dcompress.py:363 vs :206-219) -- a reference quirk;
+    # the mixer class it would use is checked directly.
+    with pytest.raises(TypeError):
+        c2.VisionMamba(**kw)
+    geoms = [c2.Mamba(32, token_size=[2, 4], layer_idx=i, scan_order="Channel-First").channel_geometry(3) for i in range(3)]
+    assert (geoms[0].outer, geoms[0].pool, geoms[0].inner) == (2, 12, 1)       # rows x (cols * tpp)
+    assert (geoms[2].outer, geoms[2].pool, geoms[2].inner) == (1, 8, 3)        # every third layer: channelwise scan
+
+
+def test_reference_mae_encoder_blocks_build_on_the_b200_masked_mixer(shimmed):
+    from fastvim_b200 import mixer_masked, vision_masked
+
+    # the MAE file also imports the plain-Vim mixer for its DECODER (mamba_ssm.modules.mamba_simple: the reference's
+    # baseline architecture, outside the FastVim hot path and not shimmed); a placeholder satisfies the import here.
+    import types
+
+    stub = types.ModuleType("mamba_ssm.modules.mamba_simple")
+    stub.Mamba = type("Mamba", (torch.nn.Module,), {})
+    sys.modules["mamba_ssm.modules.mamba_simple"] = stub
+    mm = importlib.import_module("models.mae.models_mamba_faster_mae_vimdecoder_v2")
+    assert mm.__file__.startswith(REF) and mm.Mamba_masked is mixer_masked.Mamba_masked
+    ref_blk = mm.create_block_masked(32, rms_norm=True, residual_in_fp32=True, fused_add_norm=True, layer_idx=1,
+                                     token_size=(4, 6))
+    assert isinstance(ref_blk.mixer, mixer_masked.Mamba_masked) and ref_blk.mixer.num_of_rows == 6
+    ours = vision_masked.create_block_masked(32, rms_norm=True, residual_in_fp32=True, fused_add_norm=True, layer_idx=1,
+                                             token_size=(4, 6))
+    ours.load_state_dict(ref_blk.state_dict(), strict=True)
+    assert torch.equal(ours.rotate_indices, ref_blk.rotate_indices)
