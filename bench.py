@@ -385,7 +385,8 @@ def run_ours(a):
             top = max(agg, key=lambda k: agg[k][0])
             k = kern_table[top]
             roof = {"kernel": top, "bound": "hbm", "achieved": k["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": round(k["gbs"] / peaks["hbm_gbs"], 4), "traffic": load_traffic(top),
+                    "frac": round(k["gbs"] / peaks["hbm_gbs"], 4), "frac_of_nominal_8tbs": round(k["gbs"] / 8000.0, 4),
+                    "traffic": load_traffic(top),
                     "alg_bytes_per_launch": k["alg_bytes"], "avg_us": k["avg_us"], "peak_source": peak_src,
                     "share_of_step": round(k["ms_per_step"] / ms_step, 4)}
 
