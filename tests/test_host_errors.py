@@ -95,3 +95,23 @@ def test_c_abi_reports_bad_arguments_without_launching():
     assert l.fv_gate_bwd_stream_supported(ctypes.byref(g_odd), 192, 96) == 0
     rc = l.fv_causal_conv1d_bwd(0, 1, 4, 8, null, 32, 8, null, null, 1, null, null, 32, 8, null, null, null)
     assert rc != 0 and b"null pointer" in l.fv_last_error()
+
+
+def test_random_masking_properties_cpu():
+    """random_masking (reference models_mamba_faster_mae_vimdecoder_v2.py:740-774): kept ids sorted, mask / ids_restore
+    consistent, x_masked is the gather of the kept tokens."""
+    from fastvim_b200.vision_masked import Block_masked, random_masking
+
+    torch.manual_seed(0)
+    x = torch.randn(4, 24, 5)
+    xm, mask, ids_restore, ids_keep = random_masking(x, 0.75)
+    assert xm.shape == (4, 6, 5) and ids_keep.shape == (4, 6)
+    assert torch.equal(ids_keep, ids_keep.sort(dim=1).values)
+    assert torch.equal(xm, torch.gather(x, 1, ids_keep[..., None].expand(-1, -1, 5)))
+    assert torch.equal(mask.sum(1), torch.full((4,), 18.0))
+    kept = torch.zeros(4, 24).scatter_(1, ids_keep, 1.0)
+    assert torch.equal(mask, 1.0 - kept)                          # 0 = keep, 1 = remove, in original token order
+    assert torch.equal(torch.gather(ids_restore, 1, ids_keep), torch.arange(6)[None].expand(4, -1))
+    # odd-layer id rotation: rotating a 4 x 6 grid twice (with swapped sizes) is the identity
+    r1, r2 = Block_masked.compute_rotate_indices(4, 6), Block_masked.compute_rotate_indices(6, 4)
+    assert torch.equal(r2[r1], torch.arange(24))
