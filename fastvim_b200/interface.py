@@ -51,6 +51,26 @@ def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_
     return (out, last) if return_last_state else out
 
 
+def selective_scan_fn_compressed(u, u_compressed, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
+                                 return_last_state=False):
+    """The 6-tensor form of the reference's own kernel package (``fastvim_kernel/mamba-1p1p1/faster_mamba_ssm/ops/
+    selective_scan_interface.py:129-159``, semantics ``selective_scan_ref`` :162-252): scan over the pooled
+    ``u_compressed`` (batch, dim, Lc), output repeated ``L // Lc`` times, D skip on the full-resolution ``u``
+    (batch, dim, L), optional ``silu(z)`` gate.  Runs on ``fv_selective_scan_fwd/_bwd`` + ``fv_bcast_skip_bdl_fwd``;
+    differentiable, including with ``z`` (the reference's backward raises for ``z``, :79-80, and is fp32-only)."""
+    batch, dim, L = u.shape
+    Lc = u_compressed.shape[2]
+    if L % Lc:
+        raise ValueError("Compression factor must be integer")                      # reference :191
+    cfac = L // Lc
+    res = selective_scan_fn(u_compressed, delta, A, B, C, None, None, delta_bias, delta_softplus, return_last_state)
+    s, last = res if return_last_state else (res, None)
+    out = fv_autograd.BcastSkipFn.apply(s, u.to(s.dtype).contiguous() if D is not None else None, D, Lc, cfac, 1)
+    if z is not None:
+        out = (out.float() * torch.nn.functional.silu(z.float())).to(out.dtype)
+    return (out, last) if return_last_state else out
+
+
 # --------------------------------------------------------------------------- fused "inner" functions
 # Differentiable: every kernel call below is a torch.autograd.Function over a forward / backward kernel pair
 # (autograd.CausalConv1dFn, PoolBdlFn, SelectiveScanFn, BcastSkipFn); the x_proj / dt_proj contractions are torch

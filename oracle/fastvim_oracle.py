@@ -79,6 +79,27 @@ def selective_scan_oracle(u, delta, A, B, C, D=None, z=None, delta_bias=None,
     return (y, h) if return_last_state else y
 
 
+def compressed_scan_oracle(u_full, u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_softplus=False,
+                           return_last_state=False):
+    """The 6-tensor "compressed" scan of the reference's own kernel package (``fastvim_kernel/mamba-1p1p1/
+    faster_mamba_ssm/ops/selective_scan_interface.py:162-252`` ``selective_scan_ref``): the recurrence runs over the
+    pooled ``u`` (Bt, Dm, Lc); its output is repeated ``cfac = L // Lc`` times along the sequence, the D skip uses the
+    full-resolution ``u_full`` (Bt, Dm, L), then the optional ``silu(z)`` gate (full resolution)."""
+    assert u_full.shape[2] % u.shape[2] == 0, "Compression factor must be integer"      # :191
+    cfac = u_full.shape[2] // u.shape[2]
+    dtype_in = u.dtype
+    cd = torch.float64 if u.dtype == torch.float64 else torch.float32
+    res = selective_scan_oracle(u.to(cd), delta.to(cd), A, B, C, None, None, delta_bias, delta_softplus,
+                                return_last_state=True, compute_dtype=cd)
+    y, last = res
+    y = torch.repeat_interleave(y, cfac, dim=2)                                         # :244
+    out = y if D is None else y + u_full.to(cd) * D.to(cd)[None, :, None]               # :245
+    if z is not None:
+        out = out * F.silu(z.to(cd))                                                    # :246-247
+    out = out.to(dtype_in)
+    return (out, last) if return_last_state else out
+
+
 # --------------------------------------------------------------------------- conv
 def causal_conv1d_oracle(x, weight, bias=None, activation="silu"):
     """Depthwise causal conv over the last axis.  x: (Bt, Dm, L), weight: (Dm, W).

@@ -96,7 +96,7 @@ def main():
         json.dump(manifest, f, indent=1, sort_keys=True)
 
 
-if __name__ == "__main__" and "--channel-model" not in sys.argv and "--2dcompress" not in sys.argv and "--masked-blocks" not in sys.argv:
+if __name__ == "__main__" and "--channel-model" not in sys.argv and "--2dcompress" not in sys.argv and "--masked-blocks" not in sys.argv and "--compressed" not in sys.argv:
     main()
 
 
@@ -216,3 +216,57 @@ def gen_masked_blocks():
 
 if __name__ == "__main__" and "--masked-blocks" in sys.argv:
     gen_masked_blocks()
+
+
+def gen_compressed_scan():
+    """The 6-tensor compressed scan of the reference's own kernel package (fastvim_kernel/mamba-1p1p1/faster_mamba_ssm/
+    ops/selective_scan_interface.py:162-252 selective_scan_ref), generator as in its test
+    (fastvim_kernel/mamba-1p1p1/tests/test_compressed_scan.py: seed 0, dstate 8, A = -0.5 rand, delta = 0.5 rand,
+    delta_bias = 0.5 rand), forward + autograd gradients on CPU."""
+    import contextlib
+    import importlib
+    import io
+    import types
+
+    sys.modules.setdefault("faster_selective_scan_cuda", types.ModuleType("faster_selective_scan_cuda"))
+    kroot = "/root/reference/fastvim_kernel/mamba-1p1p1"
+    if kroot not in sys.path:
+        sys.path.insert(0, kroot)
+    fssi = importlib.import_module("faster_mamba_ssm.ops.selective_scan_interface")
+    manifest_path = os.path.join(GOLD, "manifest.json")
+    manifest = json.load(open(manifest_path))
+    for name, (bs, dim, L, cfac, has_D, has_z) in (("cscan_L128_c8_D", (2, 4, 128, 8, True, False)),
+                                                   ("cscan_L254_c2_noD", (1, 1, 254, 2, False, False)),
+                                                   ("cscan_L196_c14_D_z", (2, 6, 196, 14, True, True))):
+        torch.random.manual_seed(0)
+        ds, Lc = 8, L // cfac
+        ins = dict(A=-0.5 * torch.rand(dim, ds), B=torch.randn(bs, ds, Lc), C=torch.randn(bs, ds, Lc),
+                   D=torch.randn(dim) if has_D else None, z=torch.randn(bs, dim, L) if has_z else None,
+                   delta_bias=0.5 * torch.rand(dim), u=torch.randn(bs, dim, L), delta=0.5 * torch.rand(bs, dim, Lc))
+        ins["u_compressed"] = ins["u"].reshape(bs, dim, Lc, cfac).mean(dim=3)        # pooled over consecutive positions
+
+        def run(fn):
+            lv = {k: (v.detach().clone().requires_grad_() if v is not None else None) for k, v in ins.items()}
+            with contextlib.redirect_stdout(io.StringIO()):                          # the reference prints shapes
+                out, st = fn(lv["u"], lv["u_compressed"], lv["delta"], lv["A"], lv["B"], lv["C"], lv["D"], z=lv["z"],
+                             delta_bias=lv["delta_bias"], delta_softplus=True, return_last_state=True)
+            torch.manual_seed(1)
+            g = torch.randn_like(out)
+            out.backward(g)
+            return out.detach(), st.detach(), {k: v.grad for k, v in lv.items() if v is not None and v.grad is not None}, g
+
+        out_r, st_r, gr_r, g = run(fssi.selective_scan_ref)
+        out_o, st_o, gr_o, _ = run(O.compressed_scan_oracle)
+        errs = {"out": relerr(out_o, out_r), "state": relerr(st_o, st_r)}
+        errs.update({"d" + k: relerr(gr_o[k], gr_r[k]) for k in gr_r})
+        assert max(errs.values()) < 2e-5, errs
+        path = os.path.join(GOLD, name + ".pt")
+        torch.save(dict(inputs={k: v for k, v in ins.items()}, cfac=cfac, dout=g, out=out_r, last_state=st_r, grads=gr_r), path)
+        manifest[name] = dict(oracle_vs_ref=max(errs.values()), bytes=os.path.getsize(path))
+        print(f"  {name}: oracle_vs_ref {max(errs.values()):.2e}")
+    with open(manifest_path, "w") as f:
+        json.dump(manifest, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__" and "--compressed" in sys.argv:
+    gen_compressed_scan()

@@ -91,6 +91,12 @@ def test_compat_shims_resolve_reference_module_paths():
 
         assert msf.Mamba is mixer.Mamba and mscf.Mamba is mixer_channel.Mamba
         assert ln.RMSNorm is norm.RMSNorm and ln.rms_norm_fn is norm.rms_norm_fn and ln.layer_norm_fn is norm.layer_norm_fn
+        from fastvim_b200 import mixer_channel_2dcompress, mixer_masked
+        assert importlib.import_module("mamba_ssm.modules.mamba_simple_masked_faster").Mamba_masked is mixer_masked.Mamba_masked
+        assert importlib.import_module("mamba_ssm.modules.mamba_simple_masked_faster_v2").Mamba_masked is mixer_masked.Mamba_masked
+        assert importlib.import_module("mamba_ssm.modules.mamba_simple_channel_faster_2dcompress").Mamba is mixer_channel_2dcompress.Mamba
+        assert (importlib.import_module("faster_mamba_ssm.ops.selective_scan_interface").selective_scan_fn
+                is interface.selective_scan_fn_compressed)
         for fn in ("selective_scan_fn", "mamba_inner_fn_no_out_proj", "mamba_inner_fn_no_out_proj_withoutZ",
                    "FastVim_mamba_inner_fn_no_out_proj_withoutZ"):
             assert getattr(ssi, fn) is getattr(interface, fn)
@@ -101,6 +107,6 @@ def test_compat_shims_resolve_reference_module_paths():
                 "dt_proj_b.bias", "A_log", "A_b_log", "D", "D_b", "layernorm.weight", "out_proj.weight"} <= names
     finally:
         sys.path.remove(compat)
-        for k in [k for k in sys.modules if k == "mamba_ssm" or k.startswith("mamba_ssm.")]:
+        for k in [k for k in sys.modules if k.split(".")[0] in ("mamba_ssm", "faster_mamba_ssm")]:
             del sys.modules[k]
         sys.modules.update(saved)

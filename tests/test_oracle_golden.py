@@ -197,3 +197,55 @@ def test_masked_block_rotate_indices_and_state_dict():
                                                       layer_idx=i, token_size=g["token_size"]) for i in range(g["depth"])])
     sd = {k[len("layers."):]: v for k, v in g["state_dict"].items() if k.startswith("layers.")}
     layers.load_state_dict(sd, strict=True)
+
+
+CSCAN = ["cscan_L128_c8_D", "cscan_L254_c2_noD", "cscan_L196_c14_D_z"]
+
+
+@pytest.mark.parametrize("name", CSCAN)
+def test_compressed_scan_oracle_matches_reference_vectors(name):
+    """6-tensor compressed scan (fastvim_kernel/.../faster_mamba_ssm/ops/selective_scan_interface.py:162-252): oracle forward,
+    last state and autograd gradients against the reference's own selective_scan_ref."""
+    g = load_golden(name)
+    lv = {k: (v.clone().requires_grad_() if v is not None else None) for k, v in g["inputs"].items()}
+    out, st = O.compressed_scan_oracle(lv["u"], lv["u_compressed"], lv["delta"], lv["A"], lv["B"], lv["C"], lv["D"], z=lv["z"],
+                                       delta_bias=lv["delta_bias"], delta_softplus=True, return_last_state=True)
+    out.backward(g["dout"])
+    assert_close(out, g["out"], 2e-5, "out")
+    assert_close(st, g["last_state"], 2e-5, "last_state")
+    for k, want in g["grads"].items():
+        assert_close(lv[k].grad, want, 2e-5, "d" + k)
+
+
+@pytest.mark.parametrize("name", CSCAN)
+def test_compressed_scan_host_glue_with_cpu_stand_ins(name, monkeypatch):
+    """The host glue of interface.selective_scan_fn_compressed (argument order, compression factor, D skip on the
+    full-resolution u, z gate, last state) checked on CPU: the two kernels it calls are replaced by oracle stand-ins with the
+    kernels' exact signatures.  (The kernels themselves are covered by the GPU parity tests.)"""
+    from fastvim_b200 import interface, ops
+
+    def scan_fwd(u, delta, A, B, Cm, D, z, delta_bias, delta_softplus, want_last_state=False):
+        assert B.dim() == 4 and Cm.dim() == 4 and u.is_contiguous() and delta.is_contiguous()
+        out, last = O.selective_scan_oracle(u, delta, A, B, Cm, D, z, delta_bias, delta_softplus, return_last_state=True)
+        return out, (last if want_last_state else None)
+
+    def bcast(s, xc, Dskip, outer, pool, inner=1):
+        assert s.shape[-1] == outer * inner and (xc is None or xc.shape[-1] == outer * pool * inner)
+        v = O.broadcast_oracle(s, outer, pool, inner)
+        return v if Dskip is None else v + Dskip[None, :, None] * xc
+
+    monkeypatch.setattr(ops, "selective_scan_fwd", scan_fwd)
+    monkeypatch.setattr(ops, "bcast_skip_bdl_fwd", bcast)
+    g = load_golden(name)
+    i = g["inputs"]
+    with torch.no_grad():
+        out, st = interface.selective_scan_fn_compressed(i["u"], i["u_compressed"], i["delta"], i["A"], i["B"], i["C"], i["D"],
+                                                         z=i["z"], delta_bias=i["delta_bias"], delta_softplus=True,
+                                                         return_last_state=True)
+        out_only = interface.selective_scan_fn_compressed(i["u"], i["u_compressed"], i["delta"], i["A"], i["B"], i["C"], i["D"],
+                                                          z=i["z"], delta_bias=i["delta_bias"], delta_softplus=True)
+    assert_close(out, g["out"], 2e-5, "out")
+    assert_close(st, g["last_state"], 2e-5, "last_state")
+    assert torch.equal(out, out_only)
+    with pytest.raises(ValueError):
+        interface.selective_scan_fn_compressed(i["u"][..., :-1], i["u_compressed"], i["delta"], i["A"], i["B"], i["C"])
