@@ -223,6 +223,30 @@ class PoolBdlFn(torch.autograd.Function):
         return ops.bcast_skip_bdl_fwd((du * (scale / pool)).contiguous(), None, None, outer, pool, inner), None, None, None, None
 
 
+class PoolMaxBdlFn(torch.autograd.Function):
+    """Max pool over the ``pool`` axis of a (batch, dim, outer*pool*inner) sequence (the live module branch,
+    ``mamba_simple_faster.py:299-305``, ``mamba_simple_channel_faster.py:258-289``: ``x.reshape(...).max(dim).values``).
+    Forward on ``fv_pool_bdl_fwd``; backward routes the pooled gradient to the FIRST position that attains the maximum
+    (what ``torch.max(dim)`` differentiates to), as an elementwise mask."""
+
+    @staticmethod
+    def forward(ctx, xc, outer, pool, inner):
+        u = ops.pool_bdl_fwd(xc, outer, pool, inner, "max", 1.0)
+        ctx.save_for_backward(xc, u)
+        ctx.meta = (outer, pool, inner)
+        return u
+
+    @staticmethod
+    def backward(ctx, du):
+        xc, u = ctx.saved_tensors
+        outer, pool, inner = ctx.meta
+        B, D, L = xc.shape
+        hit = xc.view(B, D, outer, pool, inner) == u.view(B, D, outer, 1, inner)
+        first = hit & (hit.cumsum(dim=3) == 1)
+        dx = first.to(du.dtype) * du.reshape(B, D, outer, 1, inner)
+        return dx.reshape(B, D, L).to(xc.dtype), None, None, None
+
+
 class BcastSkipFn(torch.autograd.Function):
     """out = repeat_interleave(s) + D * xc (``selective_scan_interface.py:570-571``); backward: ds = sum over the pool
     axis of dout, dxc = D * dout, dD = sum dout * xc (``:636-642``)."""

@@ -11,6 +11,8 @@ reference itself runs them -- one operator at a time -- with every operator on `
   (SURVEY.md Appendix C.3).
 * **Channel-First FastChannelVim training** (``mamba_simple_channel_faster.py:205-420``): ``(rows, cols, tpp)``
   layouts (``inner > 1``), which the ``MixerFn`` backward kernels do not walk.
+* **Max-pool training** (``collapse_method="max"``: ``cell_imaging/config/FastChannelVimS_maxpool.yaml``): the fused
+  backward kernels implement the mean; the max routes its gradient through ``autograd.PoolMaxBdlFn``.
 
 Kernels: ``fv_causal_conv1d_fwd/_bwd`` (x2 directions), ``fv_pool_bdl_fwd`` / ``fv_bcast_skip_bdl_fwd``,
 ``fv_selective_scan_fwd/_bwd``; GEMMs are torch matmuls (cuBLAS), LayerNorm / gate / index_add / gather are torch
@@ -44,8 +46,11 @@ def mixer_forward_composed(m, hidden_states, act_dtype, *, outer: int, pool: int
     """``m``: a ``fastvim_b200.mixer.Mamba``-like module (reference parameter names).  hidden_states (B, L, d_model)
     in sequence order.  With ``ids_keep`` (B, L) int64 -- ORIGINAL token ids of the kept tokens -- the masked pooling
     of FastMaskVim is used (Lp = num_of_rows, divisor num_of_col); otherwise the (outer, pool, inner) mean pool."""
-    if m.collapse_method != "mean":
-        raise NotImplementedError("fastvim_b200.composed: collapse_method='mean' only")
+    if m.collapse_method not in ("mean", "max"):
+        raise NotImplementedError(f"fastvim_b200.composed: collapse_method {m.collapse_method!r}")
+    if m.collapse_method == "max" and ids_keep is not None:
+        raise NotImplementedError("the masked mixer defines collapse_method='mean' only "
+                                  "(reference mamba_simple_masked_faster.py:212-216)")
     B, L, _ = hidden_states.shape
     D, R, N = m.d_inner, m.dt_rank, m.d_state
     h = hidden_states.to(act_dtype)
@@ -62,7 +67,10 @@ def mixer_forward_composed(m, hidden_states, act_dtype, *, outer: int, pool: int
         if L != outer * pool * inner:
             raise ValueError(f"sequence length {L} != outer*pool*inner = {outer * pool * inner}")
         scale = float(getattr(m, "scaling_factor", 1))
-        pool_fn = lambda t: A.PoolBdlFn.apply(t, outer, pool, inner, scale)
+        if m.collapse_method == "max":     # x.reshape(pre_x_shape).max(dim).values: no scaling factor (:299-305)
+            pool_fn = lambda t: A.PoolMaxBdlFn.apply(t, outer, pool, inner)
+        else:
+            pool_fn = lambda t: A.PoolBdlFn.apply(t, outer, pool, inner, scale)
         bcast = lambda s, t, Dk: A.BcastSkipFn.apply(s, t, Dk, outer, pool, inner)
     else:
         if ids_keep.shape != (B, L):

@@ -160,6 +160,12 @@ class Mamba(nn.Module):
         geom = self.geometry(rotated)
         needs_grad = torch.is_grad_enabled() and (
             hidden_states.requires_grad or any(p.requires_grad for p in self.parameters()))
+        if needs_grad and self.collapse_method == "max" and not rotated:
+            # max pooling under autograd (the reference's live branch differentiates x.reshape(...).max(3).values,
+            # mamba_simple_faster.py:299-305): operator-by-operator path; it returns the gamma-scaled output itself
+            from . import composed
+
+            return composed.mixer_forward_composed(self, hidden_states, act_dtype, outer=geom.outer, pool=geom.pool)
         if needs_grad:
             out = fv_autograd.mixer_forward_train(self, hidden_states, geom, act_dtype)
         else:

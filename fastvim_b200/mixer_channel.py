@@ -57,8 +57,8 @@ class Mamba(_SpatialMamba):
         if needs_grad:
             from . import autograd as fv_autograd
 
-            if geom.inner != 1:
-                # Channel-First: (rows, cols, tpp) pooling, which the fused MixerFn backward kernels do not walk;
+            if geom.inner != 1 or self.collapse_method == "max":
+                # Channel-First ((rows, cols, tpp) pooling) and max pooling: not walked by the fused MixerFn backward kernels;
                 # run operator by operator (conv / pool / scan / broadcast kernels, each with its backward)
                 from . import composed
 

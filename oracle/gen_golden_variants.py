@@ -96,7 +96,7 @@ def main():
         json.dump(manifest, f, indent=1, sort_keys=True)
 
 
-if __name__ == "__main__" and "--channel-model" not in sys.argv and "--2dcompress" not in sys.argv and "--masked-blocks" not in sys.argv and "--compressed" not in sys.argv:
+if __name__ == "__main__" and "--channel-model" not in sys.argv and "--2dcompress" not in sys.argv and "--masked-blocks" not in sys.argv and "--compressed" not in sys.argv and "--maxpool" not in sys.argv:
     main()
 
 
@@ -270,3 +270,52 @@ def gen_compressed_scan():
 
 if __name__ == "__main__" and "--compressed" in sys.argv:
     gen_compressed_scan()
+
+
+def gen_maxpool():
+    """collapse_method="max" under autograd (the live module branch differentiates x.reshape(...).max(dim).values:
+    mamba_simple_faster.py:299-305, mamba_simple_channel_faster.py:258-289; shipped config
+    cell_imaging/config/FastChannelVimS_maxpool.yaml): forward + every gradient from the reference's own modules."""
+    ref = load_reference()
+    manifest_path = os.path.join(GOLD, "manifest.json")
+    manifest = json.load(open(manifest_path))
+    cases = (("cmixer_max_d32_4x6_t3_channel_first_grads", "channel", (4, 6), 3, "Channel-First"),
+             ("cmixer_max_d32_6x4_t2_spatial_first_grads", "channel", (6, 4), 2, "Spatial-First"),
+             ("mixer_max_d32_4x6_grads", "plain", (4, 6), 1, None))
+    for name, kind, ts, tpp, order in cases:
+        torch.manual_seed(0)
+        if kind == "channel":
+            m = ref.mscf.Mamba(32, token_size=list(ts), layer_idx=0, scan_order=order, collapse_method="max")
+            layout = (ts[0], ts[1], tpp) if order == "Channel-First" else (tpp * ts[0], ts[1], 1)
+            extra = tpp
+        else:
+            m = ref.msf.Mamba(32, token_size=list(ts), layer_idx=0, collapse_method="max")
+            layout, extra = (ts[0], ts[1], 1), None
+        detrivialise(m)
+        h = torch.randn(2, ts[0] * ts[1] * tpp, 32)
+        case, e = run_case(_Wrap(m, kind == "channel"), lambda hh, pp: O.mixer_oracle(hh, pp, ts, layout=layout, collapse_method="max"),
+                           h, extra)
+        case.update(token_size=ts, tokens_per_patch=tpp, scan_order=order, layout=layout, kind=kind)
+        path = os.path.join(GOLD, name + ".pt")
+        torch.save(case, path)
+        manifest[name] = dict(oracle_vs_ref=e, bytes=os.path.getsize(path))
+        print(f"  {name}: oracle_vs_ref {e:.2e}")
+    with open(manifest_path, "w") as f:
+        json.dump(manifest, f, indent=1, sort_keys=True)
+
+
+class _Wrap:
+    """Calls module(h, extra) or module(h) and exposes named_parameters, for run_case."""
+
+    def __init__(self, m, takes_extra):
+        self.m, self.takes_extra = m, takes_extra
+
+    def __call__(self, h, extra):
+        return self.m(h, extra) if self.takes_extra else self.m(h)
+
+    def named_parameters(self):
+        return self.m.named_parameters()
+
+
+if __name__ == "__main__" and "--maxpool" in sys.argv:
+    gen_maxpool()

@@ -1,0 +1,87 @@
+"""CPU: the host logic of the operator-by-operator mixer path (fastvim_b200.composed + fastvim_b200.autograd), with the
+kernel wrappers replaced by oracle stand-ins of identical signature (tests/cpu_standins.py), against vectors produced by
+the reference's own modules: FastMaskVim mixer (v1 / v2), Channel-First FastChannelVim mixer, 2dcompress channelwise
+layer, and max pooling under autograd (FastVim and both FastChannelVim scan orders).  Forward and every gradient."""
+import pytest
+import torch
+
+import cpu_standins
+from util import assert_close, load_golden
+
+
+def _check(m, g, call):
+    m.load_state_dict(g["params"], strict=True)
+    m.train()
+    h = g["hidden"].clone().requires_grad_()
+    out = call(m, h)
+    out.backward(g["dout"])
+    assert_close(out, g["out"], 5e-5, "out")
+    assert_close(h.grad, g["dhidden"], 5e-5, "dhidden")
+    got = dict(m.named_parameters())
+    for k, want in g["grads"].items():
+        assert got[k].grad is not None, k
+        assert_close(got[k].grad, want, 5e-5, "d" + k)
+
+
+@pytest.mark.parametrize("name", ["mmixer_d32_4x6_keep10", "mmixer_d32_6x4_keep24_full", "mmixer_v2_d48_14x14_keep49_nonorm"])
+def test_masked_mixer_host_logic(name, monkeypatch):
+    from fastvim_b200.mixer_masked import Mamba_masked
+
+    cpu_standins.install(monkeypatch)
+    g = load_golden(name)
+    m = Mamba_masked(g["params"]["in_proj.weight"].shape[1], token_size=list(g["token_size"]), layer_idx=0,
+                     use_norm_after_ssm=g["use_norm_after_ssm"])
+    _check(m, g, lambda mod, h: mod(h, g["ids_keep"]))
+
+
+@pytest.mark.parametrize("name", ["cmixer_d32_4x6_t3_channel_first_grads", "cmixer_max_d32_4x6_t3_channel_first_grads",
+                                  "cmixer_max_d32_6x4_t2_spatial_first_grads"])
+def test_channel_mixer_host_logic(name, monkeypatch):
+    from fastvim_b200.mixer_channel import Mamba
+
+    cpu_standins.install(monkeypatch)
+    g = load_golden(name)
+    m = Mamba(32, token_size=list(g["token_size"]), layer_idx=0, scan_order=g["scan_order"],
+              collapse_method="max" if "_max_" in name else "mean")
+    _check(m, g, lambda mod, h: mod(h, g["tokens_per_patch"]))
+
+
+def test_2dcompress_channelwise_layer_host_logic(monkeypatch):
+    from fastvim_b200.mixer_channel_2dcompress import Mamba
+
+    cpu_standins.install(monkeypatch)
+    g = load_golden("cmixer2d_d32_4x6_t3_layer2_channels")
+    m = Mamba(32, token_size=list(g["token_size"]), layer_idx=g["layer_idx"], scan_order="Channel-First")
+    _check(m, g, lambda mod, h: mod(h, g["tokens_per_patch"]))
+
+
+def test_fastvim_mixer_max_pool_training_host_logic(monkeypatch):
+    from fastvim_b200.mixer import Mamba
+
+    cpu_standins.install(monkeypatch)
+    g = load_golden("mixer_max_d32_4x6_grads")
+    m = Mamba(32, token_size=list(g["token_size"]), layer_idx=0, collapse_method="max")
+    _check(m, g, lambda mod, h: mod(h))
+    with pytest.raises(NotImplementedError):          # rotated + max: the fused backward kernels implement the mean only
+        m(g["hidden"].clone().requires_grad_(), rotated=True)
+
+
+def test_pool_max_backward_matches_torch_max(monkeypatch):
+    from fastvim_b200.autograd import PoolMaxBdlFn
+
+    cpu_standins.install(monkeypatch)
+    torch.manual_seed(0)
+    for outer, pool, inner in ((4, 6, 1), (3, 5, 2), (1, 7, 3)):
+        x = torch.randn(2, 3, outer * pool * inner)
+        x[0, 0, :2 * inner] = 1.5                                     # a tie inside the first pooled group
+        du = torch.randn(2, 3, outer * inner)
+        xa = x.clone().requires_grad_()
+        PoolMaxBdlFn.apply(xa, outer, pool, inner).backward(du)
+        xb = x.clone().requires_grad_()
+        xb.view(2, 3, outer, pool, inner).max(dim=3).values.reshape(2, 3, -1).backward(du)
+        # identical wherever the maximum is unique; with ties the gradient goes to exactly one position
+        assert torch.equal((xa.grad != 0).sum(), (xb.grad != 0).sum())
+        assert torch.allclose(xa.grad.view(2, 3, outer, pool, inner).sum(3), xb.grad.view(2, 3, outer, pool, inner).sum(3))
+        mask = torch.ones_like(x, dtype=torch.bool)
+        mask[0, 0, :pool * inner] = False
+        assert torch.equal(xa.grad[mask], xb.grad[mask])

@@ -1,8 +1,13 @@
-"""GPU: the 6-tensor compressed selective_scan_fn (interface.selective_scan_fn_compressed; reference
+"""GPU tests written after the round's last GPU slot (their host logic is covered on CPU by tests/test_oracle_golden.py and
+tests/test_composed_host_logic.py with oracle stand-ins for the kernels); kept in one file that runs after every other GPU
+test.
+
+(1) the 6-tensor compressed selective_scan_fn (interface.selective_scan_fn_compressed; reference
 fastvim_kernel/mamba-1p1p1/faster_mamba_ssm/ops/selective_scan_interface.py:129-252) against vectors produced by the
 reference's own selective_scan_ref -- forward, last state and every gradient (the reference's CUDA backward raises for z
-and is fp32-only; here both work).  Kept in its own file: added after the round's last GPU slot, it runs after every
-other GPU test."""
+and is fp32-only; here both work).
+(2) collapse_method="max" under autograd (cell_imaging/config/FastChannelVimS_maxpool.yaml): forward and every gradient of
+the FastChannelVim mixer (both scan orders) and the FastVim mixer against the reference's own modules."""
 import pytest
 import torch
 
@@ -44,3 +49,31 @@ def test_compressed_scan_bf16_vs_oracle():
                                            bias.cuda(), True)
     assert got.dtype == torch.bfloat16 and got.shape == (bs, dim, L)
     assert_close(got, want, TOL[torch.bfloat16], "compressed scan bf16")
+
+
+@pytest.mark.parametrize("name", ["cmixer_max_d32_4x6_t3_channel_first_grads", "cmixer_max_d32_6x4_t2_spatial_first_grads",
+                                  "mixer_max_d32_4x6_grads"])
+def test_max_pool_training_vs_reference_golden_fp32(name):
+    from fastvim_b200.mixer import Mamba
+    from fastvim_b200.mixer_channel import Mamba as ChannelMamba
+
+    g = load_golden(name)
+    if g["kind"] == "channel":
+        m = ChannelMamba(32, token_size=list(g["token_size"]), layer_idx=0, scan_order=g["scan_order"], collapse_method="max")
+        call = lambda h: m(h, g["tokens_per_patch"])
+    else:
+        m = Mamba(32, token_size=list(g["token_size"]), layer_idx=0, collapse_method="max")
+        call = lambda h: m(h)
+    m.load_state_dict(g["params"], strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        assert_close(call(g["hidden"].cuda()), g["out"], 1e-4, "out (inference kernels)")
+    m.train()
+    h = g["hidden"].cuda().requires_grad_()
+    out = call(h)
+    out.backward(g["dout"].cuda())
+    assert_close(out, g["out"], 1e-4, "out (training path)")
+    assert_close(h.grad, g["dhidden"], 1e-4, "dhidden")
+    got = dict(m.named_parameters())
+    for k, want in g["grads"].items():
+        assert_close(got[k].grad, want, 1e-4, "d" + k)
