@@ -85,3 +85,63 @@ def test_pool_max_backward_matches_torch_max(monkeypatch):
         mask = torch.ones_like(x, dtype=torch.bool)
         mask[0, 0, :pool * inner] = False
         assert torch.equal(xa.grad[mask], xb.grad[mask])
+
+
+@pytest.mark.parametrize("name", ["cscan_L128_c8_D", "cscan_L254_c2_noD", "cscan_L196_c14_D_z"])
+def test_compressed_scan_autograd_host_logic(name, monkeypatch):
+    """selective_scan_fn_compressed under autograd (SelectiveScanFn + BcastSkipFn + the z gate): every gradient against the
+    reference's own selective_scan_ref, kernels replaced by stand-ins."""
+    from fastvim_b200.interface import selective_scan_fn_compressed
+
+    cpu_standins.install(monkeypatch)
+    g = load_golden(name)
+    lv = {k: (v.clone().requires_grad_() if v is not None else None) for k, v in g["inputs"].items()}
+    out, st = selective_scan_fn_compressed(lv["u"], lv["u_compressed"], lv["delta"], lv["A"], lv["B"], lv["C"], lv["D"],
+                                           z=lv["z"], delta_bias=lv["delta_bias"], delta_softplus=True, return_last_state=True)
+    assert not st.requires_grad
+    out.backward(g["dout"])
+    assert_close(out, g["out"], 2e-5, "out")
+    assert_close(st, g["last_state"], 2e-5, "last_state")
+    for k, want in g["grads"].items():
+        assert lv[k].grad is not None and lv[k].grad.shape == want.shape, k
+        assert_close(lv[k].grad, want, 2e-5, "d" + k)
+
+
+@pytest.mark.parametrize("has_z", [True, False])
+def test_mamba_inner_fn_autograd_host_logic(has_z, monkeypatch):
+    """mamba_inner_fn_no_out_proj[_withoutZ] and FastVim_mamba_inner_fn_no_out_proj_withoutZ under autograd against fp64
+    autograd through the oracle's restatement of the reference functions."""
+    import fastvim_oracle as O
+    from fastvim_b200 import interface as I
+
+    cpu_standins.install(monkeypatch)
+    torch.manual_seed(0)
+    Bt, Dm, rows, cols, N, R = 2, 16, 3, 5, 8, 3
+    L = rows * cols
+    xz = torch.randn(Bt, 2 * Dm if has_z else Dm, L)
+    cw, cb = torch.randn(Dm, 1, 4) * 0.5, torch.randn(Dm) * 0.5
+    xw, dw = torch.randn(R + 2 * N, Dm) * Dm ** -0.5, torch.randn(Dm, R) * R ** -0.5
+    A, Dp, dbias = -0.5 * torch.rand(Dm, N) - 0.05, torch.randn(Dm), 0.5 * torch.rand(Dm) - 2.0
+    dout = torch.randn(Bt, Dm, L)
+    tensors = [xz, cw, cb, xw, dw, A, Dp, dbias]
+
+    def grads(fn, conv):
+        lv = [conv(t).requires_grad_() for t in tensors]
+        out = fn(*lv)
+        out.backward(conv(dout))
+        return out.detach(), [v.grad for v in lv]
+
+    ours = I.mamba_inner_fn_no_out_proj if has_z else I.mamba_inner_fn_no_out_proj_withoutZ
+    pairs = [(lambda a, b, c, d, e, f, g_, h: ours(a, b, c, d, e, f, None, None, g_, h, delta_softplus=True),
+              lambda a, b, c, d, e, f, g_, h: O.mamba_inner_oracle(a, b, c, d, e, f, None, None, g_, h, True, has_z=has_z))]
+    if not has_z:
+        pairs.append((lambda a, b, c, d, e, f, g_, h: I.FastVim_mamba_inner_fn_no_out_proj_withoutZ(
+                          a, b, c, d, e, f, None, None, g_, h, None, None, True, cols, "mean", 0.5, (-1, Dm, rows, cols)),
+                      lambda a, b, c, d, e, f, g_, h: O.fastvim_inner_oracle(a, b, c, d, e, f, g_, h, cols, 0.5)))
+    for f_ours, f_oracle in pairs:
+        out_g, gg = grads(f_ours, lambda t: t.clone())
+        out_w, gw = grads(f_oracle, lambda t: t.double().clone())
+        assert_close(out_g, out_w, 2e-5, "out")
+        for i, (a, b) in enumerate(zip(gg, gw)):
+            assert a is not None and a.shape == b.shape, i
+            assert_close(a, b, 5e-5, f"grad {i}")
