@@ -160,12 +160,22 @@ class Mamba(nn.Module):
         geom = self.geometry(rotated)
         needs_grad = torch.is_grad_enabled() and (
             hidden_states.requires_grad or any(p.requires_grad for p in self.parameters()))
-        if needs_grad and self.collapse_method == "max" and not rotated:
+        if needs_grad and self.collapse_method == "max":
             # max pooling under autograd (the reference's live branch differentiates x.reshape(...).max(3).values,
-            # mamba_simple_faster.py:299-305): operator-by-operator path; it returns the gamma-scaled output itself
+            # mamba_simple_faster.py:299-305): operator-by-operator path; it returns the gamma-scaled output itself.
+            # That path walks the sequence in memory order, so a geometry-folded odd layer (rotated=True: memory is the
+            # (cols, rows) row-major grid) is permuted physically here, as the reference's Block does (models/fastvim.py:192-210).
             from . import composed
 
-            return composed.mixer_forward_composed(self, hidden_states, act_dtype, outer=geom.outer, pool=geom.pool)
+            B, L, dm = hidden_states.shape
+            rows, cols = self.num_of_rows, self.num_of_col
+            h = hidden_states
+            if rotated:
+                h = h.reshape(B, cols, rows, dm).transpose(1, 2).reshape(B, L, dm)
+            out = composed.mixer_forward_composed(self, h, act_dtype, outer=rows, pool=cols)
+            if rotated:
+                out = out.reshape(B, rows, cols, dm).transpose(1, 2).reshape(B, L, dm)
+            return out
         if needs_grad:
             out = fv_autograd.mixer_forward_train(self, hidden_states, geom, act_dtype)
         else:

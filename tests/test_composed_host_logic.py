@@ -62,8 +62,17 @@ def test_fastvim_mixer_max_pool_training_host_logic(monkeypatch):
     g = load_golden("mixer_max_d32_4x6_grads")
     m = Mamba(32, token_size=list(g["token_size"]), layer_idx=0, collapse_method="max")
     _check(m, g, lambda mod, h: mod(h))
-    with pytest.raises(NotImplementedError):          # rotated + max: the fused backward kernels implement the mean only
-        m(g["hidden"].clone().requires_grad_(), rotated=True)
+    # geometry-folded odd layer (rotated=True: memory holds the (cols, rows) row-major grid): same result as rotating the
+    # tokens physically around an un-rotated call, which is what the reference's Block does (models/fastvim.py:192-210)
+    rows, cols = g["token_size"]
+    h_seq = g["hidden"]
+    h_mem = h_seq.reshape(2, rows, cols, -1).transpose(1, 2).reshape(2, rows * cols, -1).clone().requires_grad_()
+    out_mem = m(h_mem, rotated=True)
+    out_seq = out_mem.reshape(2, cols, rows, -1).transpose(1, 2).reshape(2, rows * cols, -1)
+    assert_close(out_seq, g["out"], 5e-5, "rotated out")
+    out_seq.backward(g["dout"])
+    dh_seq = h_mem.grad.reshape(2, cols, rows, -1).transpose(1, 2).reshape(2, rows * cols, -1)
+    assert_close(dh_seq, g["dhidden"], 5e-5, "rotated dhidden")
 
 
 def test_pool_max_backward_matches_torch_max(monkeypatch):
