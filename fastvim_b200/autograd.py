@@ -26,6 +26,7 @@ class MixerFn(torch.autograd.Function):
         D = conv_w.shape[1]
         from . import mixer as _mixer
 
+        h = h.contiguous()   # saved for the backward's (B*L, dm) views
         xz = _mixer.linear(h, in_w, in_b)
         x, z = xz[..., :D], xz[..., D:]
         if _mixer.FUSED_BLOCK and ops.block_fwd_supported(geom, B, D, xz.dtype, dt_rank, d_state):
@@ -137,8 +138,8 @@ def add_norm_train(x, weight, bias, residual, eps, prenorm, residual_in_fp32, is
     if not prenorm:
         return out
     y, res_out = out
-    if not residual_in_fp32 and residual is None:
-        res_out = res_out.to(x.dtype)
+    if not residual_in_fp32:
+        res_out = res_out.to(x.dtype if residual is None else residual.dtype)
     return y, res_out
 
 

@@ -63,7 +63,14 @@ class Mamba(nn.Module):
         self.d_model, self.d_state, self.d_conv, self.expand = d_model, d_state, d_conv, expand
         self.d_inner = int(expand * d_model)
         self.dt_rank = math.ceil(d_model / 16) if dt_rank == "auto" else dt_rank
-        self.use_fast_path = use_fast_path  # both reference branches compute the same function
+        # The reference's two branches compute the same function EXCEPT use_fast_path=True with collapse 'mean' and no
+        # post-SSM norm, where its fused branch drops the silu(z) gate (mamba_simple_faster.py:262-267).
+        # No shipped config sets use_fast_path; this mirror implements the live branch and refuses that one combination.
+        if use_fast_path and not use_norm_after_ssm and collapse_method == "mean":
+            raise NotImplementedError(
+                "fastvim_b200 implements the live branch (silu(z) gate kept); the reference's use_fast_path=True + "
+                "use_norm_after_ssm=False branch omits the gate and is not reproduced (INTEGRATION.md)")
+        self.use_fast_path = use_fast_path
         self.layer_idx = layer_idx
         self.use_our_selective_scan = use_our_selective_scan
         self.num_of_rows, self.num_of_col = token_size[0], token_size[1]
@@ -147,6 +154,11 @@ class Mamba(nn.Module):
                 pk["x_w_packed"] = ops.block_pack_xproj(pk["x_w"])   # fragment order for the fused block kernel
         self._pack_cache = {"k": key, "v": pk}
         return pk
+
+    def invalidate(self):
+        """Drop the packed parameter copies.  ``_packed`` keys on ``Parameter._version``, which optimizer steps replayed
+        from a CUDA graph never bump: call this after graph-replayed training and before an eval forward."""
+        self._pack_cache = {}
 
     def geometry(self, rotated: bool = False) -> Geometry:
         return Geometry.grid(self.num_of_rows, self.num_of_col, rotated)

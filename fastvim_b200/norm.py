@@ -14,6 +14,7 @@ def _norm(x, weight, bias, residual, eps, prenorm, residual_in_fp32, is_rms):
         t is not None and t.requires_grad for t in (x, weight, bias, residual))
     if needs_grad:
         return fv_autograd.add_norm_train(x, weight, bias, residual, eps, prenorm, residual_in_fp32, is_rms)
+    res_dtype = None if residual is None else residual.dtype
     if residual is not None and residual.dtype != torch.float32:
         residual = residual.float()
     w = weight if weight.dtype == torch.float32 else weight.float()
@@ -21,8 +22,10 @@ def _norm(x, weight, bias, residual, eps, prenorm, residual_in_fp32, is_rms):
     y, res_out, _, _ = ops.add_norm_fwd(x, residual, w, b, eps, is_rms, want_residual=prenorm)
     if not prenorm:
         return y
-    if not residual_in_fp32 and residual is None:
-        res_out = res_out.to(x.dtype)  # reference keeps x.dtype when no fp32 residual is requested
+    if not residual_in_fp32:
+        # reference (layernorm.py:_layer_norm_fwd): residual_out keeps residual.dtype, or x.dtype without a residual,
+        # unless an fp32 residual stream was requested
+        res_out = res_out.to(res_dtype if res_dtype is not None else x.dtype)
     return y, res_out
 
 

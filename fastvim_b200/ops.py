@@ -77,9 +77,19 @@ def _stream(t: Tensor):
 
 
 def _check_cuda(*ts):
+    cur = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise _lib.FastVimLibraryError("fastvim_b200 ops need CUDA tensors (there is no CPU fallback)")
+        if cur is None:
+            cur = torch.cuda.current_device()
+        if t.device.index != cur:
+            # the C ABI launches on the given stream of the CURRENT device (no device guard inside the library)
+            raise _lib.FastVimLibraryError(
+                f"tensor on cuda:{t.device.index} but the current device is cuda:{cur}; wrap the call in "
+                "torch.cuda.device(tensor.device)")
 
 
 def _f32c(t: Optional[Tensor]) -> Optional[Tensor]:
@@ -257,7 +267,8 @@ def gemm_bf16_tn(a: Tensor, w: Tensor, out: Optional[Tensor] = None, bias: Optio
         a2 = a2.contiguous()
     M, N = a2.shape[0], w.shape[0]
     c = out if out is not None else torch.empty((M, N), device=a.device, dtype=a.dtype)
-    _lib.call("fv_gemm_bf16_tn", M, N, K, _p(a2), a2.stride(0), _p(w), w.stride(0), _p(_f32c(bias)), _p(c), c.stride(0),
+    bias32 = _f32c(bias)   # keep the converted copy alive until after the launch (_p only takes the address)
+    _lib.call("fv_gemm_bf16_tn", M, N, K, _p(a2), a2.stride(0), _p(w), w.stride(0), _p(bias32), _p(c), c.stride(0),
               _stream(a))
     return c.reshape(*a.shape[:-1], N)
 
@@ -269,8 +280,9 @@ def causal_conv1d_fwd(x: Tensor, weight: Tensor, bias: Optional[Tensor], silu: b
     B, D, L = x.shape
     assert x.stride(2) == 1 and weight.shape == (D, 4)
     out = torch.empty((B, D, L), device=x.device, dtype=x.dtype)
-    _lib.call("fv_causal_conv1d_fwd", _dt(x), B, D, L, _p(x), x.stride(0), x.stride(1), _p(_f32c(weight)),
-              _p(_f32c(bias)), int(silu), _p(out), _stream(x))
+    w32, b32 = _f32c(weight), _f32c(bias)   # converted copies must outlive the launch (_p keeps only the address)
+    _lib.call("fv_causal_conv1d_fwd", _dt(x), B, D, L, _p(x), x.stride(0), x.stride(1), _p(w32),
+              _p(b32), int(silu), _p(out), _stream(x))
     return out
 
 
@@ -292,7 +304,8 @@ def bcast_skip_bdl_fwd(s: Tensor, xc: Optional[Tensor], Dskip: Optional[Tensor],
     B, D, Lp = s.shape
     assert Lp == outer * inner and s.is_contiguous() and (xc is None or xc.is_contiguous())
     out = torch.empty((B, D, outer * pool * inner), device=s.device, dtype=s.dtype)
-    _lib.call("fv_bcast_skip_bdl_fwd", _dt(s), B, D, outer, pool, inner, _p(s), _p(xc), _p(_f32c(Dskip)), _p(out),
+    d32 = _f32c(Dskip)
+    _lib.call("fv_bcast_skip_bdl_fwd", _dt(s), B, D, outer, pool, inner, _p(s), _p(xc), _p(d32), _p(out),
               _stream(s))
     return out
 
@@ -329,7 +342,8 @@ def causal_conv1d_bwd(x: Tensor, weight: Tensor, bias: Optional[Tensor], dout: T
     dx = torch.empty((B, D, L), device=x.device, dtype=x.dtype)
     dw = torch.zeros((D, 4), device=x.device, dtype=torch.float32)
     db = torch.zeros(D, device=x.device, dtype=torch.float32) if bias is not None else None
-    _lib.call("fv_causal_conv1d_bwd", _dt(x), B, D, L, _p(x), x.stride(0), x.stride(1), _p(_f32c(weight)), _p(_f32c(bias)),
+    w32, b32 = _f32c(weight), _f32c(bias)
+    _lib.call("fv_causal_conv1d_bwd", _dt(x), B, D, L, _p(x), x.stride(0), x.stride(1), _p(w32), _p(b32),
               int(silu), _p(dout), _p(dx), dx.stride(0), dx.stride(1), _p(dw), _p(db), _stream(x))
     return dx, dw, db
 

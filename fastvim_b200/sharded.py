@@ -80,9 +80,16 @@ class ChannelShardedMamba(torch.nn.Module):
         self._cache = {}
 
     def _params(self, act_dtype):
-        if act_dtype not in self._cache:
-            self._cache[act_dtype] = shard_mixer_params(self.mixer, self.rank, self.world, act_dtype)
-        return self._cache[act_dtype]
+        # keyed like Mamba._packed: any parameter update / load_state_dict / .to() re-shards
+        key = (act_dtype,) + tuple((p.data_ptr(), p._version) for p in self.mixer.parameters())
+        if self._cache.get("k") != key:
+            self._cache = {"k": key, "v": shard_mixer_params(self.mixer, self.rank, self.world, act_dtype)}
+        return self._cache["v"]
+
+    def invalidate(self):
+        """Drop the sharded copies (needed after parameter updates that do not bump ``_version``, e.g. optimizer steps
+        replayed from a CUDA graph)."""
+        self._cache = {}
 
     @torch.no_grad()
     def forward(self, hidden_states, inference_params=None, rotated: bool = False):

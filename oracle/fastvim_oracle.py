@@ -417,6 +417,99 @@ def fastvim_oracle(images, sd: Dict[str, Tensor], *, depth, patch=16, final_pool
     return F.linear(feat, sd["head.weight"], sd["head.bias"])
 
 
+# --------------------------------------------------------------------------- FastChannelVim model
+def channelvim_oracle(images, sd: Dict[str, Tensor], *, depth, scan_order="Channel-First", patch=16,
+                      rotate_every_block=True, norm_eps=1e-5, final_pool_type="mean", **mixer_kw):
+    """``VisionMamba.forward`` of ``models/channel_wise_tokenization/models_channel_mamba_faster.py:590-683`` in eval mode
+    (no hierarchical channel sampling, ``input_channel_order=None``): per-channel patch embedding with one shared
+    ``Conv3d(1, E, (1, p, p))`` (:113-121, 180-184) + per-channel embedding, token order Channel-First
+    ``(rows, cols, tpp)`` or Spatial-First ``(tpp, rows, cols)`` (:186-199), positional embedding repeated per channel
+    (:621-630), ``Block`` (:206-336) with the odd-layer transposition (:304-331) and the mixer's pooled layout
+    (``mamba_simple_channel_faster.py:225-256, 325-340``), final add + norm, mean pool, head."""
+    Bt, Cn, H, W = images.shape
+    w3 = sd["patch_embed.proj.weight"]                         # (E, 1, 1, p, p)
+    x = F.conv3d(images[:, None], w3, sd.get("patch_embed.proj.bias"), stride=(1, patch, patch))   # (Bt, E, C, gh, gw)
+    gh, gw = x.shape[-2:]
+    ce = sd["patch_embed.channel_embed.weight"][:Cn]           # ids = arange(C)
+    x = x + ce.t()[None, :, :, None, None]
+    pe = sd.get("pos_embed")
+    if scan_order == "Channel-First":
+        x = x.permute(0, 3, 4, 2, 1).reshape(Bt, gh * gw * Cn, -1)
+        if pe is not None:
+            x = x + torch.repeat_interleave(pe, Cn, 1)
+    else:
+        x = x.permute(0, 2, 3, 4, 1).reshape(Bt, Cn * gh * gw, -1)
+        if pe is not None:
+            x = x + pe.expand(Cn, -1, -1).reshape(1, Cn * gh * gw, -1)
+    hidden, residual = x, None
+    t0, t1 = gh, gw
+    for i in range(depth):
+        pre = f"layers.{i}."
+        p = {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+        hs, residual = add_norm_oracle(hidden, p["norm.weight"], p.get("norm.bias"), residual, norm_eps, True)
+        mp = {k[len("mixer."):]: v for k, v in p.items() if k.startswith("mixer.")}
+        odd = rotate_every_block and i % 2 != 0
+        M = hs.shape[1]
+        rows, cols = (t1, t0) if odd else (t0, t1)
+        if odd:
+            if scan_order == "Spatial-First":
+                hs = hs.reshape(Bt, Cn, t0, t1, -1).transpose(2, 3).reshape(Bt, M, -1)
+            else:
+                hs = hs.reshape(Bt, t0, t1, Cn, -1).transpose(1, 2).reshape(Bt, M, -1)
+        layout = (rows, cols, Cn) if scan_order == "Channel-First" else (Cn * rows, cols, 1)
+        out = mixer_oracle(hs, mp, (rows, cols), layout=layout, **mixer_kw)
+        if odd:
+            if scan_order == "Spatial-First":
+                out = out.reshape(Bt, Cn, t1, t0, -1).transpose(2, 3).reshape(Bt, M, -1)
+            else:
+                out = out.reshape(Bt, t1, t0, Cn, -1).transpose(1, 2).reshape(Bt, M, -1)
+        hidden = out
+    hs, _ = add_norm_oracle(hidden, sd["norm_f.weight"], sd.get("norm_f.bias"), residual, norm_eps, True)
+    feat = hs.mean(dim=1) if final_pool_type == "mean" else hs[:, -1, :]
+    return F.linear(feat, sd["head.weight"], sd["head.bias"])
+
+
+# --------------------------------------------------------------------------- FastMaskVim encoder
+def masked_blocks_oracle(hidden, sd: Dict[str, Tensor], ids_keep, token_size, *, depth, rotate_every_block=True,
+                         norm_eps=1e-5, **mixer_kw):
+    """A stack of ``Block_masked`` (``models/mae/models_mamba_faster_mae_vimdecoder_v2.py:279-402``) + the final
+    add + RMSNorm of ``forward_encoder`` (:805-819).  Odd layers map the kept ids through the (h, w) -> (w, h) rotation
+    (:320-328), re-sort the tokens by rotated id (:376-386), run the mixer built with the swapped token_size and restore
+    the order (:392-396).  hidden (Bt, len_keep, E); ids_keep (Bt, len_keep) sorted original token ids."""
+    H, W = token_size
+    idx = torch.arange(H * W)
+    rot = (idx % W) * H + idx // W
+    residual = None
+    for i in range(depth):
+        pre = f"layers.{i}."
+        p = {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+        hs, residual = add_norm_oracle(hidden, p["norm.weight"], p.get("norm.bias"), residual, norm_eps, True)
+        mp = {k[len("mixer."):]: v for k, v in p.items() if k.startswith("mixer.")}
+        odd = rotate_every_block and i % 2 != 0
+        ids = ids_keep
+        if odd:
+            ids = rot[ids_keep]
+            order = torch.argsort(ids)
+            ids = torch.gather(ids, 1, order)
+            hs = torch.gather(hs, 1, order[..., None].expand(-1, -1, hs.shape[-1]))
+        ts = (W, H) if odd else (H, W)
+        out = mixer_oracle(hs, mp, ts, ids_keep=ids, **mixer_kw)
+        if odd:
+            out = torch.gather(out, 1, torch.argsort(order, -1)[..., None].expand(-1, -1, out.shape[-1]))
+        hidden = out
+    hs, _ = add_norm_oracle(hidden, sd["norm_f.weight"], sd.get("norm_f.bias"), residual, norm_eps, True)
+    return hs
+
+
+def masked_encoder_oracle(images, sd: Dict[str, Tensor], ids_keep, *, depth, patch=16, **kw):
+    """``MaskedAutoencoderViM.forward_encoder`` (:776-819) with the kept ids given: patch embedding + positional
+    embedding, gather of the kept tokens, ``masked_blocks_oracle``."""
+    x, token_size = patch_embed_oracle(images, sd["patch_embed.proj.weight"], sd["patch_embed.proj.bias"], patch)
+    x = x + sd["pos_embed"]
+    x = torch.gather(x, 1, ids_keep[..., None].expand(-1, -1, x.shape[-1]))
+    return masked_blocks_oracle(x, sd, ids_keep, token_size, depth=depth, **kw)
+
+
 # --------------------------------------------------------------------------- init helper
 def random_mixer_params(d_model, *, d_state=16, d_conv=4, expand=2, seed=0,
                         dtype=torch.float32) -> Dict[str, Tensor]:

@@ -22,6 +22,37 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     ok = True
+    if "--full-2048" in sys.argv:
+        # BASELINE.json configs[4]: the real shape, full depth, against the CPU oracle (computed on every rank: 3 s)
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import fastvim_oracle as O
+        from fastvim_b200.vision import fastvim_tiny
+
+        torch.manual_seed(0)
+        m = fastvim_tiny(img_size=2048, drop_path_rate=0.0).eval()
+        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        x = torch.randn(1, 3, 2048, 2048)
+        with torch.no_grad():
+            want = O.fastvim_oracle(x, sd, depth=24)
+        m = m.cuda()
+        for out_mode in ("gather", "reduce"):
+            for dtype in (torch.float32, torch.bfloat16):
+                torch.manual_seed(0)
+                ms = fastvim_tiny(img_size=2048, drop_path_rate=0.0).eval().cuda()
+                ms.load_state_dict(sd)
+                shard_model_channels(ms, None, out_mode)
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+                    got = ms(x.cuda()).float().cpu()
+                e = relerr(got, want)
+                good = e <= (1e-4 if dtype == torch.float32 else 2e-2)
+                ok &= good
+                if rank == 0:
+                    print(f"[sharded x{world}] 2048^2 FastVim-T {out_mode} {dtype}: rel err vs oracle {e:.2e} "
+                          f"{'ok' if good else 'FAIL'}", flush=True)
+        t = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        dist.destroy_process_group()
+        sys.exit(0 if int(t.item()) == 1 else 1)
     for (img, E, depth, norm) in [((64, 96), 64, 4, True), ((128, 128), 64, 2, False), ((256, 256), 192, 2, True)]:
         for out_mode in ("gather", "reduce"):
             for dtype in (torch.float32, torch.bfloat16):

@@ -1,0 +1,178 @@
+"""Model-level parity at the BASELINE.json configs (C2..C5 of SURVEY.md 8) against the CPU oracle -- never against this
+repo's own fp32 path.  Tolerances (BASELINE.json north_star): fp32 <= 1e-4 relative, bf16 <= 2e-2 relative, on logits
+and on every gradient (relative = max |a - b| / max |b| over the tensor; ``util.assert_close`` adds the reference's
+elementwise allclose band)."""
+import pytest
+import torch
+
+import fastvim_oracle as O
+from util import TOL, assert_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _sd(m, double=False, grad=False):
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    if double:
+        sd = {k: v.double() for k, v in sd.items()}
+    if grad:
+        sd = {k: v.requires_grad_(True) for k, v in sd.items()}
+    return sd
+
+
+# ------------------------------------------------------------------ C3: FastVim-B, 224 x 224, bf16 training
+def test_fastvim_base_224_bf16_logits_and_gradients_vs_oracle():
+    """BASELINE.json configs[2]: FastVim-B (d=768, 24 blocks) 224 x 224, bf16 autocast, batch 2: logits and every
+    parameter gradient of a soft-target cross-entropy loss against the fp64 oracle."""
+    from fastvim_b200.vision import fastvim_base
+
+    torch.manual_seed(0)
+    m = fastvim_base(drop_path_rate=0.0)
+    sd = _sd(m, double=True, grad=True)
+    imgs = torch.randn(2, 3, 224, 224)
+    tgt = torch.softmax(torch.randn(2, 1000) * 3, -1)
+    logits_o = O.fastvim_oracle(imgs.double(), sd, depth=24)
+    torch.sum(-tgt.double() * torch.log_softmax(logits_o, -1), -1).mean().backward()
+    m = m.cuda().train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        logits = m(imgs.cuda())
+    torch.sum(-tgt.cuda() * torch.log_softmax(logits.float(), -1), -1).mean().backward()
+    assert_close(logits, logits_o.detach(), 2e-2, "FastVim-B logits bf16")
+    worst = ("", 0.0)
+    for k, v in m.named_parameters():
+        assert v.grad is not None, k
+        e = assert_close(v.grad, sd[k].grad, 2e-2, f"d {k}")
+        worst = max(worst, (k, e), key=lambda t: t[1])
+    print(f"[C3] worst gradient {worst[0]}: {worst[1]:.2e}")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fastvim_base_224_inference_vs_oracle(dtype):
+    from fastvim_b200.vision import fastvim_base
+
+    torch.manual_seed(0)
+    m = fastvim_base(drop_path_rate=0.0).eval()
+    sd = _sd(m)
+    imgs = torch.randn(2, 3, 224, 224)
+    want = O.fastvim_oracle(imgs, sd, depth=24)
+    m = m.cuda()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        got = m(imgs.cuda())
+    assert_close(got, want, TOL[dtype], f"FastVim-B logits {dtype}")
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fastvim_small_224_inference_vs_oracle(dtype):
+    from fastvim_b200.vision import fastvim_small
+
+    torch.manual_seed(0)
+    m = fastvim_small(drop_path_rate=0.0).eval()
+    sd = _sd(m)
+    imgs = torch.randn(3, 3, 224, 224)
+    want = O.fastvim_oracle(imgs, sd, depth=24)
+    m = m.cuda()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        got = m(imgs.cuda())
+    assert_close(got, want, TOL[dtype], f"FastVim-S logits {dtype}")
+
+
+# ------------------------------------------------------------------ C5: FastVim-T, 2048 x 2048 (16384 tokens)
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fastvim_tiny_2048_vs_oracle(dtype):
+    """BASELINE.json configs[4] on one GPU: the full 24-block FastVim-T on one 2048 x 2048 image (128 x 128 token grid,
+    pooled length 128) against the oracle."""
+    from fastvim_b200.vision import fastvim_tiny
+
+    torch.manual_seed(0)
+    m = fastvim_tiny(img_size=2048, drop_path_rate=0.0).eval()
+    sd = _sd(m)
+    imgs = torch.randn(1, 3, 2048, 2048)
+    with torch.no_grad():
+        want = O.fastvim_oracle(imgs, sd, depth=24)
+    m = m.cuda()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        got = m(imgs.cuda())
+    assert_close(got, want, TOL[dtype], f"FastVim-T 2048^2 logits {dtype}")
+
+
+# ------------------------------------------------------------------ C4: FastChannelVim-S/16, 8-channel 224 x 224
+@pytest.mark.parametrize("order", ["Channel-First", "Spatial-First"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fastchannelvim_s16_jumpcp_shape_vs_oracle(order, dtype):
+    """BASELINE.json configs[3]: FastChannelVim-S/16 (d=384, 24 blocks) on 8-channel 224 x 224 JUMP-CP-shape synthetic
+    images (1568 tokens) against ``channelvim_oracle`` (pinned on the reference's own model, test_oracle_golden.py)."""
+    from fastvim_b200.vision_channel import VisionMamba
+
+    torch.manual_seed(0)
+    m = VisionMamba(img_size=224, depth=24, embed_dim=384, channels=8, num_classes=161, rms_norm=True,
+                    residual_in_fp32=True, fused_add_norm=True, drop_path_rate=0.0, scan_order=order, hcs=False).eval()
+    sd = _sd(m)
+    imgs = torch.randn(2, 8, 224, 224)
+    with torch.no_grad():
+        want = O.channelvim_oracle(imgs, sd, depth=24, scan_order=order)
+    m = m.cuda()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        got = m(imgs.cuda())
+    assert got.shape == (2, 161)
+    assert_close(got, want, TOL[dtype], f"FastChannelVim-S/16 {order} logits {dtype}")
+
+
+# ------------------------------------------------------------------ FastMaskVim encoder at the MAE shape
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_masked_encoder_mae_shape_vs_oracle(dtype):
+    """FastMaskVim-T-shaped encoder, 75 % masking (49 of 196 tokens kept), forward + backward against
+    ``masked_encoder_oracle`` (fp64; pinned on the reference's own Block_masked stack)."""
+    from fastvim_b200.vision_masked import MaskedEncoder
+
+    torch.manual_seed(0)
+    depth = 4
+    enc = MaskedEncoder(img_size=224, depth=depth, embed_dim=192)
+    sd = _sd(enc, double=True, grad=True)
+    imgs = torch.randn(3, 3, 224, 224)
+    ids_keep = torch.stack([torch.randperm(196)[:49].sort().values for _ in range(3)])
+    dout = torch.randn(3, 49, 192)
+    want = O.masked_encoder_oracle(imgs.double(), sd, ids_keep, depth=depth)
+    want.backward(dout.double())
+    enc = enc.cuda().train()
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        latent, _, _ = enc(imgs.cuda(), 0.75, ids_keep=ids_keep.cuda())
+    latent.backward(dout.cuda().to(latent.dtype))
+    tol = TOL[dtype]
+    assert_close(latent, want.detach(), tol, "latent")
+    for k, v in enc.named_parameters():
+        assert v.grad is not None, k
+        assert_close(v.grad, sd[k].grad, 2 * tol, f"d {k}")
+
+
+# ------------------------------------------------------------------ non-fp32 small parameters, residual dtype
+def test_causal_conv1d_with_bf16_parameters():
+    """The operator API called with bf16 conv weights AND bias (a ``model.bfloat16()`` run): the fp32 copies handed to
+    the kernel must stay alive until the launch (the bias copy could reuse the weight copy's block)."""
+    from fastvim_b200 import ops
+
+    torch.manual_seed(0)
+    x = torch.randn(4, 256, 196, device="cuda").bfloat16()
+    w = torch.randn(256, 4, device="cuda").bfloat16()
+    b = torch.randn(256, device="cuda").bfloat16()
+    for _ in range(3):
+        got = ops.causal_conv1d_fwd(x, w, b, True)
+        want = O.causal_conv1d_oracle(x.float().cpu(), w.float().cpu(), b.float().cpu())
+        assert_close(got, want, 2e-2, "conv with bf16 parameters")
+        dx, dw, db = ops.causal_conv1d_bwd(x, w, b, torch.ones_like(x), True)
+        assert torch.isfinite(dw).all() and torch.isfinite(db).all()
+
+
+def test_add_norm_keeps_residual_dtype_without_fp32_request():
+    """layer_norm_fn(..., residual bf16, residual_in_fp32=False) returns a bf16 residual, as the reference's kernel does
+    (ops/triton/layernorm.py: residual_out keeps residual.dtype unless residual_in_fp32)."""
+    from fastvim_b200.norm import layer_norm_fn
+
+    x = torch.randn(8, 64, device="cuda").bfloat16()
+    r = torch.randn(8, 64, device="cuda").bfloat16()
+    w = torch.ones(64, device="cuda")
+    for rg in (False, True):
+        xx = x.clone().requires_grad_(rg)
+        y, res = layer_norm_fn(xx, w, None, residual=r, prenorm=True, residual_in_fp32=False, is_rms_norm=True)
+        assert res.dtype == torch.bfloat16 and y.dtype == torch.bfloat16
+        y, res = layer_norm_fn(xx, w, None, residual=r, prenorm=True, residual_in_fp32=True, is_rms_norm=True)
+        assert res.dtype == torch.float32

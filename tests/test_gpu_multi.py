@@ -21,3 +21,12 @@ def test_channel_sharded_model_matches_single_gpu():
         pytest.skip("needs >= 2 GPUs")
     r = _torchrun(os.path.join(HERE, "dist_sharded_check.py"), 2)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_channel_sharded_2048_world8_matches_oracle():
+    """BASELINE.json configs[4]: FastVim-T on one 2048 x 2048 image with d_inner sharded over 8 GPUs against the CPU oracle
+    (self-skips below 8 GPUs; bench.py's sharded run asserts the same check on its own logits)."""
+    if torch.cuda.device_count() < 8:
+        pytest.skip("needs 8 GPUs")
+    r = _torchrun(os.path.join(HERE, "dist_sharded_check.py"), 8, "--full-2048", port=29541)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]

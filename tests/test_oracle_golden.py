@@ -249,3 +249,31 @@ def test_compressed_scan_host_glue_with_cpu_stand_ins(name, monkeypatch):
     assert torch.equal(out, out_only)
     with pytest.raises(ValueError):
         interface.selective_scan_fn_compressed(i["u"][..., :-1], i["u_compressed"], i["delta"], i["A"], i["B"], i["C"])
+
+
+# ------------------------------------------------------------------ model-level oracles added in round 2
+@pytest.mark.parametrize("name", ["channelvim_small_cf", "channelvim_small_sf"])
+def test_channel_model_oracle_matches_reference_vectors(name):
+    """``channelvim_oracle`` (FastChannelVim classifier, BASELINE.json configs[3]) is pinned on the reference's own
+    ``VisionMamba`` of models_channel_mamba_faster.py: logits and every parameter gradient."""
+    g = load_golden(name)
+    sd = {k: v.clone().double().requires_grad_(True) for k, v in g["state_dict"].items()}
+    logits = O.channelvim_oracle(g["images"].double(), sd, depth=g["kwargs"]["depth"], scan_order=g["scan_order"])
+    logits.backward(g["dlogits"].double())
+    assert_close(logits, g["logits"], 5e-5, "logits")
+    for k, want in g["grads"].items():
+        assert_close(sd[k].grad, want, 1e-4, "d " + k)
+
+
+def test_masked_blocks_oracle_matches_reference_vectors():
+    """``masked_blocks_oracle`` (FastMaskVim encoder stack with the odd-layer id rotation) is pinned on the reference's own
+    ``Block_masked`` stack: output, input gradient and every parameter gradient."""
+    g = load_golden("mblocks_d32_4x6_keep10")
+    sd = {k: v.clone().double().requires_grad_(True) for k, v in g["state_dict"].items()}
+    h = g["hidden"].clone().double().requires_grad_(True)
+    out = O.masked_blocks_oracle(h, sd, g["ids_keep"], g["token_size"], depth=g["depth"])
+    out.backward(g["dout"].double())
+    assert_close(out, g["out"], 5e-5, "out")
+    assert_close(h.grad, g["dhidden"], 1e-4, "dhidden")
+    for k, want in g["grads"].items():
+        assert_close(sd[k].grad, want, 1e-4, "d " + k)
