@@ -41,6 +41,8 @@ SIGNATURES = {
     "fv_selective_scan_fwd": [_I, _I, _I, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P],
     "fv_gemm_bf16_tn": [_L, _I, _I, _P, _L, _P, _L, _P, _P, _L, _P],
     "fv_gemm_supported": [_L, _I, _I],
+    "fv_patchify_supported": [_I, _I, _I, _I, _I],
+    "fv_patchify": [_I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "fv_causal_conv1d_fwd": [_I, _I, _I, _L, _P, _L, _L, _P, _P, _I, _P, _P],
     "fv_pool_bdl_fwd": [_I, _I, _I, _I, _I, _I, _P, _I, _F, _P, _P],
     "fv_bcast_skip_bdl_fwd": [_I, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P],

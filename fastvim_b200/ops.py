@@ -273,6 +273,28 @@ def gemm_bf16_tn(a: Tensor, w: Tensor, out: Optional[Tensor] = None, bias: Optio
     return c.reshape(*a.shape[:-1], N)
 
 
+_PATCH_DT = {torch.float32: 0, torch.bfloat16: 1, torch.uint8: 2}
+
+
+def patchify_supported(img: Tensor, patch: int) -> bool:
+    if img.dtype not in _PATCH_DT or img.dim() != 4 or not img.is_cuda or not img.is_contiguous():
+        return False
+    _, C, H, W = img.shape
+    return bool(_lib.lib().fv_patchify_supported(_PATCH_DT[img.dtype], C, H, W, int(patch)))
+
+
+def patchify(img: Tensor, patch: int, per_channel: bool = False) -> Tensor:
+    """img (B, C, H, W) fp32 | bf16 | uint8 contiguous -> bf16 unfolded patches, the A operand of the patch-embedding
+    GEMM: (B*gh*gw, C*p*p) or, per channel, (B*C*gh*gw, p*p).  One read of the image, one write."""
+    _check_cuda(img)
+    B, C, H, W = img.shape
+    gh, gw = H // patch, W // patch
+    rows, cols = (B * C * gh * gw, patch * patch) if per_channel else (B * gh * gw, C * patch * patch)
+    out = torch.empty((rows, cols), device=img.device, dtype=torch.bfloat16)
+    _lib.call("fv_patchify", _PATCH_DT[img.dtype], B, C, H, W, int(patch), int(per_channel), _p(img), _p(out), _stream(img))
+    return out
+
+
 # --------------------------------------------------------------------------- (B, D, L) operator-API helpers
 def causal_conv1d_fwd(x: Tensor, weight: Tensor, bias: Optional[Tensor], silu: bool = True) -> Tensor:
     """x (B, D, L) with unit stride along L (any batch / channel strides), weight (D, 4) -> (B, D, L) contiguous."""

@@ -22,6 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch import Tensor
 
+from . import ops
 from .mixer import Mamba
 from .mixer import linear as _linear
 from .norm import RMSNorm, layer_norm_fn, rms_norm_fn
@@ -46,6 +47,48 @@ class PatchEmbed(nn.Module):
         self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
         self.norm = norm_layer(embed_dim) if norm_layer else nn.Identity()
 
+    # ---- uint8 pipelines: (x / 255 - mean) / std folded into the projection ---------------------------------
+    def set_input_normalization(self, mean=None, std=None):
+        """Declare how uint8 images map to the float images the model was trained on: ``(x / 255 - mean) / std`` per
+        input channel (``None`` = plain ``x.float()``).  The fast path folds this affine map into the projection's weights
+        and bias, so a uint8 image crosses PCIe and HBM at one byte per pixel and is converted exactly (0..255 are
+        bf16-representable)."""
+        C = self.proj.weight.shape[1]
+        if mean is None and std is None:
+            self._in_norm = None
+        else:
+            mean = torch.as_tensor(0.0 if mean is None else mean, dtype=torch.float32).reshape(-1).expand(C).clone()
+            std = torch.as_tensor(1.0 if std is None else std, dtype=torch.float32).reshape(-1).expand(C).clone()
+            self._in_norm = (mean, std)
+        self._fold_cache = None
+
+    def _uint8_to_float(self, x):
+        x = x.float()
+        norm = getattr(self, "_in_norm", None)
+        if norm is not None:
+            mean, std = (t.to(x.device)[None, :, None, None] for t in norm)
+            x = (x / 255.0 - mean) / std
+        return x
+
+    def _folded(self, dtype):
+        """Projection weights (E, C*p*p) / fp32 bias for uint8 input: W' = W / (255 std_c), b' = b - sum W mean_c / std_c."""
+        w, b = self.proj.weight, self.proj.bias
+        norm = getattr(self, "_in_norm", None)
+        key = (w.data_ptr(), w._version, None if b is None else b._version, dtype, id(norm))
+        hit = getattr(self, "_fold_cache", None)
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        with torch.no_grad():
+            w32 = w.float()
+            b32 = torch.zeros(w.shape[0], device=w.device) if b is None else b.float()
+            if norm is not None:
+                mean, std = (t.to(w.device) for t in norm)
+                b32 = b32 - (w32 * (mean / std)[None, :, None, None]).sum(dim=(1, 2, 3))
+                w32 = w32 / (255.0 * std)[None, :, None, None]
+            wmat = w32.reshape(w.shape[0], -1).to(dtype).contiguous()
+        self._fold_cache = (key, wmat, b32.contiguous())
+        return wmat, b32
+
     def forward(self, x):
         B, C, H, W = x.shape
         if self.strict_img_size:
@@ -54,21 +97,37 @@ class PatchEmbed(nn.Module):
             ph = (self.patch_size[0] - H % self.patch_size[0]) % self.patch_size[0]
             pw = (self.patch_size[1] - W % self.patch_size[1]) % self.patch_size[1]
             if ph or pw:
+                if x.dtype == torch.uint8:
+                    x = self._uint8_to_float(x)   # zero padding is applied to the normalised image
                 x = F.pad(x, (0, pw, 0, ph))
         # Non-overlapping conv == GEMM over unfolded patches: (B*L, C*p*p) x (C*p*p, E).
         p0, p1 = self.patch_size
         B, C, H, W = x.shape
         gh, gw = H // p0, W // p1
         w = self.proj.weight
-        cols = x.reshape(B, C, gh, p0, gw, p1).permute(0, 2, 4, 1, 3, 5).reshape(B * gh * gw, C * p0 * p1)
-        if torch.is_autocast_enabled("cuda"):
-            cols = cols.to(torch.get_autocast_dtype("cuda"))
-        wmat = w.reshape(w.shape[0], -1).to(cols.dtype)
-        bias = None if self.proj.bias is None else self.proj.bias.to(cols.dtype)
-        if cols.is_cuda and not (torch.is_grad_enabled() and (w.requires_grad or x.requires_grad)):
-            out = _linear(cols, wmat, bias)     # tcgen05 GEMM (bf16) / cuBLAS
+        autocast = torch.is_autocast_enabled("cuda")
+        act_dtype = torch.get_autocast_dtype("cuda") if autocast else (torch.float32 if x.dtype == torch.uint8 else x.dtype)
+        no_grad = not (torch.is_grad_enabled() and (w.requires_grad or x.requires_grad))
+        if (no_grad and act_dtype == torch.bfloat16 and p0 == p1 and x.is_cuda and ops.patchify_supported(x.contiguous(), p0)
+                and ops.gemm_supported(B * gh * gw, w.shape[0], C * p0 * p1)):
+            # inference fast path: ONE pass image -> bf16 patches (fv_patchify: fp32 / bf16 / uint8 in), then the tcgen05 GEMM
+            cols = ops.patchify(x.contiguous(), p0)
+            if x.dtype == torch.uint8:
+                wmat, bias32 = self._folded(torch.bfloat16)
+            else:
+                wmat, bias32 = self._folded_plain()
+            out = ops.gemm_bf16_tn(cols, wmat, bias=bias32)
         else:
-            out = F.linear(cols, wmat, bias)
+            if x.dtype == torch.uint8:
+                x = self._uint8_to_float(x)
+            cols = x.reshape(B, C, gh, p0, gw, p1).permute(0, 2, 4, 1, 3, 5).reshape(B * gh * gw, C * p0 * p1)
+            cols = cols.to(act_dtype)
+            wmat = w.reshape(w.shape[0], -1).to(cols.dtype)
+            bias = None if self.proj.bias is None else self.proj.bias.to(cols.dtype)
+            if cols.is_cuda and no_grad:
+                out = _linear(cols, wmat, bias)     # tcgen05 GEMM (bf16) / cuBLAS
+            else:
+                out = F.linear(cols, wmat, bias)
         out = out.reshape(B, gh, gw, -1)
         if self.scanpath_type == "colwise":
             out = out.transpose(1, 2)
@@ -77,6 +136,19 @@ class PatchEmbed(nn.Module):
         else:
             out = out.permute(0, 3, 1, 2)
         return self.norm(out)
+
+    def _folded_plain(self):
+        w, b = self.proj.weight, self.proj.bias
+        key = (w.data_ptr(), w._version, None if b is None else b._version)
+        hit = getattr(self, "_plain_cache", None)
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        with torch.no_grad():
+            wmat = w.reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
+            # the reference's autocast conv adds the bias rounded to bf16; keep that rounding, in an fp32 container
+            b32 = None if b is None else b.to(torch.bfloat16).float().contiguous()
+        self._plain_cache = (key, wmat, b32)
+        return wmat, b32
 
 
 class Block(nn.Module):
@@ -216,10 +288,14 @@ class VisionMamba(nn.Module):
     def no_weight_decay(self):
         return {"pos_embed"}
 
+    def set_input_normalization(self, mean=None, std=None):
+        """uint8 images given to ``forward`` mean ``(x / 255 - mean) / std`` (see ``PatchEmbed.set_input_normalization``)."""
+        self.patch_embed.set_input_normalization(mean, std)
+
     def forward_features(self, x, inference_params=None, out_indices=None):
-        act_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
         B, _, H, W = x.shape
-        x = self.patch_embed(x.to(act_dtype))
+        # images go to the patch embedding in their host dtype (fp32, bf16 or uint8): the unfold kernel casts on the fly
+        x = self.patch_embed(x)
         if self.if_abs_pos_embed:
             gh, gw = math.ceil(H / self.patch_size), math.ceil(W / self.patch_size)
             if gh != self.token_size[0] or gw != self.token_size[1]:

@@ -24,6 +24,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch import Tensor
 
+from . import ops
 from .mixer import linear as _linear
 from .mixer_channel import Mamba
 from .norm import RMSNorm, layer_norm_fn
@@ -69,13 +70,18 @@ class PatchEmbedPerChannel(nn.Module):
         # shared non-overlapping projection == GEMM over unfolded patches: (B*C*gh*gw, p*p) x (p*p, E)
         p0, p1 = self.patch_size
         gh, gw = h // p0, w // p1
-        cols = x.reshape(B, num_channels, gh, p0, gw, p1).permute(0, 1, 2, 4, 3, 5).reshape(-1, p0 * p1)
-        if torch.is_autocast_enabled("cuda"):
-            cols = cols.to(torch.get_autocast_dtype("cuda"))
         wt = self.proj.weight
+        autocast = torch.is_autocast_enabled("cuda")
+        act_dtype = torch.get_autocast_dtype("cuda") if autocast else x.dtype
+        no_grad = not (torch.is_grad_enabled() and (wt.requires_grad or x.requires_grad))
+        if (no_grad and act_dtype == torch.bfloat16 and p0 == p1 and x.is_cuda and x.dtype in (torch.float32, torch.bfloat16)
+                and ops.patchify_supported(x.contiguous(), p0)):
+            cols = ops.patchify(x.contiguous(), p0, per_channel=True)     # one pass image -> bf16 patches (fv_patchify)
+        else:
+            cols = x.reshape(B, num_channels, gh, p0, gw, p1).permute(0, 1, 2, 4, 3, 5).reshape(-1, p0 * p1).to(act_dtype)
         wmat = wt.reshape(wt.shape[0], -1).to(cols.dtype)
         bias = None if self.proj.bias is None else self.proj.bias.to(cols.dtype)
-        if cols.is_cuda and not (torch.is_grad_enabled() and (wt.requires_grad or x.requires_grad)):
+        if cols.is_cuda and no_grad:
             out = _linear(cols, wmat, bias)
         else:
             out = F.linear(cols, wmat, bias)
@@ -211,7 +217,9 @@ class VisionMamba(nn.Module):
 
     def forward_features(self, x, inference_params=None):
         act_dtype = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
-        x, tokens_per_patch, h, w, channels_list = self.patch_embed(x.to(act_dtype))
+        if x.dtype == torch.uint8:
+            x = x.float()
+        x, tokens_per_patch, h, w, channels_list = self.patch_embed(x)
         if self.if_abs_pos_embed:                                                 # :621-630
             pe = self.pos_embed.to(x.dtype)
             if self.scan_order == "Spatial-First":

@@ -150,6 +150,17 @@ int fv_selective_scan_fwd(int dtype, int batch, int dim, int64_t L, int dstate, 
                           int delta_softplus, void* out, float* last_state, void* stream);
 
 
+/* ---- patch unfolding + cast: the A operand of the patch-embedding GEMM -----------------------------
+ * Replaces the Conv2d(k = stride = patch) of PatchEmbed.proj (models/fastvim.py:67-69, 95) / the shared
+ * Conv3d(1, E, (1, p, p)) of PatchEmbedPerChannel (models_channel_mamba_faster.py:113-121, 180-184) by
+ * "unfold once, then GEMM".  img (batch, C, H, W) contiguous in in_dtype (0 = fp32, 1 = bf16, 2 = uint8);
+ * out bf16: joint mode (batch*gh*gw, C*p*p) with column (c, py, px); per-channel mode (batch*C*gh*gw, p*p).
+ * patch % 8 == 0, H and W multiples of patch (pad first otherwise).  uint8 pixels are converted exactly.
+ */
+int fv_patchify_supported(int in_dtype, int C, int H, int W, int patch);
+int fv_patchify(int in_dtype, int batch, int C, int H, int W, int patch, int per_channel, const void* img,
+                void* out, void* stream);
+
 /* ---- tcgen05 / TMEM / TMA GEMMs for the projections -------------------------------------------
  * C (M x N) = A (M x K) . W (N x K)^T: bf16 operands (row-major, row strides lda / ldw / ldc elements,
  * 16-byte aligned, multiples of 8), fp32 accumulation in tensor memory, bf16 result.  Replaces the cuBLAS
