@@ -109,14 +109,15 @@ def call(name: str, *args) -> None:
     if _profile is not None:
         import torch
 
+        n0 = int(l.fv_launch_count())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = getattr(l, name)(*args)
         e1.record()
         tag = name
-        if name == "fv_gemm_bf16_tn":   # several GEMM shapes share one entry point: tag the record with (M, N, K)
-            tag = "fv_gemm_bf16_tn[%dx%dx%d]" % (int(args[0]), int(args[1]), int(args[2]))
-        _profile.append((tag, e0, e1))
+        if name in ("fv_gemm_bf16_tn", "fv_gemm_out_norm"):   # several GEMM shapes share one entry point: tag with (M, N, K)
+            tag = "%s[%dx%dx%d]" % (name, int(args[0]), int(args[1]), int(args[2]))
+        _profile.append((tag, e0, e1, int(l.fv_launch_count()) - n0))
     else:
         rc = getattr(l, name)(*args)
     if rc != 0:

@@ -140,3 +140,65 @@ def test_batch_sharded_gradient_exchange_world2_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert err < 1e-6, err
+
+
+def _exchange_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fastvim_b200 import parallel
+
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 8), torch.nn.Tanh(), torch.nn.Linear(8, 5), torch.nn.Tanh(),
+                              torch.nn.Linear(5, 3))
+    unused = torch.nn.Parameter(torch.ones(4))                    # never receives a gradient: reduced in finish()
+    params = list(net.parameters()) + [unused]
+    exch = parallel.GradExchange(params, world, bucket_mb=60 * 4 / 2**20)   # 60-element buckets -> several buckets
+    assert len(exch.plan) >= 3 and sorted(i for b in exch.plan for i in b) == list(range(len(params)))
+    assert exch.plan[0][0] == len(params) - 1                    # buckets start from the LAST parameter
+    exch.attach()
+    errs = []
+    for it in range(2):                                          # two steps: begin() must re-arm the hooks
+        x = torch.randn(4, 6, generator=torch.Generator().manual_seed(10 * it + rank))
+        exch.begin()
+        net(x).square().sum().backward()
+        exch.finish()
+        # reference: every rank's local gradients, averaged
+        want = [torch.zeros_like(p) for p in params]
+        for r in range(world):
+            ref = torch.nn.Sequential(torch.nn.Linear(6, 8), torch.nn.Tanh(), torch.nn.Linear(8, 5), torch.nn.Tanh(),
+                                      torch.nn.Linear(5, 3))
+            ref.load_state_dict(net.state_dict())
+            xr = torch.randn(4, 6, generator=torch.Generator().manual_seed(10 * it + r))
+            ref(xr).square().sum().backward()
+            for w_, p in zip(want, ref.parameters()):
+                w_ += p.grad / world
+        errs.append(max(float((p.grad - w_).abs().max()) for p, w_ in zip(params, want)))
+        assert all(exch.fired)
+    exch.detach()
+    if rank == 0:
+        q.put(max(errs))
+    dist.destroy_process_group()
+
+
+def test_bucketed_overlapped_gradient_exchange_world2_gloo():
+    """GradExchange (bucketed all-reduce fired from post-accumulate hooks, the captured-step exchange of bench.py):
+    averaged gradients equal the mean of the per-rank gradients, over two consecutive steps, incl. an unused parameter."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29890 + os.getpid() % 40
+    procs = [ctx.Process(target=_exchange_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    err = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert err < 1e-6, err
+
+
+def test_bucket_plan():
+    from fastvim_b200.parallel import plan_buckets
+
+    assert plan_buckets([10, 10, 10, 10], 20) == [[3, 2], [1, 0]]
+    assert plan_buckets([5, 100, 5], 20) == [[2], [1], [0]]
+    assert plan_buckets([1, 1, 1], 100) == [[2, 1, 0]]
