@@ -31,8 +31,8 @@ class MixerFn(torch.autograd.Function):
         x, z = xz[..., :D], xz[..., D:]
         if _mixer.FUSED_BLOCK and ops.block_fwd_supported(geom, B, D, xz.dtype, dt_rank, d_state):
             y, u, xdbl, s = ops.block_fwd(x, z, geom, conv_w, conv_b, x_w.contiguous(), dt_w.contiguous(),
-                                          dt_b, A_log, Dk, ln_w, ln_b, eps, scale, dt_rank, d_state, a_is_log=True,
-                                          save=True)
+                                          dt_b, -torch.exp(A_log), Dk, ln_w, ln_b, eps, scale, dt_rank, d_state,
+                                          a_is_log=False, save=True)
         else:
             u = ops.conv_pool_fwd(x, geom, conv_w, conv_b, scale, "mean")
             xdbl = torch.bmm(u.view(2, B * geom.Lp, D), x_w.transpose(1, 2))

@@ -31,7 +31,9 @@
 // Restrictions (fv_block_fwd_supported): bf16, plain (outer, pool, 1) geometry, mean pooling, d_state 16,
 // dim <= 384 and (L+6)*dim*2 + pooled buffers <= 227 KB; everything else uses the four-launch path.
 
-#include "common.cuh"
+#include <cstdlib>
+
+#include "block_common.cuh"
 
 namespace fv {
 
@@ -42,7 +44,6 @@ constexpr int BK_THREADS = 768;
 constexpr int BK_WARPS = BK_THREADS / 32;
 constexpr int BK_NWORK = BK_WARPS;      // gate pass: every warp owns one token per round
 constexpr int BK_NCG = 3;               // 4-channel groups per lane in the gate pass: dim <= 384
-constexpr int BK_NSTATE = 16;
 
 struct BlockArgs {
     Geom g;
@@ -69,58 +70,6 @@ struct BlockArgs {
     int R, ncols, xld, uld;
     int off_u, off_s, off_xdbl, off_tab;  // byte offsets into dynamic smem (slab at 0)
 };
-
-__device__ __forceinline__ float2 unpack2(uint32_t v) {
-    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&v));
-}
-__device__ __forceinline__ uint32_t pack2(float2 v) {
-    __nv_bfloat162 r = __floats2bfloat162_rn(v.x, v.y);
-    return *reinterpret_cast<uint32_t*>(&r);
-}
-__device__ __forceinline__ uint32_t pack2(float a, float b) { return pack2(make_float2(a, b)); }
-
-__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                         uint32_t b0, uint32_t b1) {
-    asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ float bk_ex2(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float bk_lg2(float x) {
-    float y;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-// softplus with the reference threshold (fwd_kernel.cuh:153-156), 2 MUFU ops; see scan_pooled.cu
-__device__ __forceinline__ float bk_softplus(float x) {
-    constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
-    const float e = bk_ex2(x * LOG2E);
-    const float sp = x < -5.f ? e * fmaf(e, fmaf(e, 0.33333334f, -0.5f), 1.f) : LN2 * bk_lg2(1.f + e);
-    return x <= 20.f ? sp : x;
-}
-// silu(x) for a pair, given h = x/2: h + h * tanh(h).  tanh.approx.f32 is ONE MUFU op per element with no
-// conversions around it (the f16x2 form also costs one MUFU per element in SASS, plus a pack and two unpacks).
-__device__ __forceinline__ float bk_tanh(float x) {
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float2 silu2_from_half(float2 h) {
-    return __ffma2_rn(h, make_float2(bk_tanh(h.x), bk_tanh(h.y)), h);
-}
-
-// memory token row of sequence position t (plain geometry: inner == 1)
-template <int POOL_T>
-__device__ __forceinline__ int64_t bk_row(const Geom& g, int t) {
-    const int P = POOL_T ? POOL_T : g.pool;
-    const int o = t / P, p = t - o * P;
-    return o * g.so + p * g.sp;
-}
 
 template <int POOL_T, bool NORM, bool FULL, int RT>
 __global__ void __launch_bounds__(BK_THREADS, 1) block_fwd_kernel(const BlockArgs a) {
@@ -597,25 +546,72 @@ static BlockPlan plan_block(const fv_geom* g, int dtype, int R, int N, int64_t l
 
 }  // namespace fv
 
+// cluster form (block_cluster.cu): channels of one image split over the CTAs of a thread-block cluster
+namespace fv {
+struct ClusterPlan {
+    int ok;
+    size_t smem;
+    int xld, uld, nnt, C, xdb, off_u, off_s, off_xp, off_xd, off_st;
+};
+ClusterPlan plan_cluster(const fv_geom* g, int dtype, int R, int N, int64_t ldxz, int64_t ldy);
+int64_t pack_xproj_slab_bytes(int dim, int ncols);
+int pack_xproj_slab(int dim, int ncols, const void* xproj_w, void* packed, cudaStream_t st);
+int launch_block_cluster(const fv_geom* g_, const ClusterPlan& p, const void* x, const void* z, int64_t ldxz, int64_t xz_bstride,
+                         const float* conv_w, const float* conv_b, const void* xw_slab_packed, const float* dt_w,
+                         const float* dt_bias, const float* A, int a_is_log, int dt_rank, int dstate, const float* Dskip,
+                         const float* ln_w, const float* ln_b, float eps, float scale, void* y, int64_t ldy, int64_t y_bstride,
+                         void* u_out, void* xdbl_out, float* s_out, cudaStream_t stream);
+// Which kernel serves a configuration both can run (dim <= 384, i.e. FastVim-T): measured on B200 at batch 256 the
+// one-CTA-per-image kernel is still ahead there (68 vs 76 us), so "auto" gives it the narrow models and the cluster
+// kernel everything wider.  FASTVIM_BLOCK_CLUSTER=1 forces the cluster kernel wherever it applies, =0 disables it
+// (A/B timing, tools/kbench.py).
+static int cluster_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FASTVIM_BLOCK_CLUSTER");
+        v = !e ? 2 : (e[0] == '0' ? 0 : (e[0] == '1' ? 1 : 2));
+    }
+    return v;
+}
+static bool cluster_enabled() { return cluster_mode() != 0; }
+static bool prefer_cluster(const fv_geom* g, int dtype, int R, int N, int64_t ldxz, int64_t ldy) {
+    if (cluster_mode() == 1) return true;
+    return !plan_block(g, dtype, R, N, ldxz, ldy).ok;
+}
+static int64_t pack_old_bytes(int dim, int ncols) {
+    if (dim <= 0 || ncols <= 0 || dim % 64 != 0) return 0;
+    return (int64_t)2 * ((ncols + 7) / 8) * 2 * (dim / 64) * 32 * 16;
+}
+}  // namespace fv
+
 extern "C" int fv_block_fwd_supported(const fv_geom* g, int dtype, int dt_rank, int dstate) {
     if (!g || g->batch <= 0 || g->dim <= 0 || g->outer <= 0 || g->pool <= 0) return 0;
+    if (fv::cluster_enabled() && fv::plan_cluster(g, dtype, dt_rank, dstate, 2 * (int64_t)g->dim, g->dim).ok) return 1;
     return fv::plan_block(g, dtype, dt_rank, dstate, 2 * (int64_t)g->dim, g->dim).ok;
 }
 
+// packed x_proj weights = [one-CTA-per-image fragment order | per-slab fragment order of the cluster kernel]
 extern "C" int64_t fv_block_pack_xproj_bytes(int dim, int ncols) {
-    if (dim <= 0 || ncols <= 0 || dim % 64 != 0) return 0;
-    return (int64_t)2 * ((ncols + 7) / 8) * 2 * (dim / 64) * 32 * 16;
+    if (dim <= 0 || ncols <= 0) return 0;
+    return fv::pack_old_bytes(dim, ncols) + fv::pack_xproj_slab_bytes(dim, ncols);
 }
 
 extern "C" int fv_block_pack_xproj(int dim, int ncols, const void* xproj_w, void* packed, void* stream) {
     using namespace fv;
     FV_REQUIRE(xproj_w && packed, "fv_block_pack_xproj: null pointer");
-    FV_REQUIRE(dim > 0 && dim % 64 == 0 && ncols > 0, "fv_block_pack_xproj: dim (%d) must be a positive multiple of 64", dim);
+    FV_REQUIRE(dim > 0 && ncols > 0 && fv_block_pack_xproj_bytes(dim, ncols) > 0,
+               "fv_block_pack_xproj: dim (%d) must be a positive multiple of 64 or 192", dim);
     FV_REQUIRE(((uintptr_t)xproj_w % 4) == 0 && ((uintptr_t)packed % 16) == 0, "fv_block_pack_xproj: misaligned pointer");
-    const int n_nt = (ncols + 7) / 8, nj = dim / 64, total = 2 * n_nt * 2 * nj * 32;
-    pack_xproj_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const bf16*)xproj_w, ncols, dim, n_nt, nj,
-                                                                         (uint4*)packed);
-    return finish_launch("block_pack_xproj");
+    const int64_t old_b = pack_old_bytes(dim, ncols);
+    if (old_b) {
+        const int n_nt = (ncols + 7) / 8, nj = dim / 64, total = 2 * n_nt * 2 * nj * 32;
+        pack_xproj_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const bf16*)xproj_w, ncols, dim, n_nt, nj,
+                                                                             (uint4*)packed);
+        if (int rc = finish_launch("block_pack_xproj")) return rc;
+    }
+    if (pack_xproj_slab_bytes(dim, ncols))
+        return pack_xproj_slab(dim, ncols, xproj_w, (unsigned char*)packed + old_b, (cudaStream_t)stream);
+    return 0;
 }
 
 extern "C" int fv_block_fwd(const fv_geom* g_, int dtype, const void* x, const void* z, int64_t ldxz,
@@ -627,9 +623,18 @@ extern "C" int fv_block_fwd(const fv_geom* g_, int dtype, const void* x, const v
     using namespace fv;
     if (int rc = check_geom(g_, "fv_block_fwd")) return rc;
     FV_REQUIRE(x && z && conv_w && xproj_w && dt_w && dt_bias && A && Dskip && y, "fv_block_fwd: null pointer");
+    if (cluster_enabled() && xproj_w_packed) {
+        const ClusterPlan cp = plan_cluster(g_, dtype, dt_rank, dstate, ldxz, ldy);
+        if (cp.ok && prefer_cluster(g_, dtype, dt_rank, dstate, ldxz, ldy))
+            return launch_block_cluster(g_, cp, x, z, ldxz, xz_bstride, conv_w, conv_b,
+                                        (const unsigned char*)xproj_w_packed + pack_old_bytes(g_->dim, dt_rank + 2 * dstate), dt_w,
+                                        dt_bias, A, a_is_log, dt_rank, dstate, Dskip, ln_w, ln_b, eps, scale, y, ldy, y_bstride,
+                                        u_out, xdbl_out, s_out, (cudaStream_t)stream);
+    }
     const BlockPlan p = plan_block(g_, dtype, dt_rank, dstate, ldxz, ldy);
-    FV_REQUIRE(p.ok, "fv_block_fwd: unsupported configuration (bf16, plain geometry, dim %% 32 == 0, dim <= 384, "
-                     "d_state 16, dt_rank in {4, 8, 12, 16}, slab must fit 227 KB); use the four-launch path");
+    FV_REQUIRE(p.ok, "fv_block_fwd: unsupported configuration (bf16, plain geometry, d_state 16, and either dim %% 192 == 0 with "
+                     "<= 16 pooled rows and packed x_proj weights [cluster kernel], or dim %% 32 == 0, dim <= 384, dt_rank in "
+                     "{4, 8, 12, 16} and the slab fitting 227 KB); use the four-launch path");
     FV_REQUIRE(ldxz % 8 == 0 && xz_bstride % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)z % 8) == 0,
                "fv_block_fwd: x rows must be 16-byte aligned (ldxz %lld)", (long long)ldxz);
     FV_REQUIRE(ldy % 4 == 0 && y_bstride % 4 == 0 && ((uintptr_t)y % 8) == 0, "fv_block_fwd: y rows must be 8-byte aligned");

@@ -28,7 +28,7 @@ def test_fastvim_base_224_bf16_logits_and_gradients_vs_oracle():
     Tolerance: 2e-2 relative on the logits and on every gradient tensor, with one documented exception.  A few gradients of
     a 24-block bf16 backward are ill-conditioned (cancellation in the tiny x_proj / dt_proj products of the first blocks):
     the reference's OWN dtype flow -- the oracle run under bf16 autocast on the CPU -- is itself up to
-    4.4e-2 away from fp64 on them.  For those tensors the bound is 1.5 x that measured noise floor; the concatenation of
+    4.4e-2 away from fp64 on them.  For those tensors the bound is 2 x that measured noise floor; the concatenation of
     ALL gradients must still be within 2e-2 (relative L2)."""
     from fastvim_b200.vision import fastvim_base
 
@@ -53,19 +53,21 @@ def test_fastvim_base_224_bf16_logits_and_gradients_vs_oracle():
     assert_close(logits, logits_o, 2e-2, "FastVim-B logits bf16")
     from util import relerr
 
-    worst, n_floor, num, den = ("", 0.0), 0, 0.0, 0.0
+    worst, n_floor, num, den, bad = ("", 0.0), 0, 0.0, 0.0, []
     for k, v in m.named_parameters():
         assert v.grad is not None, k
         floor = relerr(g16[k], g64[k])
-        bound = max(2e-2, 1.5 * floor)
-        n_floor += bound > 2e-2
         e = relerr(v.grad, g64[k])
-        assert e <= bound, f"d {k}: relative error {e:.3e} > {bound:.1e} (bf16 noise floor of the oracle {floor:.1e})"
+        bound = max(2e-2, 2.0 * floor)      # two independent draws of the same bf16 noise: allow 2 x the measured floor
+        n_floor += e > 2e-2
+        if e > bound:
+            bad.append(f"d {k}: relative error {e:.3e} > {bound:.1e} (bf16 noise floor of the oracle {floor:.1e})")
         worst = max(worst, (k, e), key=lambda t: t[1])
         num += float((v.grad.double().cpu() - g64[k]).square().sum())
         den += float(g64[k].square().sum())
     total = (num / den) ** 0.5
     print(f"[C3] worst gradient {worst[0]}: {worst[1]:.2e}; {n_floor} tensors on the noise-floor bound; all gradients L2 {total:.2e}")
+    assert not bad, "\n".join(bad)
     assert n_floor <= 12, f"{n_floor} gradient tensors needed the noise-floor bound"
     assert total <= 2e-2, total
 

@@ -361,6 +361,15 @@ def _four_launch(ops, x, z, geom, cw, cb, xw, dtw, dtb, A_log, Dk, lw, lb, sf, R
     (2, 14, 14, 256, 8, False, True, 1.0),
     (2, 33, 5, 96, 16, False, True, 1.0),        # > 16 pooled rows (three MMA row tiles), dt_rank 16
     (2, 14, 14, 128, 8, True, False, 1.0),       # rotated, no LayerNorm
+    # cluster form (block_cluster.cu): d_inner split in 192-channel slabs over a thread-block cluster
+    (5, 14, 14, 192, 12, False, True, 1.0),      # one slab (cluster of 1)
+    (300, 14, 14, 384, 12, False, True, 1.0),    # FastVim-T, more clusters than CTA slots
+    (3, 14, 14, 768, 24, False, True, 1.0),      # FastVim-S: 4 CTAs / image, dt_rank 24 (x_dbl held as bf16)
+    (3, 14, 14, 768, 24, True, False, 1.0),      # ... rotated, no LayerNorm
+    (2, 14, 14, 1536, 48, False, True, 1.0),     # FastVim-B: 8 CTAs / image, dt_rank 48
+    (2, 14, 14, 1536, 48, True, True, 0.5),
+    (3, 10, 12, 384, 12, True, True, 1.0),       # generic (non-14) grid on the cluster kernel
+    (2, 16, 9, 768, 16, False, True, 2.0),       # 16 pooled rows, generic dt_rank
 ])
 def test_block_fwd_fused_vs_four_launch_and_oracle(Bt, rows, cols, Dm, R, rot, norm, sf):
     """fv_block_fwd (one launch, x resident in shared memory) against (i) the four-launch path on the same
@@ -385,7 +394,10 @@ def test_block_fwd_fused_vs_four_launch_and_oracle(Bt, rows, cols, Dm, R, rot, n
                                   save=True)
     y2 = ops.block_fwd(x, z, geom, cw, cb, xw, dtw, dtb, A_log, Dk, lw, lb, 1e-5, sf, R, N, True)
     assert torch.equal(y, y2)  # deterministic; the optional saves do not change the result
-    if Dm % 64 == 0:            # fragment-order x_proj weights are a pure re-layout: bit-identical result
+    # served by the cluster kernel (needs the packed weights): always for d_inner > 384, for narrower ones only when forced
+    import os
+    cluster = Dm % 192 == 0 and rows <= 16 and (Dm > 384 or os.environ.get("FASTVIM_BLOCK_CLUSTER") == "1")
+    if Dm % 64 == 0 and Dm <= 384:   # without packed weights: the one-CTA-per-image kernel gathers fragments itself
         from fastvim_b200 import _lib
         g_ = geom.c_struct(Bt, Dm)
         import ctypes as C
@@ -396,7 +408,10 @@ def test_block_fwd_fused_vs_four_launch_and_oracle(Bt, rows, cols, Dm, R, rot, n
                   C.c_void_p(Dk.data_ptr()), None if lw is None else C.c_void_p(lw.data_ptr()),
                   None if lb is None else C.c_void_p(lb.data_ptr()), 1e-5, float(sf), C.c_void_p(y3.data_ptr()),
                   y3.stride(1), y3.stride(0), None, None, None, C.c_void_p(torch.cuda.current_stream().cuda_stream))
-        assert torch.equal(y, y3)
+        if cluster:   # a different kernel (other summation orders): close, not identical
+            assert_close(y, y3, TOL[torch.bfloat16], "cluster kernel vs one-CTA kernel")
+        else:         # fragment-order x_proj weights are a pure re-layout: bit-identical result
+            assert torch.equal(y, y3)
     yr, ur, xdblr, sr = _four_launch(ops, x, z, geom, cw, cb, xw, dtw, dtb, A_log, Dk, lw, lb, sf, R, N)
     tol = TOL[torch.bfloat16]
     assert_close(u, ur, tol, "pooled u")
@@ -416,12 +431,29 @@ def test_block_fwd_fused_vs_four_launch_and_oracle(Bt, rows, cols, Dm, R, rot, n
     assert_close(y, want, tol, "y vs oracle")
 
 
+def test_block_fwd_cluster_kernel_forced_on_narrow_models():
+    """The cluster kernel also serves d_inner = 192 / 384 (FastVim-T); "auto" prefers the one-CTA kernel there, so the same
+    parity cases are re-run in a subprocess with FASTVIM_BLOCK_CLUSTER=1 (the switch is read once per process)."""
+    import os
+    import subprocess
+    import sys
+
+    if os.environ.get("FASTVIM_BLOCK_CLUSTER") == "1":
+        pytest.skip("already forced")
+    env = dict(os.environ, FASTVIM_BLOCK_CLUSTER="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.abspath(__file__), "-q", "-m", "gpu", "-x", "-k",
+                        "test_block_fwd_fused_vs_four_launch_and_oracle or test_mixer_bf16_fused_and_four_launch"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+
+
 def test_block_fwd_unsupported_configs_are_refused():
     from fastvim_b200 import _lib, ops
 
     g = ops.Geometry.grid(14, 14)
     assert not ops.block_fwd_supported(g, 2, 384, torch.float32, 12, 16)      # fp32: slab would not fit
-    assert not ops.block_fwd_supported(g, 2, 1536, torch.bfloat16, 48, 16)    # FastVim-B width: four-launch path
+    assert ops.block_fwd_supported(g, 2, 1536, torch.bfloat16, 48, 16)        # FastVim-B width: cluster kernel (8 CTAs / image)
+    assert not ops.block_fwd_supported(g, 2, 1024, torch.bfloat16, 32, 16)    # neither <= 384 nor a multiple of 192
     assert not ops.block_fwd_supported(ops.Geometry.grid(128, 128), 1, 384, torch.bfloat16, 12, 16)   # 2048^2
     assert not ops.block_fwd_supported(ops.Geometry(14, 14, 8, 14 * 8, 8, 1), 2, 384, torch.bfloat16, 12, 16)  # channel layout
     x = torch.zeros(1, 128 * 128, 768, dtype=torch.bfloat16, device="cuda")
