@@ -268,8 +268,11 @@ class Ctx:
         torch.cuda.set_device(self.local)
         self.dev = torch.device("cuda", self.local)
         if self.world > 1:
-            if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-                os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner out of stdout (one JSON line only)
+            # keep NCCL's own prints (version banner at VERSION / WARN level, INFO lines when the caller asks for them)
+            # out of stdout: rank 0 prints ONE JSON line there
+            if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "WARN"):
+                os.environ["NCCL_DEBUG"] = "NONE"
+            os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/fastvim_bench_nccl_%h_%p.log")
             dist.init_process_group("nccl", device_id=self.dev)
 
     def barrier(self):
@@ -556,16 +559,21 @@ def run_infer(a, ctx: Ctx, workload: str, main: bool):
 
     # ---- sharded 2048^2: the bench's own logits against the CPU oracle ----
     parity = None
-    if sharded and rank == 0 and not a.no_cpu:
-        sys.path.insert(0, os.path.join(ROOT, "oracle"))
-        import fastvim_oracle as O
-        inner = model
-        sd = {k.replace(".mixer.mixer.", ".mixer."): v.detach().float().cpu() for k, v in inner.state_dict().items()}
-        with torch.no_grad():
-            want = O.fastvim_oracle(host_imgs["f32"][0], sd, depth=24)
-        got = step(0).float().cpu()
-        err = float((got - want).abs().max() / want.abs().max())
-        parity = {"rel_err_vs_oracle": round(err, 6), "tol": 2e-2, "ok": err <= 2e-2}
+    if sharded and not a.no_cpu:
+        got = step(0).float().cpu()        # the step holds collectives: EVERY rank replays it; rank 0 checks
+        torch.cuda.synchronize()
+        if rank == 0:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import fastvim_oracle as O
+            nthr = torch.get_num_threads()
+            torch.set_num_threads(max(1, min(16, os.cpu_count() or 1)))   # torchrun pins OMP_NUM_THREADS=1
+            sd = {k.replace(".mixer.mixer.", ".mixer."): v.detach().float().cpu() for k, v in model.state_dict().items()}
+            with torch.no_grad():
+                want = O.fastvim_oracle(host_imgs["f32"][0], sd, depth=24)
+            torch.set_num_threads(nthr)
+            err = float((got - want).abs().max() / want.abs().max())
+            parity = {"rel_err_vs_oracle": round(err, 6), "tol": 2e-2, "ok": err <= 2e-2}
+        ctx.barrier()
 
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------
     cpu = None

@@ -36,7 +36,10 @@ SIGNATURES = {
     "fv_block_pack_xproj_bytes": [_I, _I],
     "fv_block_pack_xproj": [_I, _I, _P, _P, _P],
     "fv_block_fwd": [_G, _I, _P, _P, _L, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _F, _F, _P, _L, _L,
-                     _P, _P, _P, _P],
+                     _P, _P, _P, _P, _P],
+    "fv_block_fwd_saves_v": [_G, _I, _I, _I],
+    "fv_gate_bwd_v_supported": [_G, _I],
+    "fv_gate_bwd_v": [_G, _I, _P, _P, _L, _L, _P, _L, _L, _P, _P, _F, _P, _P, _P, _P, _P, _P],
     "fv_add_norm_fwd": [_I, _L, _I, _P, _L, _P, _P, _P, _F, _I, _P, _L, _P, _P, _P, _P],
     "fv_selective_scan_fwd": [_I, _I, _I, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P],
     "fv_gemm_bf16_tn": [_L, _I, _I, _P, _L, _P, _L, _P, _P, _L, _P],
@@ -60,7 +63,7 @@ SIGNATURES = {
     "fv_scan_bwd_short": [_G, _I, _I, _P, _P, _L, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P],
     "fv_scan_bwd": [_G, _I, _I, _P, _P, _L, _I, _I, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P, _P],
     "fv_reduce_planes": [_I, _P, _I, _L, _P, _P],
-    "fv_conv_pool_bwd": [_G, _I, _P, _L, _L, _P, _P, _P, _P, _P, _F, _I, _P, _P, _P, _P],
+    "fv_conv_pool_bwd": [_G, _I, _P, _L, _L, _P, _P, _P, _P, _P, _F, _I, _P, _P, _P, _P, _P],
     "fv_add_norm_bwd": [_I, _L, _I, _P, _L, _P, _P, _P, _F, _I, _P, _L, _P, _P, _P, _P],
 }
 

@@ -12,7 +12,12 @@ from __future__ import annotations
 import torch
 import torch.nn.functional as F
 
+import os
+
 from . import ops
+
+# streaming gate backward from the saved pre-norm value (csrc/gate_bwd_v.cu); "0" = round-1 recomputing kernel
+GATE_BWD_V = os.environ.get("FASTVIM_GATE_BWD_V", "1") != "0"
 
 
 class MixerFn(torch.autograd.Function):
@@ -29,23 +34,26 @@ class MixerFn(torch.autograd.Function):
         h = h.contiguous()   # saved for the backward's (B*L, dm) views
         xz = _mixer.linear(h, in_w, in_b)
         x, z = xz[..., :D], xz[..., D:]
+        v = None
         if _mixer.FUSED_BLOCK and ops.block_fwd_supported(geom, B, D, xz.dtype, dt_rank, d_state):
-            y, u, xdbl, s = ops.block_fwd(x, z, geom, conv_w, conv_b, x_w.contiguous(), dt_w.contiguous(),
-                                          dt_b, -torch.exp(A_log), Dk, ln_w, ln_b, eps, scale, dt_rank, d_state,
-                                          a_is_log=False, save=True)
+            # the cluster kernel also saves the pre-norm value v (instead of the scan planes s) for the streaming gate backward
+            want_v = GATE_BWD_V and ops.gate_bwd_v_supported(geom, B, D, xz.dtype)
+            y, u, xdbl, s, v = ops.block_fwd(x, z, geom, conv_w, conv_b, x_w.contiguous(), dt_w.contiguous(),
+                                             dt_b, -torch.exp(A_log), Dk, ln_w, ln_b, eps, scale, dt_rank, d_state,
+                                             a_is_log=False, save=True, save_v=want_v)
         else:
             u = ops.conv_pool_fwd(x, geom, conv_w, conv_b, scale, "mean")
             xdbl = torch.bmm(u.view(2, B * geom.Lp, D), x_w.transpose(1, 2))
             s = ops.scan_fwd(u, xdbl, geom, dt_rank, d_state, dt_w, dt_b, A_log, a_is_log=True)
             y = ops.gate_fwd(x, z, s, geom, conv_w, conv_b, Dk, ln_w, ln_b, eps)
         out = _mixer.linear(y, out_w, out_b)
-        ctx.save_for_backward(h, in_w, conv_w, conv_b, x_w, dt_w, dt_b, A_log, Dk, ln_w, ln_b, out_w, xz, u, xdbl, s, y)
+        ctx.save_for_backward(h, in_w, conv_w, conv_b, x_w, dt_w, dt_b, A_log, Dk, ln_w, ln_b, out_w, xz, u, xdbl, s, y, v)
         ctx.meta = (geom, scale, eps, d_state, dt_rank, in_b is not None, out_b is not None)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        (h, in_w, conv_w, conv_b, x_w, dt_w, dt_b, A_log, Dk, ln_w, ln_b, out_w, xz, u, xdbl, s, y) = ctx.saved_tensors
+        (h, in_w, conv_w, conv_b, x_w, dt_w, dt_b, A_log, Dk, ln_w, ln_b, out_w, xz, u, xdbl, s, y, v) = ctx.saved_tensors
         geom, scale, eps, N, R, has_in_b, has_out_b = ctx.meta
         B, L, dm = h.shape
         D = conv_w.shape[1]
@@ -60,7 +68,11 @@ class MixerFn(torch.autograd.Function):
         # epilogue
         x, z = xz[..., :D], xz[..., D:]
         dxz = torch.empty_like(xz)
-        e, ds, dDk, dln_w, dln_b = ops.gate_bwd(x, z, dy, s, geom, conv_w, conv_b, Dk, ln_w, ln_b, eps, dxz[..., D:])
+        if v is not None:   # streaming: v, z, dy in -> dz, e out; the D-skip gradients come from the conv backward below
+            e, ds, dln_w, dln_b = ops.gate_bwd_v(v, z, dy, geom, ln_w, ln_b, eps, dxz[..., D:])
+            dDk = None
+        else:
+            e, ds, dDk, dln_w, dln_b = ops.gate_bwd(x, z, dy, s, geom, conv_w, conv_b, Dk, ln_w, ln_b, eps, dxz[..., D:])
         # scan
         du, ddelta, dbc, dA_log, d_dt_b = ops.scan_bwd(ds, u, xdbl, geom, R, N, dt_w, dt_b, A_log, True)
         ddelta2 = ddelta.view(2, B * Lp, D)
@@ -71,7 +83,11 @@ class MixerFn(torch.autograd.Function):
         d_x_w = torch.bmm(dxdbl.transpose(1, 2), u2)                            # (2, R+2N, D)
         du_total = torch.baddbmm(du.view(2, B * Lp, D), dxdbl, x_w).view(2, B, Lp, D).contiguous()
         # conv + pool (+ D skip)
-        d_conv_w, d_conv_b = ops.conv_pool_bwd(x, e, du_total, geom, conv_w, conv_b, Dk, scale, dxz[..., :D])
+        if dDk is None:
+            d_conv_w, d_conv_b, dDk = ops.conv_pool_bwd(x, e, du_total, geom, conv_w, conv_b, Dk, scale, dxz[..., :D],
+                                                        want_dD=True)
+        else:
+            d_conv_w, d_conv_b = ops.conv_pool_bwd(x, e, du_total, geom, conv_w, conv_b, Dk, scale, dxz[..., :D])
         # in_proj
         dxz2 = dxz.view(B * L, 2 * D)
         dh = (dxz2 @ in_w).view(B, L, dm)

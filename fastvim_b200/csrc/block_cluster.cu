@@ -63,6 +63,7 @@ struct ClusterArgs {
     bf16* u_out;
     bf16* xdbl_out;
     float* s_out;
+    bf16* v_out;       // (B, L, dim) pre-norm merged value, memory token order (saved for fv_gate_bwd_v), or null
     int R, ncols, xld, uld, nnt, C;
     int off_u, off_s, off_xp, off_xd, off_st;
 };
@@ -545,12 +546,14 @@ __global__ void __launch_bounds__(BC_THREADS, 2) block_cluster_kernel(const Clus
                 const unsigned char* wrow = smem + (uint32_t)(t + 3) * rowB + q16 * 8;
                 const float* srow = ssum + tj * DC + q16 * 4;
                 bf16* yrow = yb + (int64_t)(tj * so32 + tp * sp32) * a.ldy;
+                bf16* vrow = a.v_out ? a.v_out + ((int64_t)img * L + (tj * so32 + tp * sp32)) * D + dbase + q16 * 4 : nullptr;
 #pragma unroll
                 for (int i = 0; i < BC_NG; ++i) {
                     const uint2 wv = *reinterpret_cast<const uint2*>(wrow + 128 * i);
                     const float4 s0 = *reinterpret_cast<const float4*>(srow + 64 * i);
                     float2 o0 = __ffma2_rn(half2c, make_float2(s0.x, s0.y), unpack2(wv.x));
                     float2 o1 = __ffma2_rn(half2c, make_float2(s0.z, s0.w), unpack2(wv.y));
+                    if (vrow) *reinterpret_cast<uint2*>(vrow + 64 * i) = make_uint2(pack2(o0), pack2(o1));
                     if (NORM) {
                         o0 = __ffma2_rn(__fmul2_rn(__fadd2_rn(o0, nmean), gsc), gam[i][0], bet[i][0]);
                         o1 = __ffma2_rn(__fmul2_rn(__fadd2_rn(o1, nmean), gsc), gam[i][1], bet[i][1]);
@@ -653,7 +656,7 @@ int launch_block_cluster(const fv_geom* g_, const ClusterPlan& p, const void* x,
                          const float* conv_w, const float* conv_b, const void* xw_slab_packed, const float* dt_w,
                          const float* dt_bias, const float* A, int a_is_log, int dt_rank, int dstate, const float* Dskip,
                          const float* ln_w, const float* ln_b, float eps, float scale, void* y, int64_t ldy, int64_t y_bstride,
-                         void* u_out, void* xdbl_out, float* s_out, cudaStream_t stream) {
+                         void* u_out, void* xdbl_out, float* s_out, void* v_out, cudaStream_t stream) {
     FV_REQUIRE(ldxz % 8 == 0 && xz_bstride % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)z % 16) == 0,
                "fv_block_fwd: x / z rows must be 16-byte aligned (ldxz %lld)", (long long)ldxz);
     FV_REQUIRE(ldy % 8 == 0 && y_bstride % 8 == 0 && ((uintptr_t)y % 16) == 0, "fv_block_fwd: y rows must be 16-byte aligned");
@@ -667,7 +670,7 @@ int launch_block_cluster(const fv_geom* g_, const ClusterPlan& p, const void* x,
     a.A = A; a.a_is_log = a_is_log; a.Dskip = Dskip; a.lnw = ln_w; a.lnb = ln_b; a.eps = eps;
     a.scale = scale / (float)g_->pool;
     a.y = (bf16*)y; a.ldy = ldy; a.ybs = y_bstride;
-    a.u_out = (bf16*)u_out; a.xdbl_out = (bf16*)xdbl_out; a.s_out = s_out;
+    a.u_out = (bf16*)u_out; a.xdbl_out = (bf16*)xdbl_out; a.s_out = s_out; a.v_out = (bf16*)v_out;
     a.R = dt_rank; a.ncols = dt_rank + 2 * dstate; a.xld = p.xld; a.uld = p.uld; a.nnt = p.nnt; a.C = p.C;
     a.off_u = p.off_u; a.off_s = p.off_s; a.off_xp = p.off_xp; a.off_xd = p.off_xd; a.off_st = p.off_st;
 

@@ -187,14 +187,32 @@ __device__ __forceinline__ float2 dsilu2(float2 x) {
     }
     return make_float2(dsilu(x.x), dsilu(x.y));
 }
+// the same with silu(x) itself as a second result (needed for the D-skip gradient dD = sum e * silu(conv))
+template <bool FAST>
+__device__ __forceinline__ float2 dsilu2_val(float2 x, float2& sl) {
+    if (FAST) {
+        const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+        float tx, ty;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(tx) : "f"(h.x));
+        asm("tanh.approx.f32 %0, %1;" : "=f"(ty) : "f"(h.y));
+        const float2 s = __ffma2_rn(make_float2(tx, ty), make_float2(0.5f, 0.5f), make_float2(0.5f, 0.5f));
+        const float2 oms = __ffma2_rn(s, make_float2(-1.f, -1.f), make_float2(1.f, 1.f));
+        sl = __fmul2_rn(x, s);
+        return __fmul2_rn(s, __ffma2_rn(x, oms, make_float2(1.f, 1.f)));
+    }
+    sl = make_float2(silu_exact(x.x), silu_exact(x.y));
+    return make_float2(dsilu(x.x), dsilu(x.y));
+}
 
-template <typename T>
+// WITH_DD: also accumulate the D-skip gradients dD_f = sum e * xc_f, dD_b = sum e * xc_b (the conv outputs are formed here
+// anyway; the streaming gate backward fv_gate_bwd_v works from the saved pre-norm value and never sees them)
+template <typename T, bool WITH_DD>
 __global__ void __launch_bounds__(256, 2)
 conv_pool_bwd_stream_kernel(Geom g, int nseg, int seg_len, int64_t nitems, int nslots, int chunks,
                             const T* __restrict__ x, int64_t ldx, int64_t xbs, const T* __restrict__ e,
                             const T* __restrict__ du, const float* __restrict__ cw, const float* __restrict__ cb,
                             const float* __restrict__ Dskip, float scale, T* __restrict__ dx,
-                            float* __restrict__ dcw, float* __restrict__ dcb) {
+                            float* __restrict__ dcw, float* __restrict__ dcb, float* __restrict__ dDs) {
     typedef Pair<T> P;
     typedef typename P::type PT;
     constexpr bool FAST = is_fast<T>::value;
@@ -218,6 +236,7 @@ conv_pool_bwd_stream_kernel(Geom g, int nseg, int seg_len, int64_t nitems, int n
     const float2 Df = make_float2(Dskip[d0], Dskip[d0 + 1]), Db = make_float2(Dskip[D + d0], Dskip[D + d0 + 1]);
     const float2 z2 = make_float2(0.f, 0.f);
     float2 awf[4] = {z2, z2, z2, z2}, awb[4] = {z2, z2, z2, z2}, abf = z2, abb = z2;
+    float2 aDf = z2, aDb = z2;
 
     for (int64_t item = slot; item < nitems; item += nslots) {
         const int b = (int)(item / nseg), sgi = (int)(item - (int64_t)b * nseg);
@@ -244,6 +263,7 @@ conv_pool_bwd_stream_kernel(Geom g, int nseg, int seg_len, int64_t nitems, int n
             qe[k] = oe >= 0 ? P::ld(eb + oe) : P::zero();
         }
         float2 xw[4] = {z2, z2, z2, z2}, cbw[4] = {z2, z2, z2, z2}, gfw[4] = {z2, z2, z2, z2}, gbw[4] = {z2, z2, z2, z2};
+        float2 ew[4] = {z2, z2, z2, z2};   // e[f-m] in slot (k - m) & 3 (WITH_DD only)
         float2 duf = z2, dub = z2;
         int jcur = -1;
         for (int base = 0; base < n6; base += 4) {
@@ -270,9 +290,19 @@ conv_pool_bwd_stream_kernel(Geom g, int nseg, int seg_len, int64_t nitems, int n
                 const float2 x3 = xw[(k + 1) & 3], x2 = xw[(k + 2) & 3], x1 = xw[(k + 3) & 3], x0 = xw[k];  // x[f-3..f]
                 const float2 cf = __ffma2_rn(wf[3], x0, __ffma2_rn(wf[2], x1, __ffma2_rn(wf[1], x2, __ffma2_rn(wf[0], x3, bf_))));
                 const float2 cbk = __ffma2_rn(wb[3], x3, __ffma2_rn(wb[2], x2, __ffma2_rn(wb[1], x1, __ffma2_rn(wb[0], x0, bb_))));
-                float2 Gf = __fmul2_rn(__ffma2_rn(ev, Df, duf), dsilu2<FAST>(cf));        // G_f[f]
+                float2 Gf, Gb;
+                if (WITH_DD) {
+                    ew[k] = inr ? ev : z2;
+                    float2 slf, slb;
+                    Gf = __fmul2_rn(__ffma2_rn(ev, Df, duf), dsilu2_val<FAST>(cf, slf));  // G_f[f]
+                    Gb = __fmul2_rn(cbw[(k + 1) & 3], dsilu2_val<FAST>(cbk, slb));        // G_b[f-3] (0 outside)
+                    if (i >= 3 && i < n + 3 && inr) aDf = __ffma2_rn(ev, slf, aDf);       // xc_f[f] = silu(cf)
+                    if (i >= 6 && i < n6) aDb = __ffma2_rn(ew[(k + 1) & 3], slb, aDb);    // xc_b[f-3] = silu(cbk)
+                } else {
+                    Gf = __fmul2_rn(__ffma2_rn(ev, Df, duf), dsilu2<FAST>(cf));           // G_f[f]
+                    Gb = __fmul2_rn(cbw[(k + 1) & 3], dsilu2<FAST>(cbk));                 // G_b[f-3] (0 outside)
+                }
                 if (!inr) Gf = z2;
-                const float2 Gb = __fmul2_rn(cbw[(k + 1) & 3], dsilu2<FAST>(cbk));         // G_b[f-3] (0 outside)
                 gfw[k] = Gf;
                 gbw[k] = Gb;
                 // ownership: G_f[f] for f in [t0, t0+n) <=> 3 <= i < n+3;  token t = f-3 (dx, G_b) <=> 6 <= i < n+6
@@ -308,16 +338,20 @@ conv_pool_bwd_stream_kernel(Geom g, int nseg, int seg_len, int64_t nitems, int n
         atomicAdd(dcb + d0, abf.x); atomicAdd(dcb + d0 + 1, abf.y);
         atomicAdd(dcb + D + d0, abb.x); atomicAdd(dcb + D + d0 + 1, abb.y);
     }
+    if (WITH_DD) {
+        atomicAdd(dDs + d0, aDf.x); atomicAdd(dDs + d0 + 1, aDf.y);
+        atomicAdd(dDs + D + d0, aDb.x); atomicAdd(dDs + D + d0 + 1, aDb.y);
+    }
 }
 
 template <typename T>
 static int launch_conv_bwd_stream(const Geom& g, const T* x, int64_t ldx, int64_t xbs, const T* e, const T* du,
                                   const float* cw, const float* cb, const float* Dskip, float scale, T* dx, float* dcw,
-                                  float* dcb, cudaStream_t st) {
+                                  float* dcb, float* dDs, cudaStream_t st) {
     const int threads = stream_block(g.D), chunks = (g.D / 2) / threads;
     const int nseg = ceil_div(g.L, 56), seg_len = ceil_div(g.L, nseg);   // equal runs of <= 56 tokens
     const int64_t nitems = (int64_t)g.B * nseg;
-    auto kern = conv_pool_bwd_stream_kernel<T>;
+    auto kern = dDs ? conv_pool_bwd_stream_kernel<T, true> : conv_pool_bwd_stream_kernel<T, false>;
     int occ = 0;
     cudaError_t er = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, 0);
     FV_REQUIRE(er == cudaSuccess && occ > 0, "fv_conv_pool_bwd: occupancy query failed (%s)", cudaGetErrorString(er));
@@ -328,7 +362,7 @@ static int launch_conv_bwd_stream(const Geom& g, const T* x, int64_t ldx, int64_
     const int64_t rounds = (nitems + nslots - 1) / nslots;
     nslots = (nitems + rounds - 1) / rounds;
     kern<<<(unsigned)(nslots * chunks), threads, 0, st>>>(g, nseg, seg_len, nitems, (int)nslots, chunks, x, ldx, xbs, e, du, cw,
-                                                          cb, Dskip, scale, dx, dcw, dcb);
+                                                          cb, Dskip, scale, dx, dcw, dcb, dDs);
     return finish_launch("conv_pool_bwd");
 }
 
@@ -374,7 +408,7 @@ static int launch_conv_bwd(const Geom& g, int tpg, int tile_len, const T* x, int
 extern "C" int fv_conv_pool_bwd(const fv_geom* g_, int dtype, const void* x, int64_t ldx, int64_t x_bstride,
                                 const void* e, const void* du, const float* conv_w, const float* conv_b,
                                 const float* Dskip, float scale, int pool_mode, void* dx, float* dconv_w,
-                                float* dconv_b, void* stream) {
+                                float* dconv_b, float* dDskip, void* stream) {
     using namespace fv;
     if (int rc = check_geom(g_, "fv_conv_pool_bwd")) return rc;
     FV_REQUIRE(x && e && du && conv_w && Dskip && dx && dconv_w, "fv_conv_pool_bwd: null pointer");
@@ -388,12 +422,13 @@ extern "C" int fv_conv_pool_bwd(const fv_geom* g_, int dtype, const void* x, int
     if (!tiled_only && stream_block(g.D) > 0 && ldx % 2 == 0 && x_bstride % 2 == 0) {
         if (dtype == FV_F32)
             return launch_conv_bwd_stream<float>(g, (const float*)x, ldx, x_bstride, (const float*)e, (const float*)du, conv_w,
-                                                 conv_b, Dskip, scale, (float*)dx, dconv_w, dconv_b, st);
+                                                 conv_b, Dskip, scale, (float*)dx, dconv_w, dconv_b, dDskip, st);
         if (dtype == FV_BF16)
             return launch_conv_bwd_stream<bf16>(g, (const bf16*)x, ldx, x_bstride, (const bf16*)e, (const bf16*)du, conv_w,
-                                                conv_b, Dskip, scale, (bf16*)dx, dconv_w, dconv_b, st);
+                                                conv_b, Dskip, scale, (bf16*)dx, dconv_w, dconv_b, dDskip, st);
         return fail("fv_conv_pool_bwd: unsupported dtype %d", dtype);
     }
+    FV_REQUIRE(!dDskip, "fv_conv_pool_bwd: dDskip is produced by the streaming kernel only (dim %% 64 == 0, even strides)");
     const size_t budget = 200 * 1024;
     int maxlen = 8;
     if ((dtype == FV_F32 ? conv_bwd_smem<float, 8>(g.D) : conv_bwd_smem<bf16, 8>(g.D)) > budget) maxlen = 4;

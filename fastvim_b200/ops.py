@@ -174,10 +174,15 @@ def block_pack_xproj(xproj_w: Tensor) -> Optional[Tensor]:
 def block_fwd(x: Tensor, z: Tensor, geom: Geometry, conv_w: Tensor, conv_b: Optional[Tensor], xproj_w: Tensor,
               dt_w: Tensor, dt_bias: Tensor, A: Tensor, Dskip: Tensor, ln_w: Optional[Tensor], ln_b: Optional[Tensor],
               eps: float, scale: float, dt_rank: int, d_state: int, a_is_log: bool = True, save: bool = False,
-              xproj_w_packed: Optional[Tensor] = None):
+              xproj_w_packed: Optional[Tensor] = None, save_v: Optional[bool] = None):
     """K-fused.  x, z (B, L, D) bf16 halves of the in_proj output -> y (B, L, D) bf16 (the out_proj input).
     xproj_w (2, R+2N, D) bf16, dt_w (2, D, R) fp32.  With ``save`` also returns the pooled intermediates
-    (u (2, B, Lp, D) bf16, xdbl (2, B*Lp, R+2N) bf16, s (2, B, Lp, D) fp32) the backward kernels need."""
+    (u (2, B, Lp, D) bf16, xdbl (2, B*Lp, R+2N) bf16, s (2, B, Lp, D) fp32) the backward kernels need.  With ``save_v``
+    (implies ``save``) returns (y, u, xdbl, s, v): when the cluster kernel serves the configuration, v (B, L, D) bf16 --
+    the pre-norm merged value, for ``gate_bwd_v`` -- is saved INSTEAD of s (s is None); otherwise v is None."""
+    want5 = save_v is not None     # the 5-tuple form (training path) whenever the caller names save_v
+    save_v = bool(save_v)
+    save = save or want5
     _check_cuda(x, z, xproj_w, dt_w)
     B, L, D = x.shape
     assert L == geom.L and x.dtype == torch.bfloat16 and xproj_w.dtype == torch.bfloat16 and dt_w.dtype == torch.float32
@@ -188,15 +193,21 @@ def block_fwd(x: Tensor, z: Tensor, geom: Geometry, conv_w: Tensor, conv_b: Opti
         xproj_w_packed = block_pack_xproj(xproj_w)
     y = torch.empty((B, L, D), device=x.device, dtype=x.dtype)
     ncols = dt_rank + 2 * d_state
-    u = xdbl = s = None
+    u = xdbl = s = v = None
+    g = geom.c_struct(B, D)
     if save:
         u = torch.empty((2, B, geom.Lp, D), device=x.device, dtype=x.dtype)
         xdbl = torch.empty((2, B * geom.Lp, ncols), device=x.device, dtype=x.dtype)
-        s = torch.empty((2, B, geom.Lp, D), device=x.device, dtype=torch.float32)
-    g = geom.c_struct(B, D)
+        if save_v and _lib.lib().fv_block_fwd_saves_v(C.byref(g), FV_BF16, int(dt_rank), int(d_state)):
+            # the streaming gate backward works from the saved pre-norm value; the per-direction scan outputs are not needed
+            v = torch.empty((B, L, D), device=x.device, dtype=x.dtype)
+        else:
+            s = torch.empty((2, B, geom.Lp, D), device=x.device, dtype=torch.float32)
     _lib.call("fv_block_fwd", C.byref(g), FV_BF16, _p(x), _p(z), ldx, bs, _p(conv_w), _p(conv_b), _p(xproj_w), _p(xproj_w_packed),
               _p(dt_w), _p(dt_bias), _p(A), int(a_is_log), int(dt_rank), int(d_state), _p(Dskip), _p(ln_w), _p(ln_b), float(eps),
-              float(scale), _p(y), y.stride(1), y.stride(0), _p(u), _p(xdbl), _p(s), _stream(x))
+              float(scale), _p(y), y.stride(1), y.stride(0), _p(u), _p(xdbl), _p(s), _p(v), _stream(x))
+    if want5:
+        return y, u, xdbl, s, v
     return (y, u, xdbl, s) if save else y
 
 
@@ -452,19 +463,50 @@ def scan_bwd(ds: Tensor, u: Tensor, xdbl: Tensor, geom: Geometry, dt_rank: int, 
     return du, ddelta, dbc, dA, dbias
 
 
+def gate_bwd_v_supported(geom: Geometry, batch: int, dim: int, dtype: torch.dtype) -> bool:
+    if dtype != torch.bfloat16:
+        return False
+    g = geom.c_struct(batch, dim)
+    # the conv backward must be able to produce dD as well (streaming kernel: dim % 64 == 0)
+    return bool(_lib.lib().fv_gate_bwd_v_supported(C.byref(g), FV_BF16)) and dim % 64 == 0
+
+
+def gate_bwd_v(v: Tensor, z: Tensor, dy: Tensor, geom: Geometry, ln_w: Optional[Tensor], ln_b: Optional[Tensor], eps: float,
+               dz: Tensor):
+    """K2b-bwd from the saved pre-norm value v (B, L, D).  Writes dz in place; returns (e (B, L, D), ds (1, B, Lp, D) fp32,
+    dln_w, dln_b).  The D-skip gradients come from ``conv_pool_bwd(..., want_dD=True)``."""
+    _check_cuda(v, z, dy)
+    B, L, D = v.shape
+    assert v.is_contiguous()
+    ldz, zbs = _tokmajor(z, "z")
+    assert _tokmajor(dz, "dz") == (ldz, zbs)
+    lddy, dybs = _tokmajor(dy, "dy")
+    f32 = dict(device=v.device, dtype=torch.float32)
+    e = torch.empty((B, L, D), device=v.device, dtype=v.dtype)
+    ds = torch.empty((1, B, geom.Lp, D), **f32)
+    dlw = torch.zeros(D, **f32) if ln_w is not None else None
+    dlb = torch.zeros(D, **f32) if ln_w is not None else None
+    g = geom.c_struct(B, D)
+    _lib.call("fv_gate_bwd_v", C.byref(g), _dt(v), _p(v), _p(z), ldz, zbs, _p(dy), lddy, dybs, _p(ln_w), _p(ln_b), float(eps),
+              _p(dz), _p(e), _p(ds), _p(dlw), _p(dlb), _stream(v))
+    return e, ds, dlw, dlb
+
+
 def conv_pool_bwd(x: Tensor, e: Tensor, du: Tensor, geom: Geometry, conv_w: Tensor, conv_b: Optional[Tensor],
-                  Dskip: Tensor, scale: float, dx: Tensor):
-    """K1-bwd.  Writes dx in place (the x half of the d(xz) buffer); returns (dconv_w (2, D, 4), dconv_b (2, D))."""
+                  Dskip: Tensor, scale: float, dx: Tensor, want_dD: bool = False):
+    """K1-bwd.  Writes dx in place (the x half of the d(xz) buffer); returns (dconv_w (2, D, 4), dconv_b (2, D)) and,
+    with ``want_dD``, also dDskip (2, D) = sum e * xc."""
     _check_cuda(x, e, du)
     B, L, D = x.shape
     ldx, bs = _tokmajor(x, "x")
     assert _tokmajor(dx, "dx") == (ldx, bs) and e.is_contiguous() and du.is_contiguous()
     dcw = torch.zeros((2, D, 4), device=x.device, dtype=torch.float32)
     dcb = torch.zeros((2, D), device=x.device, dtype=torch.float32) if conv_b is not None else None
+    dD = torch.zeros((2, D), device=x.device, dtype=torch.float32) if want_dD else None
     g = geom.c_struct(B, D)
     _lib.call("fv_conv_pool_bwd", C.byref(g), _dt(x), _p(x), ldx, bs, _p(e), _p(du), _p(conv_w), _p(conv_b),
-              _p(Dskip), float(scale), FV_POOL_MEAN, _p(dx), _p(dcw), _p(dcb), _stream(x))
-    return dcw, dcb
+              _p(Dskip), float(scale), FV_POOL_MEAN, _p(dx), _p(dcw), _p(dcb), _p(dD), _stream(x))
+    return (dcw, dcb, dD) if want_dD else (dcw, dcb)
 
 
 def add_norm_bwd(dy: Tensor, dres_out: Optional[Tensor], res_out: Tensor, weight: Tensor, eps: float, is_rms: bool,

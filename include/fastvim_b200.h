@@ -126,7 +126,12 @@ int fv_block_fwd(const fv_geom* g, int dtype, const void* x, const void* z, int6
                  const void* xproj_w_packed, const float* dt_w, const float* dt_bias, const float* A, int a_is_log, int dt_rank,
                  int dstate, const float* Dskip, const float* ln_w, const float* ln_b, float eps,
                  float scale, void* y, int64_t ldy, int64_t y_bstride, void* u_out,
-                 void* xdbl_out, float* s_out, void* stream);
+                 void* xdbl_out, float* s_out, void* v_out, void* stream);
+/* v_out (optional): (B, L, dim) bf16 in memory token order, the pre-norm merged value
+ *   v = (s_f[j] + s_b[j] + D_f xc_f + D_b xc_b) / 2   (the reference's (out + out_b.flip) / 2, mamba_simple_faster.py:438)
+ * saved for fv_gate_bwd_v.  Only the cluster kernel (dim a multiple of 192, <= 16 pooled rows) writes it:
+ * fv_block_fwd_saves_v() == 1; fv_block_fwd fails when v_out is given and the configuration does not qualify. */
+int fv_block_fwd_saves_v(const fv_geom* g, int dtype, int dt_rank, int dstate);
 
 /* ---- fused residual add + RMSNorm / LayerNorm (prenorm form) ------------------------
  * Replaces mamba_ssm/ops/triton/layernorm.py:66-121 as used by Block.forward
@@ -270,11 +275,23 @@ int fv_reduce_planes(int out_dtype, const float* in, int nplanes, int64_t n, voi
 
 /* K1-bwd.  e from fv_gate_bwd, du (2, B, Lp, dim) dtype = total gradient of the pooled conv outputs.
  * Outputs: dx (same layout/strides as x: the x half of the d(xz) buffer), dconv_w (2, dim, 4),
- * dconv_b (2, dim) fp32 accumulated. */
+ * dconv_b (2, dim) fp32 accumulated; optionally dDskip (2, dim) fp32 accumulated = sum e * xc_{f,b} (pass it when
+ * e comes from fv_gate_bwd_v, which does not form the D-skip gradients; NULL otherwise). */
 int fv_conv_pool_bwd(const fv_geom* g, int dtype, const void* x, int64_t ldx, int64_t x_bstride,
                      const void* e, const void* du, const float* conv_w, const float* conv_b,
                      const float* Dskip, float scale, int pool_mode, void* dx, float* dconv_w,
-                     float* dconv_b, void* stream);
+                     float* dconv_b, float* dDskip, void* stream);
+
+/* K2b-bwd, streaming form: backward of (LayerNorm + SiLU gate) from the pre-norm value v saved by fv_block_fwd (v_out).
+ * Replaces autograd through mamba_simple_faster.py:434-453.  v, e, dy-independent layouts as fv_block_fwd: v and e are
+ * (B, L, dim) bf16 in memory token order, z / dz rows have stride ldz (the z half of the (d)xz buffer), dy has lddy.
+ * Outputs: dz, e = dv / 2 (consumed by fv_conv_pool_bwd), ds (B, Lp, dim) fp32 = sum of e over each pooled row (ONE
+ * plane, valid for both scan directions), dln_w / dln_b (dim) fp32 accumulated.  bf16, plain geometry,
+ * dim in {384, 768, 1536, 3072}: fv_gate_bwd_v_supported(). */
+int fv_gate_bwd_v_supported(const fv_geom* g, int dtype);
+int fv_gate_bwd_v(const fv_geom* g, int dtype, const void* v, const void* z, int64_t ldz, int64_t z_bstride,
+                  const void* dy, int64_t lddy, int64_t dy_bstride, const float* ln_w, const float* ln_b, float eps,
+                  void* dz, void* e, float* ds, float* dln_w, float* dln_b, void* stream);
 
 /* add + norm backward.  residual_out is the fp32 sum saved by the forward; dresidual_out (grad of that
  * output) may be NULL.  dx (dtype) and/or dresidual_in (fp32) receive the same gradient. */

@@ -264,11 +264,19 @@ def _oracle_mixer_grads(h, p, ts, dout, **kw):
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-@pytest.mark.parametrize("d_model,ts,norm", [(192, (14, 14), True), (64, (5, 9), True), (96, (3, 40), True),
-                                              (64, (20, 2), False), (768, (14, 14), True)])
-def test_mixer_backward_vs_oracle(dtype, d_model, ts, norm):
-    """Gradients of the CUDA training path (MixerFn: gate_bwd, scan_bwd, conv_pool_bwd) w.r.t. the input
+@pytest.mark.parametrize("d_model,ts,norm,gate_v", [
+    (192, (14, 14), True, True), (64, (5, 9), True, True), (96, (3, 40), True, True), (64, (20, 2), False, True),
+    (768, (14, 14), True, True),
+    (384, (14, 14), True, True),       # FastVim-S: 4-CTA clusters, 2 warps per token in the streaming gate backward
+    (192, (10, 12), False, True),      # no LayerNorm on the streaming gate backward, generic grid
+    (192, (14, 14), True, False),      # round-1 recomputing gate backward (FASTVIM_GATE_BWD_V=0) stays covered
+    (768, (14, 14), True, False)])
+def test_mixer_backward_vs_oracle(dtype, d_model, ts, norm, gate_v, monkeypatch):
+    """Gradients of the CUDA training path (MixerFn: gate_bwd_v | gate_bwd, scan_bwd, conv_pool_bwd) w.r.t. the input
     and every parameter against autograd through the fp64 oracle."""
+    from fastvim_b200 import autograd as fv_autograd
+
+    monkeypatch.setattr(fv_autograd, "GATE_BWD_V", gate_v)
     p = O.random_mixer_params(d_model, seed=5)
     if not norm:
         p = {k: v for k, v in p.items() if not k.startswith("layernorm")}
@@ -407,7 +415,7 @@ def test_block_fwd_fused_vs_four_launch_and_oracle(Bt, rows, cols, Dm, R, rot, n
                   C.c_void_p(dtw.data_ptr()), C.c_void_p(dtb.data_ptr()), C.c_void_p(A_log.data_ptr()), 1, R, N,
                   C.c_void_p(Dk.data_ptr()), None if lw is None else C.c_void_p(lw.data_ptr()),
                   None if lb is None else C.c_void_p(lb.data_ptr()), 1e-5, float(sf), C.c_void_p(y3.data_ptr()),
-                  y3.stride(1), y3.stride(0), None, None, None, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                  y3.stride(1), y3.stride(0), None, None, None, None, C.c_void_p(torch.cuda.current_stream().cuda_stream))
         if cluster:   # a different kernel (other summation orders): close, not identical
             assert_close(y, y3, TOL[torch.bfloat16], "cluster kernel vs one-CTA kernel")
         else:         # fragment-order x_proj weights are a pure re-layout: bit-identical result

@@ -120,6 +120,13 @@ def main():
         t = timeit(lambda i: ops.conv_pool_bwd(xz[i][..., :D], e_[i], u[i], geom, cw, cb, Dk, 1.0, dxz[i & 1][..., :D]),
                    nrot, a.iters)
         rep("conv_pool_bwd", t, 3 * Bt * L * D * s + 2 * Bt * Lp * D * s)
+        if ops.gate_bwd_v_supported(geom, Bt, D, dt):
+            vv = [torch.randn(Bt, L, D, device=dev).to(dt) for _ in range(nrot)]
+            t = timeit(lambda i: ops.gate_bwd_v(vv[i], xz[i][..., D:], dy[i], geom, lw, lb, 1e-5, dxz[i & 1][..., D:]), nrot, a.iters)
+            rep("gate_bwd_v", t, 5 * Bt * L * D * s + Bt * Lp * D * 4)
+            t = timeit(lambda i: ops.conv_pool_bwd(xz[i][..., :D], e_[i], u[i], geom, cw, cb, Dk, 1.0, dxz[i & 1][..., :D],
+                                                   want_dD=True), nrot, a.iters)
+            rep("conv_pool_bwd(+dD)", t, 3 * Bt * L * D * s + 2 * Bt * Lp * D * s)
     if not only or "add_norm" in only:
         t = timeit(lambda i: ops.add_norm_fwd(hs[i], res[i], nw, None, 1e-5, True), nrot, a.iters)
         rep("add_norm_fwd", t, Bt * L * dm * (s + 4) * 2)
