@@ -386,9 +386,22 @@ def run_infer(a, ctx: Ctx, workload: str, main: bool):
     # one very large image: d_inner channels sharded over the ranks (strong scaling), same image on every rank
     sharded = img >= 1024 and world > 1
     shard_info = None
+    runner = model
     if sharded:
-        from fastvim_b200.sharded import shard_model_channels
-        shard_model_channels(model, None, a.out_mode)
+        from fastvim_b200 import sharded as fv_sharded
+        if a.out_mode == "hybrid" and fv_sharded.hybrid_supported(model, world, (img, img)):
+            try:   # peer-memory exchanges (csrc/peer.cu); needs torch symmetric memory for the mapping
+                runner = fv_sharded.shard_model_hybrid(model, None)
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+                    runner(torch.zeros(1, C_in, img, img, device=dev))
+                torch.cuda.synchronize()
+            except Exception as ex:
+                sys.stderr.write(f"[bench] hybrid peer-memory sharding unavailable ({type(ex).__name__}: {ex}); NCCL path\n")
+                runner = model
+        if runner is model:
+            fv_sharded.shard_model_channels(model, None, "gather" if a.out_mode == "hybrid" else a.out_mode)
+            model._shard_desc = (f"d_inner channel-sharded x{world}: NCCL all-reduce of x_proj partials + LN sums, "
+                                 f"{a.out_mode} around out_proj")
         shard_info = getattr(model, "_shard_desc", None)
     n_img_step = Bt if sharded else Bt * world
     g = torch.Generator(device="cpu").manual_seed(100 + (0 if sharded else rank))
@@ -402,7 +415,7 @@ def run_infer(a, ctx: Ctx, workload: str, main: bool):
 
     def fwd(x):
         with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-            return model(x)
+            return runner(x)
 
     # ---- static buffers + CUDA graphs (two per host format, for the double-buffered e2e loops)
     static_in = {f: [host_imgs[f][i].to(dev) for i in range(2)] for f in formats}
@@ -606,7 +619,7 @@ def run_infer(a, ctx: Ctx, workload: str, main: bool):
         if parity is not None:
             line["parity_check"] = parity
     # release everything this workload holds on the device (extra workloads follow in the same process)
-    del graphs, static_out, static_in, model
+    del graphs, static_out, static_in, model, runner
     gc.collect()
     torch.cuda.synchronize()
     torch.cuda.empty_cache()
@@ -893,8 +906,9 @@ def main():
     ap.add_argument("--no-competitor", action="store_true")
     ap.add_argument("--no-e2e-variants", action="store_true", help="only the fp32-host e2e loop")
     ap.add_argument("--bucket-mb", type=float, default=64.0, help="gradient bucket size of the captured exchange")
-    ap.add_argument("--out-mode", default="gather", choices=["gather", "reduce"],
-                    help="channel-sharded 2048^2 mode: all-gather y before out_proj, or row-sharded out_proj + all-reduce")
+    ap.add_argument("--out-mode", default="hybrid", choices=["hybrid", "gather", "reduce"],
+                    help="single-image multi-GPU mode: hybrid token/channel sharding over peer memory (default), or the "
+                         "round-1 NCCL channel sharding (all-gather y before out_proj | row-sharded out_proj + all-reduce)")
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work for the CPU legs")
     a = ap.parse_args()
     if a.impl == "reference":

@@ -166,6 +166,21 @@ int fv_patchify_supported(int in_dtype, int C, int H, int W, int patch);
 int fv_patchify(int in_dtype, int batch, int C, int H, int W, int patch, int per_channel, const void* img,
                 void* out, void* stream);
 
+/* ---- peer-memory exchanges of the single-image multi-GPU mode (csrc/peer.cu) ------------------------------------
+ * The reference is data-parallel only; BASELINE.json configs[4] (one 2048 x 2048 image over 8 GPUs) shards the block.
+ * Every rank owns one SYMMETRIC buffer (same size and layout on all ranks, mapped into every process by the host, e.g.
+ * torch.distributed._symmetric_memory); bufs[q] is rank q's buffer as addressed from the calling process.  The first
+ * fv_peer_header_bytes() bytes hold the flag words (zero them once, then barrier on the host before the first call).
+ * Each call = a barrier over all ranks followed by direct NVLink reads of the peers' buffers, in ONE kernel; all ranks
+ * must issue the same sequence of fv_peer_* calls.  No NCCL on the data path. */
+int64_t fv_peer_header_bytes(void);
+int fv_peer_sum_f32(int world, int rank, const void* const* bufs, int64_t off, int64_t n, float* out32, void* out16,
+                    void* stream);
+int fv_peer_copy2d(int world, int rank, const void* const* bufs, int nparts, int rows, int64_t row_bytes,
+                   const int64_t* src_off, int64_t src_ld, const int64_t* dst_off, int64_t dst_ld, void* dst,
+                   void* stream);
+int fv_peer_error(const void* local_buf);
+
 /* ---- tcgen05 / TMEM / TMA GEMMs for the projections -------------------------------------------
  * C (M x N) = A (M x K) . W (N x K)^T: bf16 operands (row-major, row strides lda / ldw / ldc elements,
  * 16-byte aligned, multiples of 8), fp32 accumulation in tensor memory, bf16 result.  Replaces the cuBLAS

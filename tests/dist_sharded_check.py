@@ -35,12 +35,16 @@ def main():
         with torch.no_grad():
             want = O.fastvim_oracle(x, sd, depth=24)
         m = m.cuda()
-        for out_mode in ("gather", "reduce"):
+        for out_mode in ("hybrid", "gather", "reduce"):
             for dtype in (torch.float32, torch.bfloat16):
                 torch.manual_seed(0)
                 ms = fastvim_tiny(img_size=2048, drop_path_rate=0.0).eval().cuda()
                 ms.load_state_dict(sd)
-                shard_model_channels(ms, None, out_mode)
+                if out_mode == "hybrid":
+                    from fastvim_b200.sharded import shard_model_hybrid
+                    ms = shard_model_hybrid(ms, None)
+                else:
+                    shard_model_channels(ms, None, out_mode)
                 with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
                     got = ms(x.cuda()).float().cpu()
                 e = relerr(got, want)
@@ -53,18 +57,28 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         dist.destroy_process_group()
         sys.exit(0 if int(t.item()) == 1 else 1)
+    from fastvim_b200.sharded import hybrid_supported, shard_model_hybrid
     for (img, E, depth, norm) in [((64, 96), 64, 4, True), ((128, 128), 64, 2, False), ((256, 256), 192, 2, True)]:
-        for out_mode in ("gather", "reduce"):
+        for out_mode in ("hybrid", "gather", "reduce"):
             for dtype in (torch.float32, torch.bfloat16):
                 torch.manual_seed(0)
                 m = VisionMamba(img_size=img, embed_dim=E, depth=depth, num_classes=10, rms_norm=True, residual_in_fp32=True,
                                 fused_add_norm=True, final_pool_type="mean", drop_path_rate=0.0,
                                 use_norm_after_ssm=norm).eval().cuda()
                 x = torch.randn(1, 3, *img, device="cuda")
+                if out_mode == "hybrid" and not hybrid_supported(m, world, img):
+                    continue      # token bands would split a token row at this world size
                 with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
                     want = m(x).float()
-                    shard_model_channels(m, None, out_mode)
-                    got = m(x).float()
+                    if out_mode == "hybrid":
+                        runner = shard_model_hybrid(m, None)
+                        got = runner(x).float()
+                        got2 = runner(x).float()      # second call: flags, buffers and caches are reusable
+                        assert torch.equal(got, got2)
+                        assert runner._state["pb"].error() == 0, "a peer spin timed out"
+                    else:
+                        shard_model_channels(m, None, out_mode)
+                        got = m(x).float()
                 e = relerr(got, want)
                 tol = 1e-4 if dtype == torch.float32 else 2e-2
                 good = e <= tol

@@ -44,7 +44,7 @@ def test_ctypes_table_matches_header(built_lib):
     src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
     for name, args in _lib.SIGNATURES.items():
         decl = re.search(r"\b%s\s*\((.*?)\)\s*;" % name, src, flags=re.S).group(1)
-        assert len([a for a in decl.split(",") if a.strip()]) == len(args), name
+        assert len([a for a in decl.split(",") if a.strip() and a.strip() != "void"]) == len(args), name
     l = _lib.lib()
     assert l.fv_version() >= 100
     assert l.fv_last_error() is not None
