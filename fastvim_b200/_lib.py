@@ -44,6 +44,7 @@ SIGNATURES = {
     "fv_selective_scan_fwd": [_I, _I, _I, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P],
     "fv_gemm_bf16_tn": [_L, _I, _I, _P, _L, _P, _L, _P, _P, _L, _P],
     "fv_gemm_supported": [_L, _I, _I],
+    "fv_ln_gate_fwd": [_I, _L, _I, _P, _L, _P, _L, _P, _P, _F, _P, _L, _P],
     "fv_peer_header_bytes": [],
     "fv_peer_sum_f32": [_I, _I, _P, _L, _L, _P, _P, _P],
     "fv_peer_copy2d": [_I, _I, _P, _I, _I, _L, _P, _L, _P, _L, _P, _P],

@@ -253,3 +253,92 @@ extern "C" int fv_add_norm_bwd(int dtype, int64_t rows, int cols, const void* dy
         return launch_add_norm_bwd<bf16>(rows, cols, (const bf16*)dy, lddy, dresidual_out, residual_out, weight, eps, is_rms, (bf16*)dx, lddx, dresidual_in, dweight, dbias, st);
     return fail("fv_add_norm_bwd: unsupported dtype %d", dtype);
 }
+
+// ---- token-side LayerNorm + SiLU gate of the hybrid-sharded mode ------------------------------------------------------
+// y = LayerNorm_D(v; gamma, beta) * silu(z)   (mamba_simple_faster.py:437-441; without gamma: y = v * silu(z), :445-453)
+// for rows that hold ALL d_inner channels of a token: after the channel -> token all-to-all of the single-image
+// multi-GPU mode the LayerNorm over d_inner is token-local, so no statistics have to cross GPUs.  One warp per row,
+// row in registers, two-pass variance like add_norm_fwd_kernel.
+namespace fv {
+
+template <typename T, int NV>
+__global__ void __launch_bounds__(NORM_WARPS * 32)
+ln_gate_fwd_kernel(int64_t rows, int cols, const T* __restrict__ v, int64_t ldv, const T* __restrict__ z, int64_t ldz,
+                   const float* __restrict__ w, const float* __restrict__ bias, float eps, T* __restrict__ y, int64_t ldy) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * NORM_WARPS + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int nvec = cols >> 2;
+    float4 r[NV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + i * 32;
+        if (c < nvec) {
+            r[i] = ld4(v + row * ldv + c * 4);
+            sum += (r[i].x + r[i].y) + (r[i].z + r[i].w);
+        }
+    }
+    float mean = 0.f, rstd = 1.f;
+    if (w) {
+        mean = warp_sum(sum) / (float)cols;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + i * 32;
+            if (c < nvec) {
+                const float dx = r[i].x - mean, dy = r[i].y - mean, dz = r[i].z - mean, dw = r[i].w - mean;
+                sq += fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
+            }
+        }
+        rstd = rsqrtf(warp_sum(sq) / (float)cols + eps);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + i * 32;
+        if (c < nvec) {
+            float4 a = r[i];
+            if (w) {
+                const float4 g = ld4(w + c * 4), bb = bias ? ld4(bias + c * 4) : zero4();
+                a.x = fmaf((a.x - mean) * rstd, g.x, bb.x); a.y = fmaf((a.y - mean) * rstd, g.y, bb.y);
+                a.z = fmaf((a.z - mean) * rstd, g.z, bb.z); a.w = fmaf((a.w - mean) * rstd, g.w, bb.w);
+            }
+            const float4 zz = ld4(z + row * ldz + c * 4);
+            a.x *= silu_exact(zz.x); a.y *= silu_exact(zz.y); a.z *= silu_exact(zz.z); a.w *= silu_exact(zz.w);
+            st4(y + row * ldy + c * 4, a);
+        }
+    }
+}
+
+template <typename T>
+static int launch_ln_gate(int64_t rows, int cols, const T* v, int64_t ldv, const T* z, int64_t ldz, const float* w,
+                          const float* b, float eps, T* y, int64_t ldy, cudaStream_t st) {
+    const int nv = (cols / 4 + 31) / 32;
+    const unsigned grid = (unsigned)((rows + NORM_WARPS - 1) / NORM_WARPS);
+#define FV_LG(NV_) ln_gate_fwd_kernel<T, NV_><<<grid, NORM_WARPS * 32, 0, st>>>(rows, cols, v, ldv, z, ldz, w, b, eps, y, ldy)
+    if (nv <= 1) FV_LG(1);
+    else if (nv <= 2) FV_LG(2);
+    else if (nv <= 3) FV_LG(3);
+    else if (nv <= 6) FV_LG(6);
+    else if (nv <= 12) FV_LG(12);
+    else if (nv <= 24) FV_LG(24);
+    else return fail("fv_ln_gate_fwd: cols %d too large (max 3072)", cols);
+#undef FV_LG
+    return finish_launch("ln_gate_fwd");
+}
+
+}  // namespace fv
+
+extern "C" int fv_ln_gate_fwd(int dtype, int64_t rows, int cols, const void* v, int64_t ldv, const void* z, int64_t ldz,
+                              const float* ln_w, const float* ln_b, float eps, void* y, int64_t ldy, void* stream) {
+    using namespace fv;
+    FV_REQUIRE(v && z && y, "fv_ln_gate_fwd: null pointer");
+    FV_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0 && rows / NORM_WARPS < (1ll << 31), "fv_ln_gate_fwd: bad shape rows %lld cols %d", (long long)rows, cols);
+    FV_REQUIRE(ldv % 4 == 0 && ldz % 4 == 0 && ldy % 4 == 0, "fv_ln_gate_fwd: row strides must be multiples of 4");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == FV_F32)
+        return launch_ln_gate<float>(rows, cols, (const float*)v, ldv, (const float*)z, ldz, ln_w, ln_b, eps, (float*)y, ldy, st);
+    if (dtype == FV_BF16)
+        return launch_ln_gate<bf16>(rows, cols, (const bf16*)v, ldv, (const bf16*)z, ldz, ln_w, ln_b, eps, (bf16*)y, ldy, st);
+    return fail("fv_ln_gate_fwd: unsupported dtype %d", dtype);
+}

@@ -4,16 +4,16 @@
 // The reference has no counterpart (it is data-parallel only).  Round 1 sharded d_inner over the
 // ranks and called three NCCL collectives per block (72 per step): at 11 KB .. 12.6 MB per message they are latency-bound
 // (~20 us each inside a CUDA graph) and N = 2 ran at 0.55x of one GPU.  Here every exchange is ONE kernel:
-//   barrier   CTA 0: thread q signals peer q (system-scope CAS 0 -> 1 on the peer's flag word for this rank) and consumes
-//             the peer's signal (CAS 1 -> 0 on the local word); the protocol is replay-safe (no epochs baked into a
-//             captured CUDA graph) and single-buffered: a rank can only re-signal once its previous signal was consumed.
-//             The other CTAs of the launch are released through local flag words with the same CAS pair.
+//   barrier   CTA 0: thread q tells peer q "I have entered my k-th peer kernel" with a one-way system-scope RED on the
+//             peer's arrival counter and spins on its own counter for q; k is a device-resident sequence number, so the
+//             protocol is replay-safe (no epochs baked into a captured CUDA graph) and costs one NVLink one-way latency.
+//             The other CTAs of the launch are released through local tokens.
 //   data      every CTA then reads the peers' buffers directly (ld.global.cg over NVLink) -- a rank-ordered sum of fp32
 //             partials (x_proj partial products, LayerNorm sums: deterministic, identical on all ranks) or a strided 2-D
 //             copy (the token <-> channel all-to-all) -- and writes local memory.
 // A spin that lasts longer than ~2 s sets an error word and falls through instead of hanging the GPU.
-// Symmetric buffer layout (same on every rank): [0, 32) rank flag words, [1024, 1536) CTA flag words, [2048] error word,
-// data from byte 4096 on (the host carves it).
+// Symmetric buffer layout (same on every rank): [0, 384) flag words (arrivals[8] | seq | go, one 128-byte line each), [2048] error word, data from
+// byte 4096 on (the host carves it).
 
 #include "common.cuh"
 
@@ -27,38 +27,65 @@ struct PeerBase {
     int world, rank;
 };
 
-__device__ __forceinline__ bool spin_cas(unsigned int* p, unsigned int from, unsigned int to, bool sys, unsigned int* err) {
-    const long long t0 = clock64();
-    while (true) {
-        const unsigned int old = sys ? atomicCAS_system(p, from, to) : atomicCAS(p, from, to);
-        if (old == from) return true;
-        if (clock64() - t0 > (1ll << 32)) {  // ~2 s: a peer never arrived
-            atomicExch(err, 1u);
-            return false;
-        }
-        __nanosleep(40);
-    }
+// flag words of a rank's buffer: bytes [0, 32) arrivals[q] = number of peer kernels rank q has entered (written by q with a
+// one-way system-scope RED), byte 128 seq = number of peer kernels THIS rank has entered, byte 256 go = release tokens for
+// the other CTAs of the current launch (each on its own 128-byte line).  All state lives in device memory, so a captured CUDA graph replays correctly.
+__device__ __forceinline__ unsigned int ld_volatile_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_add_sys(unsigned int* p, unsigned int v) {
+    asm volatile("red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
 // all ranks have reached this kernel (so everything they launched before it is complete and visible)
 __device__ __forceinline__ void peer_sync(const PeerBase& pb) {
     unsigned char* mine = pb.buf[pb.rank];
     unsigned int* err = reinterpret_cast<unsigned int*>(mine + PEER_OFF_ERR);
-    unsigned int* cta = reinterpret_cast<unsigned int*>(mine + PEER_OFF_CTA);
+    unsigned int* flags = reinterpret_cast<unsigned int*>(mine);   // arrivals[8]: their own 128-byte line (remote REDs land here)
+    unsigned int* seq = flags + 32;                                   // byte 128
+    unsigned int* go = flags + 64;                                    // byte 256: polled by the other CTAs, away from the arrivals
+    __shared__ unsigned int s_expected;
     if (blockIdx.x == 0) {
+        if (threadIdx.x == 0) s_expected = ++seq[0];          // single writer: CTA 0 of the (stream-serialised) peer kernels
+        __syncthreads();
+        const unsigned int expected = s_expected;
         const int q = threadIdx.x;
         if (q < pb.world && q != pb.rank) {
             __threadfence_system();
-            spin_cas(reinterpret_cast<unsigned int*>(pb.buf[q]) + pb.rank, 0u, 1u, true, err);   // signal peer q
-            spin_cas(reinterpret_cast<unsigned int*>(mine) + q, 1u, 0u, true, err);              // consume q's signal
+            red_add_sys(reinterpret_cast<unsigned int*>(pb.buf[q]) + pb.rank, 1u);   // one-way: "rank entered kernel #expected"
+            const long long t0 = clock64();
+            while ((int)(ld_volatile_sys(flags + q) - expected) < 0) {
+                if (clock64() - t0 > (1ll << 32)) {  // ~2 s: a peer never arrived
+                    atomicExch(err, 1u);
+                    break;
+                }
+                __nanosleep(20);
+            }
             __threadfence_system();
         }
         __syncthreads();
-        const int c = threadIdx.x;
-        if (c > 0 && c < (int)gridDim.x) spin_cas(cta + c, 0u, 1u, false, err);
+        if (threadIdx.x == 0 && gridDim.x > 1) {
+            __threadfence();
+            atomicAdd(go, gridDim.x - 1);
+        }
     } else {
         if (threadIdx.x == 0) {
-            spin_cas(cta + blockIdx.x, 1u, 0u, false, err);
+            const long long t0 = clock64();
+            while (true) {   // take one release token
+                // exactly gridDim.x - 1 tokens are published for the gridDim.x - 1 waiting CTAs, so once tokens are visible
+                // ONE atomic decrement per CTA always succeeds (a CAS retry loop made the release O(CTAs^2): 100 us at 128 CTAs)
+                if (*reinterpret_cast<volatile unsigned int*>(go) > 0) {
+                    atomicSub(go, 1u);
+                    break;
+                }
+                if (clock64() - t0 > (1ll << 33)) {
+                    atomicExch(err, 1u);
+                    break;
+                }
+                __nanosleep(100);
+            }
             __threadfence();
         }
         __syncthreads();
@@ -106,17 +133,31 @@ __global__ void __launch_bounds__(256) peer_copy_kernel(const PeerCopyArgs a) {
     peer_sync(a.pb);
     const int64_t per_peer = (int64_t)a.nparts * a.rows * a.seg16;
     const int64_t total = per_peer * a.pb.world;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        // peer varies slowest per thread-stride so that consecutive threads stream one peer's rows; start each rank on a
-        // different peer (rank + k) to spread the load over the NVSwitch ports
-        const int k = (int)(i / per_peer);
-        int64_t r = i - (int64_t)k * per_peer;
-        const int q = (a.pb.rank + k) % a.pb.world;
-        const int part = (int)(r / ((int64_t)a.rows * a.seg16));
-        r -= (int64_t)part * a.rows * a.seg16;
-        const int row = (int)(r / a.seg16), c = (int)(r - (int64_t)row * a.seg16);
-        const uint4 v = __ldcg(reinterpret_cast<const uint4*>(a.pb.buf[q] + a.src_off[q][part] + (int64_t)row * a.src_ld) + c);
-        *(reinterpret_cast<uint4*>(a.dst + a.dst_off[q][part] + (int64_t)row * a.dst_ld) + c) = v;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    constexpr int UN = 8;   // 16-byte NVLink loads in flight per thread: the copy is latency- not bandwidth-bound otherwise
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * UN) {
+        uint4 v[UN];
+        unsigned char* d[UN];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const int64_t i = i0 + u * stride;
+            d[u] = nullptr;
+            if (i < total) {
+                // peer varies slowest so that consecutive threads stream one peer's rows; every rank starts on a different
+                // peer (rank + k) to spread the load over the NVSwitch ports
+                const int k = (int)(i / per_peer);
+                int64_t r = i - (int64_t)k * per_peer;
+                const int q = (a.pb.rank + k) % a.pb.world;
+                const int part = (int)(r / ((int64_t)a.rows * a.seg16));
+                r -= (int64_t)part * a.rows * a.seg16;
+                const int row = (int)(r / a.seg16), c = (int)(r - (int64_t)row * a.seg16);
+                v[u] = __ldcg(reinterpret_cast<const uint4*>(a.pb.buf[q] + a.src_off[q][part] + (int64_t)row * a.src_ld) + c);
+                d[u] = a.dst + a.dst_off[q][part] + (int64_t)row * a.dst_ld + (int64_t)c * 16;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u)
+            if (d[u]) *reinterpret_cast<uint4*>(d[u]) = v[u];
     }
 }
 

@@ -222,6 +222,17 @@ def norm_gate_apply(y: Tensor, z: Tensor, stats: Tensor, geom: Geometry, full_di
     return y
 
 
+def ln_gate_fwd(v: Tensor, z: Tensor, ln_w: Optional[Tensor], ln_b: Optional[Tensor], eps: float) -> Tensor:
+    """(rows, D) v, z (unit channel stride, any row stride) -> y (rows, D) = LayerNorm(v) * silu(z)."""
+    _check_cuda(v, z)
+    rows, D = v.shape
+    assert v.stride(1) == 1 and z.stride(1) == 1 and z.shape == v.shape and z.dtype == v.dtype
+    y = torch.empty((rows, D), device=v.device, dtype=v.dtype)
+    _lib.call("fv_ln_gate_fwd", _dt(v), rows, D, _p(v), v.stride(0), _p(z), z.stride(0), _p(ln_w), _p(ln_b), float(eps),
+              _p(y), D, _stream(v))
+    return y
+
+
 def add_norm_fwd(x: Tensor, residual: Optional[Tensor], weight: Tensor, bias: Optional[Tensor],
                  eps: float, is_rms: bool, want_residual: bool = True, want_stats: bool = False):
     """Fused (x + residual) -> fp32 residual_out, y = norm(residual_out).  x: (..., C)."""

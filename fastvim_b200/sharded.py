@@ -212,11 +212,12 @@ class HybridShardedVisionMamba(torch.nn.Module):
         token-sharded   (each rank: L/G tokens = a band of token rows)   patch embed, add + RMSNorm, in_proj, out_proj
         channel-sharded (each rank: d_inner/G channels, all tokens)      conv + pool, x_proj partial, scan, gate
 
-    joined by peer-memory exchanges (csrc/peer.cu), four per block:
-        A  all-to-all  token -> channel of the in_proj output      (L x 2 d_inner/G per rank, bf16: 3.1 MB at 2048^2)
-        B  sum of the x_proj partial products                       (2 x Lp x (R + 2N) fp32: 45 KB)
-        C  sum of the per-token LayerNorm sums                      (L x 2 fp32: 131 KB)
-        D  all-to-all  channel -> token of the gated y              (L/G x d_inner per rank: 1.6 MB)
+    joined by peer-memory exchanges (csrc/peer.cu), three per block:
+        A  all-to-all  token -> channel of the x half of the in_proj output   (L x d_inner/G per rank, bf16: 1.6 MB at 2048^2)
+        B  sum of the x_proj partial products                                  (2 x Lp x (R + 2N) fp32: 45 KB)
+        D  all-to-all  channel -> token of the pre-norm merged value v         (L/G x d_inner per rank: 1.6 MB)
+    z stays on the token side and LayerNorm + gate run there (fv_ln_gate_fwd), where a rank holds every channel of its
+    tokens, so the LayerNorm statistics never cross GPUs.
     Nothing is replicated and no NCCL collective runs on the data path (round 1: three NCCL collectives per block and
     add_norm / out_proj / patch embed replicated on every rank; slower than one GPU).  Follows the structure of
     ``Mamba.forward`` (mamba_simple_faster.py:181-457): conv, pool, scan recurrence, D skip and gate are per channel,
@@ -228,7 +229,7 @@ class HybridShardedVisionMamba(torch.nn.Module):
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self._state = {}
         model._shard_desc = (f"hybrid token/channel sharding x{self.world}: token-sharded patch embed / add+norm / in_proj / "
-                             f"out_proj, channel-sharded conv+pool / scan / gate; 4 peer-memory exchanges per block "
+                             f"LayerNorm+gate / out_proj, channel-sharded conv+pool / scan / D skip; 3 peer-memory exchanges per block "
                              f"(fv_peer_copy2d, fv_peer_sum_f32 over NVLink), no NCCL on the data path")
 
     # ---- per-dtype state: sharded parameters + symmetric buffer ------------------------------------------------
@@ -269,6 +270,10 @@ class HybridShardedVisionMamba(torch.nn.Module):
                 # x_proj weights padded to ncp columns so the partial product lands float4-aligned
                 xw = sp["x_w_t"].float()
                 sp["x_w_t32"] = torch.nn.functional.pad(xw, (0, st["ncp"] - ncols)).contiguous()
+                mx = blk.mixer
+                sp["ln_w_full"] = mx.layernorm.weight.float().contiguous() if mx.use_norm_after_ssm else None
+                sp["ln_b_full"] = mx.layernorm.bias.float().contiguous() if mx.use_norm_after_ssm else None
+                sp["ln_w_one"] = torch.ones(Dl, device=device, dtype=torch.float32)   # selects fv_gate_fwd's pre-norm mode
         self._state = {"k": key, "v": st, "pb": pb, "dt": act_dtype}
         torch.cuda.synchronize(device)
         dist.barrier(self.group)
@@ -291,15 +296,16 @@ class HybridShardedVisionMamba(torch.nn.Module):
             ops.gemm_bf16_tn(h2, sp["in_w_full"], out=xz_tok)
         else:
             xz_tok.copy_(F.linear(h2, sp["in_w_full"], sp["in_b_full"]))
-        # A: all-to-all token -> channel: my channel columns (x and z halves) of every rank's tokens
-        xz_ch = torch.empty((1, L, 2 * Dl), device=h_tok.device, dtype=act)
+        # A: all-to-all token -> channel of the x half only: my channel columns of every rank's tokens.  z never travels --
+        # the gate is applied on the token side, where this rank already holds z for all channels of its tokens.
+        x_ch = torch.empty((1, L, Dl), device=h_tok.device, dtype=act)
         lo = r * Dl
         src_off, dst_off = [], []
         for q in range(G):
-            src_off += [st["off_xz"] + lo * es, st["off_xz"] + (D + lo) * es]
-            dst_off += [q * Lt * 2 * Dl * es, q * Lt * 2 * Dl * es + Dl * es]
-        pb.copy2d(2, Lt, Dl * es, src_off, 2 * D * es, dst_off, 2 * Dl * es, xz_ch)
-        x, z = xz_ch[..., :Dl], xz_ch[..., Dl:]
+            src_off += [st["off_xz"] + lo * es, 0]
+            dst_off += [q * Lt * Dl * es, 0]
+        pb.copy2d(1, Lt, Dl * es, src_off, 2 * D * es, dst_off, Dl * es, x_ch)
+        x = x_ch
         u = ops.conv_pool_fwd(x, geom, sp["conv_w"], sp["conv_b"], float(m.scaling_factor), m.collapse_method)
         # B: x_proj partial over my channels -> symmetric buffer -> rank-ordered sum on every rank
         xpart = st["xpart"][:, :Lp]
@@ -316,23 +322,20 @@ class HybridShardedVisionMamba(torch.nn.Module):
             xdbl = xdbl.contiguous()
         s = ops.scan_fwd(u, xdbl, geom, m.dt_rank, m.d_state, sp["dt_w"], sp["dt_b"], sp["A_log"], a_is_log=True)
         eps = m.layernorm.eps if m.use_norm_after_ssm else 1e-5
-        y_ch = st["y_ch"]
-        if m.use_norm_after_ssm:
-            ops.gate_fwd(x, z, s, geom, sp["conv_w"], sp["conv_b"], sp["D"], sp["ln_w"], sp["ln_b"], eps, out=y_ch,
-                         stats=st["stats"])
-            # C: LayerNorm sums over all d_inner channels
-            stats = torch.empty((1, L, 2), device=h_tok.device, dtype=torch.float32)
-            pb.sum_f32(st["off_st"], L * 2, out32=stats)
-            ops.norm_gate_apply(y_ch, z, stats, geom, D, sp["ln_w"], sp["ln_b"], eps)
-        else:
-            ops.gate_fwd(x, z, s, geom, sp["conv_w"], sp["conv_b"], sp["D"], None, None, eps, out=y_ch)
+        # channel side ends with the PRE-norm merged value v = (s_f + s_b + D_f xc_f + D_b xc_b) / 2 (fv_gate_fwd's
+        # statistics mode writes exactly that; its per-shard sums are not needed any more)
+        v_ch = st["y_ch"]
+        ops.gate_fwd(x, x, s, geom, sp["conv_w"], sp["conv_b"], sp["D"], sp["ln_w_one"], None, eps, out=v_ch,
+                     stats=st["stats"])
         # D: all-to-all channel -> token: all d_inner channels of my tokens
-        y_tok = torch.empty((Lt, D), device=h_tok.device, dtype=act)
+        v_tok = torch.empty((Lt, D), device=h_tok.device, dtype=act)
         src_off, dst_off = [], []
         for q in range(G):
             src_off += [st["off_y"] + r * Lt * Dl * es, 0]
             dst_off += [q * Dl * es, 0]
-        pb.copy2d(1, Lt, Dl * es, src_off, Dl * es, dst_off, D * es, y_tok)
+        pb.copy2d(1, Lt, Dl * es, src_off, Dl * es, dst_off, D * es, v_tok)
+        # token side: LayerNorm over d_inner is local now; gate with the z this rank computed for its own tokens
+        y_tok = ops.ln_gate_fwd(v_tok, xz_tok[:, D:], sp["ln_w_full"], sp["ln_b_full"], eps)
         out = _linear(y_tok, sp["out_w"], sp["out_b"]).view(1, Lt, -1)
         if m.init_layer_scale is not None:
             out = out * m.gamma

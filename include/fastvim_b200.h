@@ -166,6 +166,11 @@ int fv_patchify_supported(int in_dtype, int C, int H, int W, int patch);
 int fv_patchify(int in_dtype, int batch, int C, int H, int W, int patch, int per_channel, const void* img,
                 void* out, void* stream);
 
+/* y = LayerNorm_cols(v; ln_w, ln_b) * silu(z) per row (ln_w NULL: y = v * silu(z)): the token-side half of
+ * mamba_simple_faster.py:437-453 for rows holding ALL d_inner channels of a token (hybrid-sharded multi-GPU mode). */
+int fv_ln_gate_fwd(int dtype, int64_t rows, int cols, const void* v, int64_t ldv, const void* z, int64_t ldz,
+                   const float* ln_w, const float* ln_b, float eps, void* y, int64_t ldy, void* stream);
+
 /* ---- peer-memory exchanges of the single-image multi-GPU mode (csrc/peer.cu) ------------------------------------
  * The reference is data-parallel only; BASELINE.json configs[4] (one 2048 x 2048 image over 8 GPUs) shards the block.
  * Every rank owns one SYMMETRIC buffer (same size and layout on all ranks, mapped into every process by the host, e.g.
