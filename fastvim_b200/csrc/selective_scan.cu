@@ -76,6 +76,8 @@ selective_scan_fwd_kernel(int batch, int dim, int64_t L, int N, int groups, cons
             dv[k] = (t0 + k < L) ? x : 0.f;  // delta = 0 past the end: a = 1, b = 0 (identity map)
             y[k] = 0.f;
         }
+        // two states in flight: their shuffle scans are independent chains (latency-bound at small batch x dim)
+#pragma unroll 2
         for (int n = 0; n < N; ++n) {
             const float A2 = __shfl_sync(0xffffffffu, A2lane, n);
             const float hin = __shfl_sync(0xffffffffu, carry, n);
@@ -249,6 +251,7 @@ selective_scan_bwd_kernel(int batch, int dim, int64_t L, int N, int groups, cons
             ys[k] = 0.f;
         }
         const float cin = (nchunks > 1 && lane < N) ? wsr[(int64_t)c * N + lane] : 0.f;
+#pragma unroll 2
         for (int n = 0; n < N; ++n) {
             const float A2 = __shfl_sync(0xffffffffu, A2lane, n);
             const float An = __shfl_sync(0xffffffffu, Alane, n);
@@ -361,6 +364,20 @@ selective_scan_bwd_kernel(int batch, int dim, int64_t L, int N, int groups, cons
 
 }  // namespace fv
 
+// short sequences (L <= 16, d_state 16): selective_scan_short.cu
+namespace fv {
+int ss_short_fwd_rows(int dim, int64_t L, int dstate, int groups);
+bool ss_short_bwd_ok(int dim, int64_t L, int dstate, int groups);
+template <typename T>
+int launch_ss_short_fwd(int rows, int batch, int dim, int L, int groups, const T* u, const T* delta, const float* A, const T* B,
+                        const T* C, const float* D, const T* z, const float* dbias, int softplus, T* out, float* last,
+                        cudaStream_t st);
+template <typename T>
+int launch_ss_short_bwd(int batch, int dim, int L, int groups, const T* u, const T* delta, const float* A, const T* B, const T* C,
+                        const float* D, const T* z, const float* dbias, int softplus, const T* dout, T* du, T* ddelta,
+                        float* dA, float* dB, float* dC, float* dD, T* dz, float* ddbias, cudaStream_t st);
+}  // namespace fv
+
 extern "C" int fv_selective_scan_fwd(int dtype, int batch, int dim, int64_t L, int dstate, int groups,
                                      const void* u, const void* delta, const float* A, const void* B,
                                      const void* C, const float* D, const void* z,
@@ -372,8 +389,17 @@ extern "C" int fv_selective_scan_fwd(int dtype, int batch, int dim, int64_t L, i
     FV_REQUIRE(dstate >= 1 && dstate <= 32, "fv_selective_scan_fwd: d_state %d not in [1, 32]", dstate);
     FV_REQUIRE(groups >= 1 && dim % groups == 0, "fv_selective_scan_fwd: dim %d not divisible by groups %d", dim, groups);
     FV_REQUIRE(batch <= 65535, "fv_selective_scan_fwd: batch > 65535");
-    dim3 grid(ceil_div(dim, SS_WARPS), batch), block(SS_WARPS * 32);
     cudaStream_t st = (cudaStream_t)stream;
+    if (const int rows = ss_short_fwd_rows(dim, L, dstate, groups)) {   // thread-per-row kernel for the pooled FastVim lengths
+        if (dtype == FV_F32)
+            return launch_ss_short_fwd<float>(rows, batch, dim, (int)L, groups, (const float*)u, (const float*)delta, A, (const float*)B,
+                                              (const float*)C, D, (const float*)z, delta_bias, delta_softplus, (float*)out, last_state, st);
+        if (dtype == FV_BF16)
+            return launch_ss_short_fwd<bf16>(rows, batch, dim, (int)L, groups, (const bf16*)u, (const bf16*)delta, A, (const bf16*)B,
+                                             (const bf16*)C, D, (const bf16*)z, delta_bias, delta_softplus, (bf16*)out, last_state, st);
+        return fail("fv_selective_scan_fwd: unsupported dtype %d", dtype);
+    }
+    dim3 grid(ceil_div(dim, SS_WARPS), batch), block(SS_WARPS * 32);
     if (dtype == FV_F32)
         selective_scan_fwd_kernel<float><<<grid, block, 0, st>>>(batch, dim, L, dstate, groups, (const float*)u, (const float*)delta, A, (const float*)B, (const float*)C, D, (const float*)z, delta_bias, delta_softplus, (float*)out, last_state);
     else if (dtype == FV_BF16)
@@ -406,8 +432,19 @@ extern "C" int fv_selective_scan_bwd(int dtype, int batch, int dim, int64_t L, i
     FV_REQUIRE(need == 0 || (workspace && workspace_bytes >= need), "fv_selective_scan_bwd: workspace of %lld bytes required",
                (long long)need);
     FV_REQUIRE(L % 4 != 0 || (((uintptr_t)dB | (uintptr_t)dC) % 16) == 0, "fv_selective_scan_bwd: dB / dC must be 16-byte aligned");
-    dim3 grid(ceil_div(dim, SS_WARPS), batch), block(SS_WARPS * 32);
     cudaStream_t st = (cudaStream_t)stream;
+    if (ss_short_bwd_ok(dim, L, dstate, groups)) {
+        if (dtype == FV_F32)
+            return launch_ss_short_bwd<float>(batch, dim, (int)L, groups, (const float*)u, (const float*)delta, A, (const float*)B,
+                                              (const float*)C, D, (const float*)z, delta_bias, delta_softplus, (const float*)dout,
+                                              (float*)du, (float*)ddelta, dA, dB, dC, dD, (float*)dz, ddelta_bias, st);
+        if (dtype == FV_BF16)
+            return launch_ss_short_bwd<bf16>(batch, dim, (int)L, groups, (const bf16*)u, (const bf16*)delta, A, (const bf16*)B,
+                                             (const bf16*)C, D, (const bf16*)z, delta_bias, delta_softplus, (const bf16*)dout,
+                                             (bf16*)du, (bf16*)ddelta, dA, dB, dC, dD, (bf16*)dz, ddelta_bias, st);
+        return fail("fv_selective_scan_bwd: unsupported dtype %d", dtype);
+    }
+    dim3 grid(ceil_div(dim, SS_WARPS), batch), block(SS_WARPS * 32);
     if (dtype == FV_F32)
         selective_scan_bwd_kernel<float><<<grid, block, 0, st>>>(batch, dim, L, dstate, groups, (const float*)u, (const float*)delta, A, (const float*)B, (const float*)C, D, (const float*)z, delta_bias, delta_softplus, (const float*)dout, (float*)du, (float*)ddelta, dA, dB, dC, dD, (float*)dz, ddelta_bias, (float*)workspace);
     else if (dtype == FV_BF16)

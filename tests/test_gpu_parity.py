@@ -645,6 +645,11 @@ def test_selective_scan_fn_bwd_vs_reference_golden(name):
     (3, 384, 14, 16, 1, False, False, True, True),    # FastVim-T pooled scan
     (2, 96, 128, 16, 1, True, True, False, False),    # 2048^2 pooled length, exactly one chunk
     (1, 12, 129, 4, 3, True, False, True, True),      # one element into the second chunk
+    # short-sequence kernels (selective_scan_short.cu: L <= 16, d_state 16)
+    (2, 256, 16, 16, 2, True, True, True, True),      # two groups of 128 channels, z gate
+    (2, 96, 9, 16, 3, True, True, False, False),      # groups of 32 channels (32-row forward CTAs), no softplus
+    (1, 40, 7, 16, 1, False, True, True, True),       # ragged channel count (partial CTAs), odd L
+    (4, 1536, 14, 16, 1, True, False, True, True),    # FastVim-B pooled scan with z
 ])
 def test_selective_scan_fn_bwd_vs_oracle(dtype, Bt, Dm, L, N, G, has_z, has_D, has_bias, softplus):
     """du, ddelta, dA, dB, dC, dD, dz, ddelta_bias against fp64 autograd through the oracle on the same (rounded) inputs."""
