@@ -33,7 +33,43 @@ SOURCES = ["selective_scan.cpp", "selective_scan_fwd_fp32.cu", "selective_scan_f
            "selective_scan_bwd_bf16_complex.cu"]
 
 
+PYREF = os.path.join(OUT, "pyref")
+REF_ROOT = os.environ.get("FASTVIM_REFERENCE_ROOT", "/root/reference")
+
+
+def stage_python_reference() -> int:
+    """Stages the reference's own PYTHON packages (``mamba-1p1p1/mamba_ssm`` and ``models``, .py files only, unmodified)
+    into the git-ignored ``oracle/_ref/pyref/`` so that they exist on the GPU box, where /root/reference does not:
+      * ``bench.py --impl reference`` / ``cpu_baseline`` then time the REFERENCE'S OWN CPU path (``selective_scan_ref`` /
+        ``mamba_inner_ref`` through its ``VisionMamba``) instead of the oracle port (kind "reference");
+      * ``tests/test_gpu_reference_model_over_shims.py`` drives the reference's own ``models/fastvim.py`` forward over the
+        ``fastvim_b200/compat`` import shims on the GPU.
+    Like the compiled ``selective_scan_cuda.so`` next to it this is a build artefact of the checker: never committed
+    (``oracle/_ref/`` is git-ignored), never imported by the product package."""
+    import shutil
+
+    n = 0
+    for sub in (os.path.join("mamba-1p1p1", "mamba_ssm"), "models"):
+        src_root = os.path.join(REF_ROOT, sub)
+        if not os.path.isdir(src_root):
+            continue
+        for dirpath, _dirs, files in os.walk(src_root):
+            for f in files:
+                if not f.endswith(".py"):
+                    continue
+                rel = os.path.relpath(os.path.join(dirpath, f), REF_ROOT)
+                dst = os.path.join(PYREF, rel)
+                os.makedirs(os.path.dirname(dst), exist_ok=True)
+                if not os.path.exists(dst) or os.path.getmtime(dst) < os.path.getmtime(os.path.join(dirpath, f)):
+                    shutil.copyfile(os.path.join(dirpath, f), dst)
+                n += 1
+    print(f"[build_ref] staged {n} reference .py files under {PYREF}")
+    return 0
+
+
 def main(jobs: int) -> int:
+    if os.path.isdir(os.path.join(REF_ROOT, "models")):
+        stage_python_reference()
     if not os.path.isdir(SRC):
         print(f"[build_ref] {SRC} not present (GPU box or stripped container): nothing to do")
         return 0

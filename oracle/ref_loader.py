@@ -32,7 +32,10 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-REFERENCE_ROOT = os.environ.get("FASTVIM_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STAGED = os.path.join(_HERE, "_ref", "pyref")     # oracle/build_ref.py stages the reference's .py files here (git-ignored)
+REFERENCE_ROOT = os.environ.get("FASTVIM_REFERENCE_ROOT") or (
+    "/root/reference" if os.path.isdir("/root/reference/mamba-1p1p1/mamba_ssm") else _STAGED)
 
 
 def reference_available() -> bool:
@@ -175,10 +178,14 @@ def load_reference():
     ln.layer_norm_fn = _layer_norm_fn
     import models.fastvim as fastvim  # noqa: E402
 
-    import mamba_ssm.modules.mamba_simple_channel_faster as mscf  # noqa: E402  (FastChannelVim mixer)
+    mscf = msmf = msmf2 = None
+    try:
+        import mamba_ssm.modules.mamba_simple_channel_faster as mscf  # noqa: E402  (FastChannelVim mixer)
 
-    import mamba_ssm.modules.mamba_simple_masked_faster as msmf  # noqa: E402  (FastMaskVim encoder mixer)
-    import mamba_ssm.modules.mamba_simple_masked_faster_v2 as msmf2  # noqa: E402
+        import mamba_ssm.modules.mamba_simple_masked_faster as msmf  # noqa: E402  (FastMaskVim encoder mixer)
+        import mamba_ssm.modules.mamba_simple_masked_faster_v2 as msmf2  # noqa: E402
+    except ImportError:     # only the FastVim classifier is needed by bench.py's reference arm
+        pass
 
     ns = types.SimpleNamespace(ssi=ssi, msf=msf, mscf=mscf, msmf=msmf, msmf2=msmf2, ln=ln, fastvim=fastvim)
     _loaded = ns

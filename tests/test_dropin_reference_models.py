@@ -88,15 +88,16 @@ def test_reference_channel_models_build_on_the_b200_mixers(shimmed):
 def test_reference_mae_encoder_blocks_build_on_the_b200_masked_mixer(shimmed):
     from fastvim_b200 import mixer_masked, vision_masked
 
-    # the MAE file also imports the plain-Vim mixer for its DECODER (mamba_ssm.modules.mamba_simple: the reference's
-    # baseline architecture, outside the FastVim hot path and not shimmed); a placeholder satisfies the import here.
-    import types
+    # the MAE file imports the plain-Vim mixer for its DECODER (mamba_ssm.modules.mamba_simple.Mamba): shimmed by
+    # fastvim_b200.mixer_plain since round 2, so the reference's MAE model imports and constructs unchanged
+    from fastvim_b200 import mixer_plain
 
-    stub = types.ModuleType("mamba_ssm.modules.mamba_simple")
-    stub.Mamba = type("Mamba", (torch.nn.Module,), {})
-    sys.modules["mamba_ssm.modules.mamba_simple"] = stub
     mm = importlib.import_module("models.mae.models_mamba_faster_mae_vimdecoder_v2")
-    assert mm.__file__.startswith(REF) and mm.Mamba_masked is mixer_masked.Mamba_masked
+    assert mm.__file__.startswith(REF) and mm.Mamba_masked is mixer_masked.Mamba_masked and mm.Mamba is mixer_plain.Mamba
+    mae = mm.MaskedAutoencoderViM(img_size=64, patch_size=16, embed_dim=32, depth=2, decoder_embed_dim=32, decoder_depth=1,
+                                  rms_norm=True, residual_in_fp32=True, fused_add_norm=True)
+    assert all(isinstance(b.mixer, mixer_plain.Mamba) for b in mae.decoder_blocks)
+    assert all(isinstance(b.mixer, mixer_masked.Mamba_masked) for b in mae.layers)
     ref_blk = mm.create_block_masked(32, rms_norm=True, residual_in_fp32=True, fused_add_norm=True, layer_idx=1,
                                      token_size=(4, 6))
     assert isinstance(ref_blk.mixer, mixer_masked.Mamba_masked) and ref_blk.mixer.num_of_rows == 6

@@ -258,3 +258,41 @@ def test_uint8_images_with_folded_normalisation_vs_oracle():
             got16 = m(u8.cuda())                   # folded into the bf16 patch-embedding GEMM
     assert_close(got32, want, 1e-4, "uint8 -> fp32 path")
     assert_close(got16, want, 2e-2, "uint8 folded bf16 path")
+
+
+# ------------------------------------------------------------------ plain (un-pooled) Vim mixer: mamba_simple.Mamba shim
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("norm", [True, False])
+def test_plain_vim_mixer_fwd_bwd_vs_oracle(dtype, norm):
+    """``fastvim_b200.mixer_plain.Mamba`` (mirror of the reference's ``mamba_ssm.modules.mamba_simple.Mamba``, the MAE
+    decoder's block) = the pooled mixer with a pooling window of one token: forward and every gradient vs the oracle."""
+    from fastvim_b200.mixer_plain import Mamba
+
+    d_model, L = 64, 50
+    p = O.random_mixer_params(d_model, seed=3)
+    if not norm:
+        p = {k: v for k, v in p.items() if not k.startswith("layernorm")}
+    torch.manual_seed(1)
+    h = torch.randn(2, L, d_model)
+    dout = torch.randn(2, L, d_model)
+    m = Mamba(d_model, use_norm_after_ssm=norm)
+    m.load_state_dict(p, strict=True)
+    m = m.cuda()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        out_inf = m.eval()(h.cuda())
+    pd = {k: v.clone().double().requires_grad_(True) for k, v in p.items()}
+    hd = h.clone().double().requires_grad_(True)
+    want = O.mixer_oracle(hd, pd, (L, 1), use_norm_after_ssm=norm)
+    want.backward(dout.double())
+    tol = TOL[dtype]
+    assert_close(out_inf, want.detach(), tol, "plain mixer, inference kernels")
+    m.train()
+    hc = h.cuda().requires_grad_(True)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=dtype == torch.bfloat16):
+        out = m(hc)
+    out.backward(dout.cuda().to(out.dtype))
+    assert_close(out, want.detach(), tol, "plain mixer, training path")
+    assert_close(hc.grad, hd.grad, tol, "d hidden")
+    got = dict(m.named_parameters())
+    for k, v in pd.items():
+        assert_close(got[k].grad, v.grad, tol if dtype == torch.float32 else 2 * tol, f"d {k}")
