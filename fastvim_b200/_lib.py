@@ -36,7 +36,7 @@ SIGNATURES = {
     "fv_block_pack_xproj_bytes": [_I, _I],
     "fv_block_pack_xproj": [_I, _I, _P, _P, _P],
     "fv_block_fwd": [_G, _I, _P, _P, _L, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _F, _F, _P, _L, _L,
-                     _P, _P, _P, _P, _P],
+                     _P, _P, _P, _P, _P, _P],
     "fv_block_fwd_saves_v": [_G, _I, _I, _I],
     "fv_gate_bwd_v_supported": [_G, _I],
     "fv_gate_bwd_v": [_G, _I, _P, _P, _L, _L, _P, _L, _L, _P, _P, _F, _P, _P, _P, _P, _P, _P],

@@ -20,41 +20,71 @@ from . import ops
 GATE_BWD_V = os.environ.get("FASTVIM_GATE_BWD_V", "1") != "0"
 
 
+def _mm_f32(a, b):
+    """a @ b for bf16 / fp32 operands with an fp32 RESULT (tensor-core GEMM, fp32 accumulator written out unrounded):
+    weight gradients go straight into fp32 master-gradient buffers, no bf16 rounding and no cast pass."""
+    if a.dtype == torch.float32:
+        return a @ b
+    try:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    except (TypeError, RuntimeError):   # older torch / CPU stand-in runs
+        return (a @ b).float()
+
+
+def _bmm_f32(a, b):
+    if a.dtype == torch.float32:
+        return torch.bmm(a, b)
+    try:
+        return torch.bmm(a, b, out_dtype=torch.float32)
+    except (TypeError, RuntimeError):
+        return torch.bmm(a, b).float()
+
+
 class MixerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, in_w, in_b, conv_w, conv_b, x_w, dt_w, dt_b, A_log, Dk, ln_w, ln_b, out_w, out_b,
                 geom, scale, eps, d_state, dt_rank):
-        """h (B, L, dm) act dtype; in_w (2D, dm), out_w (dm, D), x_w (2, R+2N, D) act dtype;
+        """h (B, L, dm) act dtype; in_w (2D, dm), out_w (dm, D), x_w (2, R+2N, D): MASTER weights (fp32 under autocast) --
+        they are cast to the activation dtype here, outside autograd, and their gradients are returned in their own dtype;
         conv_w (2, D, 4), conv_b (2, D) | None, dt_w (2, D, R), dt_b (2, D), A_log (2, D, N), Dk (2, D),
         ln_w / ln_b (D) | None: fp32."""
         B, L, _ = h.shape
         D = conv_w.shape[1]
         from . import mixer as _mixer
 
+        act = h.dtype
+        w_dtypes = (in_w.dtype, out_w.dtype, x_w.dtype, None if in_b is None else in_b.dtype,
+                    None if out_b is None else out_b.dtype)
+        in_w, out_w, x_w = in_w.to(act), out_w.to(act), x_w.to(act).contiguous()
+        in_b = None if in_b is None else in_b.to(act)
+        out_b = None if out_b is None else out_b.to(act)
         h = h.contiguous()   # saved for the backward's (B*L, dm) views
         xz = _mixer.linear(h, in_w, in_b)
         x, z = xz[..., :D], xz[..., D:]
-        v = None
+        v = pre = None
         if _mixer.FUSED_BLOCK and ops.block_fwd_supported(geom, B, D, xz.dtype, dt_rank, d_state):
             # the cluster kernel also saves the pre-norm value v (instead of the scan planes s) for the streaming gate backward
             want_v = GATE_BWD_V and ops.gate_bwd_v_supported(geom, B, D, xz.dtype)
-            y, u, xdbl, s, v = ops.block_fwd(x, z, geom, conv_w, conv_b, x_w.contiguous(), dt_w.contiguous(),
-                                             dt_b, -torch.exp(A_log), Dk, ln_w, ln_b, eps, scale, dt_rank, d_state,
-                                             a_is_log=False, save=True, save_v=want_v)
+            y, u, xdbl, s, vp = ops.block_fwd(x, z, geom, conv_w, conv_b, x_w, dt_w.contiguous(),
+                                              dt_b, -torch.exp(A_log), Dk, ln_w, ln_b, eps, scale, dt_rank, d_state,
+                                              a_is_log=False, save=True, save_v=want_v)
+            if vp is not None:
+                v, pre = vp
         else:
             u = ops.conv_pool_fwd(x, geom, conv_w, conv_b, scale, "mean")
             xdbl = torch.bmm(u.view(2, B * geom.Lp, D), x_w.transpose(1, 2))
             s = ops.scan_fwd(u, xdbl, geom, dt_rank, d_state, dt_w, dt_b, A_log, a_is_log=True)
             y = ops.gate_fwd(x, z, s, geom, conv_w, conv_b, Dk, ln_w, ln_b, eps)
         out = _mixer.linear(y, out_w, out_b)
-        ctx.save_for_backward(h, in_w, conv_w, conv_b, x_w, dt_w, dt_b, A_log, Dk, ln_w, ln_b, out_w, xz, u, xdbl, s, y, v)
-        ctx.meta = (geom, scale, eps, d_state, dt_rank, in_b is not None, out_b is not None)
+        ctx.save_for_backward(h, in_w, conv_w, conv_b, x_w, dt_w, dt_b, A_log, Dk, ln_w, ln_b, out_w, xz, u, xdbl, s, y, v, pre)
+        ctx.meta = (geom, scale, eps, d_state, dt_rank, in_b is not None, out_b is not None, w_dtypes)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        (h, in_w, conv_w, conv_b, x_w, dt_w, dt_b, A_log, Dk, ln_w, ln_b, out_w, xz, u, xdbl, s, y, v) = ctx.saved_tensors
-        geom, scale, eps, N, R, has_in_b, has_out_b = ctx.meta
+        (h, in_w, conv_w, conv_b, x_w, dt_w, dt_b, A_log, Dk, ln_w, ln_b, out_w, xz, u, xdbl, s, y, v, pre) = ctx.saved_tensors
+        geom, scale, eps, N, R, has_in_b, has_out_b, w_dtypes = ctx.meta
+        in_w_dt, out_w_dt, x_w_dt, in_b_dt, out_b_dt = w_dtypes
         B, L, dm = h.shape
         D = conv_w.shape[1]
         Lp = geom.Lp
@@ -63,8 +93,8 @@ class MixerFn(torch.autograd.Function):
         dout2 = dout.view(B * L, dm)
         # out_proj
         dy = (dout2 @ out_w).view(B, L, D)
-        d_out_w = dout2.t() @ y.view(B * L, D)
-        d_out_b = dout2.sum(0) if has_out_b else None
+        d_out_w = _mm_f32(dout2.t(), y.view(B * L, D)).to(out_w_dt)
+        d_out_b = dout2.sum(0).to(out_b_dt) if has_out_b else None
         # epilogue
         x, z = xz[..., :D], xz[..., D:]
         dxz = torch.empty_like(xz)
@@ -74,13 +104,13 @@ class MixerFn(torch.autograd.Function):
         else:
             e, ds, dDk, dln_w, dln_b = ops.gate_bwd(x, z, dy, s, geom, conv_w, conv_b, Dk, ln_w, ln_b, eps, dxz[..., D:])
         # scan
-        du, ddelta, dbc, dA_log, d_dt_b = ops.scan_bwd(ds, u, xdbl, geom, R, N, dt_w, dt_b, A_log, True)
+        du, ddelta, dbc, dA_log, d_dt_b = ops.scan_bwd(ds, u, xdbl, geom, R, N, dt_w, dt_b, A_log, True, pre=pre)
         ddelta2 = ddelta.view(2, B * Lp, D)
         ddt = torch.bmm(ddelta2, dt_w.to(dt))                                   # (2, B*Lp, R)
-        d_dt_w = torch.bmm(ddelta2.transpose(1, 2), xdbl[..., :R]).float()      # (2, D, R)
+        d_dt_w = _bmm_f32(ddelta2.transpose(1, 2), xdbl[..., :R])               # (2, D, R) fp32
         dxdbl = torch.cat([ddt, dbc], dim=-1)                                   # (2, B*Lp, R+2N)
         u2 = u.view(2, B * Lp, D)
-        d_x_w = torch.bmm(dxdbl.transpose(1, 2), u2)                            # (2, R+2N, D)
+        d_x_w = _bmm_f32(dxdbl.transpose(1, 2), u2).to(x_w_dt)                  # (2, R+2N, D)
         du_total = torch.baddbmm(du.view(2, B * Lp, D), dxdbl, x_w).view(2, B, Lp, D).contiguous()
         # conv + pool (+ D skip)
         if dDk is None:
@@ -91,8 +121,8 @@ class MixerFn(torch.autograd.Function):
         # in_proj
         dxz2 = dxz.view(B * L, 2 * D)
         dh = (dxz2 @ in_w).view(B, L, dm)
-        d_in_w = dxz2.t() @ h.view(B * L, dm)
-        d_in_b = dxz2.sum(0) if has_in_b else None
+        d_in_w = _mm_f32(dxz2.t(), h.view(B * L, dm)).to(in_w_dt)
+        d_in_b = dxz2.sum(0).to(in_b_dt) if has_in_b else None
         return (dh, d_in_w, d_in_b, d_conv_w, d_conv_b, d_x_w, d_dt_w, d_dt_b, dA_log, dDk, dln_w, dln_b, d_out_w,
                 d_out_b, None, None, None, None, None)
 
@@ -108,17 +138,17 @@ def mixer_forward_train(mixer, hidden_states, geom, act_dtype):
     m = mixer
     conv_w = torch.stack([m.conv1d.weight[:, 0], m.conv1d_b.weight[:, 0]]).to(f32)
     conv_b = None if m.conv1d.bias is None else torch.stack([m.conv1d.bias, m.conv1d_b.bias]).to(f32)
-    x_w = torch.stack([m.x_proj.weight, m.x_proj_b.weight]).to(act_dtype)
+    x_w = torch.stack([m.x_proj.weight, m.x_proj_b.weight])     # master dtype: cast inside MixerFn
     dt_w = torch.stack([m.dt_proj.weight, m.dt_proj_b.weight]).to(f32)
     dt_b = torch.stack([m.dt_proj.bias, m.dt_proj_b.bias]).to(f32)
     A_log = torch.stack([m.A_log, m.A_b_log]).to(f32)
     Dk = torch.stack([m.D, m.D_b]).to(f32)
     ln_w = m.layernorm.weight.to(f32) if m.use_norm_after_ssm else None
     ln_b = m.layernorm.bias.to(f32) if m.use_norm_after_ssm else None
-    in_b = None if m.in_proj.bias is None else m.in_proj.bias.to(act_dtype)
-    out_b = None if m.out_proj.bias is None else m.out_proj.bias.to(act_dtype)
-    return MixerFn.apply(hidden_states.to(act_dtype), m.in_proj.weight.to(act_dtype), in_b, conv_w, conv_b, x_w, dt_w,
-                         dt_b, A_log, Dk, ln_w, ln_b, m.out_proj.weight.to(act_dtype), out_b, geom,
+    # in_proj / out_proj / x_proj master weights go in as they are: MixerFn casts them to the activation dtype outside
+    # autograd and hands back gradients in the master dtype (fp32 GEMM results, no bf16 rounding, no cast pass)
+    return MixerFn.apply(hidden_states.to(act_dtype), m.in_proj.weight, m.in_proj.bias, conv_w, conv_b, x_w, dt_w,
+                         dt_b, A_log, Dk, ln_w, ln_b, m.out_proj.weight, m.out_proj.bias, geom,
                          float(m.scaling_factor), m.layernorm.eps if m.use_norm_after_ssm else 1e-5, m.d_state,
                          m.dt_rank)
 

@@ -64,6 +64,7 @@ struct ClusterArgs {
     bf16* xdbl_out;
     float* s_out;
     bf16* v_out;       // (B, L, dim) pre-norm merged value, memory token order (saved for fv_gate_bwd_v), or null
+    float* pre_out;    // (2, B, Lp, dim) dt_proj pre-activation dt_bias + W_dt . dt (saved for fv_scan_bwd_short), or null
     int R, ncols, xld, uld, nnt, C;
     int off_u, off_s, off_xp, off_xd, off_st;
 };
@@ -385,6 +386,7 @@ __global__ void __launch_bounds__(BC_THREADS, 2) block_cluster_kernel(const Clus
                 const bf16 ub = ubuf[(dirrow + j) * a.uld + d];
                 const uint32_t xi = (dirrow + j) * a.xld + R;
                 const float delta = bk_softplus(dpre[s]);
+                if (a.pre_out) a.pre_out[(gplane + j) * D + dg] = dpre[s];
                 const float du = delta * __bfloat162float(ub);
                 float2 y2 = make_float2(0.f, 0.f);
                 const float2 dl2 = make_float2(delta, delta), du2 = make_float2(du, du);
@@ -656,7 +658,7 @@ int launch_block_cluster(const fv_geom* g_, const ClusterPlan& p, const void* x,
                          const float* conv_w, const float* conv_b, const void* xw_slab_packed, const float* dt_w,
                          const float* dt_bias, const float* A, int a_is_log, int dt_rank, int dstate, const float* Dskip,
                          const float* ln_w, const float* ln_b, float eps, float scale, void* y, int64_t ldy, int64_t y_bstride,
-                         void* u_out, void* xdbl_out, float* s_out, void* v_out, cudaStream_t stream) {
+                         void* u_out, void* xdbl_out, float* s_out, void* v_out, float* pre_out, cudaStream_t stream) {
     FV_REQUIRE(ldxz % 8 == 0 && xz_bstride % 8 == 0 && ((uintptr_t)x % 16) == 0 && ((uintptr_t)z % 16) == 0,
                "fv_block_fwd: x / z rows must be 16-byte aligned (ldxz %lld)", (long long)ldxz);
     FV_REQUIRE(ldy % 8 == 0 && y_bstride % 8 == 0 && ((uintptr_t)y % 16) == 0, "fv_block_fwd: y rows must be 16-byte aligned");
@@ -670,7 +672,7 @@ int launch_block_cluster(const fv_geom* g_, const ClusterPlan& p, const void* x,
     a.A = A; a.a_is_log = a_is_log; a.Dskip = Dskip; a.lnw = ln_w; a.lnb = ln_b; a.eps = eps;
     a.scale = scale / (float)g_->pool;
     a.y = (bf16*)y; a.ldy = ldy; a.ybs = y_bstride;
-    a.u_out = (bf16*)u_out; a.xdbl_out = (bf16*)xdbl_out; a.s_out = s_out; a.v_out = (bf16*)v_out;
+    a.u_out = (bf16*)u_out; a.xdbl_out = (bf16*)xdbl_out; a.s_out = s_out; a.v_out = (bf16*)v_out; a.pre_out = pre_out;
     a.R = dt_rank; a.ncols = dt_rank + 2 * dstate; a.xld = p.xld; a.uld = p.uld; a.nnt = p.nnt; a.C = p.C;
     a.off_u = p.off_u; a.off_s = p.off_s; a.off_xp = p.off_xp; a.off_xd = p.off_xd; a.off_st = p.off_st;
 

@@ -560,7 +560,7 @@ int launch_block_cluster(const fv_geom* g_, const ClusterPlan& p, const void* x,
                          const float* conv_w, const float* conv_b, const void* xw_slab_packed, const float* dt_w,
                          const float* dt_bias, const float* A, int a_is_log, int dt_rank, int dstate, const float* Dskip,
                          const float* ln_w, const float* ln_b, float eps, float scale, void* y, int64_t ldy, int64_t y_bstride,
-                         void* u_out, void* xdbl_out, float* s_out, void* v_out, cudaStream_t stream);
+                         void* u_out, void* xdbl_out, float* s_out, void* v_out, float* pre_out, cudaStream_t stream);
 // Which kernel serves a configuration both can run (dim <= 384, i.e. FastVim-T): measured on B200 at batch 256 the
 // one-CTA-per-image kernel is still ahead there (68 vs 76 us), so "auto" gives it the narrow models and the cluster
 // kernel everything wider.  FASTVIM_BLOCK_CLUSTER=1 forces the cluster kernel wherever it applies, =0 disables it
@@ -624,7 +624,7 @@ extern "C" int fv_block_fwd(const fv_geom* g_, int dtype, const void* x, const v
                             const void* xproj_w_packed, const float* dt_w, const float* dt_bias, const float* A, int a_is_log,
                             int dt_rank, int dstate, const float* Dskip, const float* ln_w, const float* ln_b,
                             float eps, float scale, void* y, int64_t ldy, int64_t y_bstride,
-                            void* u_out, void* xdbl_out, float* s_out, void* v_out, void* stream) {
+                            void* u_out, void* xdbl_out, float* s_out, void* v_out, float* pre_out, void* stream) {
     using namespace fv;
     if (int rc = check_geom(g_, "fv_block_fwd")) return rc;
     FV_REQUIRE(x && z && conv_w && xproj_w && dt_w && dt_bias && A && Dskip && y, "fv_block_fwd: null pointer");
@@ -635,9 +635,9 @@ extern "C" int fv_block_fwd(const fv_geom* g_, int dtype, const void* x, const v
             return launch_block_cluster(g_, cp, x, z, ldxz, xz_bstride, conv_w, conv_b,
                                         (const unsigned char*)xproj_w_packed + pack_old_bytes(g_->dim, dt_rank + 2 * dstate), dt_w,
                                         dt_bias, A, a_is_log, dt_rank, dstate, Dskip, ln_w, ln_b, eps, scale, y, ldy, y_bstride,
-                                        u_out, xdbl_out, s_out, v_out, (cudaStream_t)stream);
+                                        u_out, xdbl_out, s_out, v_out, pre_out, (cudaStream_t)stream);
     }
-    FV_REQUIRE(!v_out, "fv_block_fwd: v_out needs the cluster kernel (fv_block_fwd_saves_v() == 1 and packed x_proj weights)");
+    FV_REQUIRE(!v_out && !pre_out, "fv_block_fwd: v_out / pre_out need the cluster kernel (fv_block_fwd_saves_v() == 1 and packed x_proj weights)");
     const BlockPlan p = plan_block(g_, dtype, dt_rank, dstate, ldxz, ldy);
     FV_REQUIRE(p.ok, "fv_block_fwd: unsupported configuration (bf16, plain geometry, d_state 16, and either dim %% 192 == 0 with "
                      "<= 16 pooled rows and packed x_proj weights [cluster kernel], or dim %% 32 == 0, dim <= 384, dt_rank in "

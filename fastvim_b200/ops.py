@@ -179,7 +179,8 @@ def block_fwd(x: Tensor, z: Tensor, geom: Geometry, conv_w: Tensor, conv_b: Opti
     xproj_w (2, R+2N, D) bf16, dt_w (2, D, R) fp32.  With ``save`` also returns the pooled intermediates
     (u (2, B, Lp, D) bf16, xdbl (2, B*Lp, R+2N) bf16, s (2, B, Lp, D) fp32) the backward kernels need.  With ``save_v``
     (implies ``save``) returns (y, u, xdbl, s, v): when the cluster kernel serves the configuration, v (B, L, D) bf16 --
-    the pre-norm merged value, for ``gate_bwd_v`` -- is saved INSTEAD of s (s is None); otherwise v is None."""
+    the pre-norm merged value, for ``gate_bwd_v`` -- and the fp32 dt_proj pre-activation (2, B*Lp, D), for ``scan_bwd``, are
+    saved INSTEAD of s (s is None; the last element is the pair (v, pre)); otherwise the last element is None."""
     want5 = save_v is not None     # the 5-tuple form (training path) whenever the caller names save_v
     save_v = bool(save_v)
     save = save or want5
@@ -193,7 +194,7 @@ def block_fwd(x: Tensor, z: Tensor, geom: Geometry, conv_w: Tensor, conv_b: Opti
         xproj_w_packed = block_pack_xproj(xproj_w)
     y = torch.empty((B, L, D), device=x.device, dtype=x.dtype)
     ncols = dt_rank + 2 * d_state
-    u = xdbl = s = v = None
+    u = xdbl = s = v = pre = None
     g = geom.c_struct(B, D)
     if save:
         u = torch.empty((2, B, geom.Lp, D), device=x.device, dtype=x.dtype)
@@ -201,13 +202,14 @@ def block_fwd(x: Tensor, z: Tensor, geom: Geometry, conv_w: Tensor, conv_b: Opti
         if save_v and _lib.lib().fv_block_fwd_saves_v(C.byref(g), FV_BF16, int(dt_rank), int(d_state)):
             # the streaming gate backward works from the saved pre-norm value; the per-direction scan outputs are not needed
             v = torch.empty((B, L, D), device=x.device, dtype=x.dtype)
+            pre = torch.empty((2, B * geom.Lp, D), device=x.device, dtype=torch.float32)   # dt_proj pre-activation
         else:
             s = torch.empty((2, B, geom.Lp, D), device=x.device, dtype=torch.float32)
     _lib.call("fv_block_fwd", C.byref(g), FV_BF16, _p(x), _p(z), ldx, bs, _p(conv_w), _p(conv_b), _p(xproj_w), _p(xproj_w_packed),
               _p(dt_w), _p(dt_bias), _p(A), int(a_is_log), int(dt_rank), int(d_state), _p(Dskip), _p(ln_w), _p(ln_b), float(eps),
-              float(scale), _p(y), y.stride(1), y.stride(0), _p(u), _p(xdbl), _p(s), _p(v), _stream(x))
+              float(scale), _p(y), y.stride(1), y.stride(0), _p(u), _p(xdbl), _p(s), _p(v), _p(pre), _stream(x))
     if want5:
-        return y, u, xdbl, s, v
+        return y, u, xdbl, s, (None if v is None else (v, pre))
     return (y, u, xdbl, s) if save else y
 
 
@@ -447,7 +449,7 @@ def gate_bwd(x: Tensor, z: Tensor, dy: Tensor, s: Tensor, geom: Geometry, conv_w
 
 
 def scan_bwd(ds: Tensor, u: Tensor, xdbl: Tensor, geom: Geometry, dt_rank: int, d_state: int, dt_w: Tensor,
-             dt_bias: Tensor, A: Tensor, a_is_log: bool = True):
+             dt_bias: Tensor, A: Tensor, a_is_log: bool = True, pre: Optional[Tensor] = None):
     """K2a-bwd -> (du, ddelta (2, B, Lp, D) act dtype, dBC (2, B*Lp, 2N) act dtype, dA (2, D, N), d_dt_bias (2, D))."""
     _check_cuda(ds, u, xdbl)
     _, B, Lp, D = u.shape
@@ -462,7 +464,8 @@ def scan_bwd(ds: Tensor, u: Tensor, xdbl: Tensor, geom: Geometry, dt_rank: int, 
     g = geom.c_struct(B, D)
     if SCAN_BWD_SHORT and _lib.lib().fv_scan_bwd_short_supported(C.byref(g), d_state):
         # dt_proj as a GEMM (fp32, cuBLAS): delta_pre = dt_bias + dt . W_dt^T, (2, B*Lp, D)
-        pre = torch.baddbmm(dt_bias.float()[:, None, :], xdbl[..., :dt_rank].float(), dt_w.float().transpose(1, 2))
+        if pre is None:
+            pre = torch.baddbmm(dt_bias.float()[:, None, :], xdbl[..., :dt_rank].float(), dt_w.float().transpose(1, 2))
         _lib.call("fv_scan_bwd_short", C.byref(g), _dt(u), ds.shape[0], _p(u), _p(xdbl), xdbl.stride(1), dt_rank, d_state,
                   _p(pre), _p(A), int(a_is_log), _p(ds), _p(du), _p(ddelta), _p(planes), _p(dA), _p(dbias), _stream(u))
     else:

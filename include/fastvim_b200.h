@@ -126,8 +126,10 @@ int fv_block_fwd(const fv_geom* g, int dtype, const void* x, const void* z, int6
                  const void* xproj_w_packed, const float* dt_w, const float* dt_bias, const float* A, int a_is_log, int dt_rank,
                  int dstate, const float* Dskip, const float* ln_w, const float* ln_b, float eps,
                  float scale, void* y, int64_t ldy, int64_t y_bstride, void* u_out,
-                 void* xdbl_out, float* s_out, void* v_out, void* stream);
-/* v_out (optional): (B, L, dim) bf16 in memory token order, the pre-norm merged value
+                 void* xdbl_out, float* s_out, void* v_out, float* pre_out, void* stream);
+/* pre_out (optional, with v_out): (2, B, Lp, dim) fp32 dt_proj pre-activation dt_bias + W_dt . dt, the input
+ * fv_scan_bwd_short otherwise needs from a separate fp32 GEMM.
+ * v_out (optional): (B, L, dim) bf16 in memory token order, the pre-norm merged value
  *   v = (s_f[j] + s_b[j] + D_f xc_f + D_b xc_b) / 2   (the reference's (out + out_b.flip) / 2, mamba_simple_faster.py:438)
  * saved for fv_gate_bwd_v.  Only the cluster kernel (dim a multiple of 192, <= 16 pooled rows) writes it:
  * fv_block_fwd_saves_v() == 1; fv_block_fwd fails when v_out is given and the configuration does not qualify. */

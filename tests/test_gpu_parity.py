@@ -415,7 +415,7 @@ def test_block_fwd_fused_vs_four_launch_and_oracle(Bt, rows, cols, Dm, R, rot, n
                   C.c_void_p(dtw.data_ptr()), C.c_void_p(dtb.data_ptr()), C.c_void_p(A_log.data_ptr()), 1, R, N,
                   C.c_void_p(Dk.data_ptr()), None if lw is None else C.c_void_p(lw.data_ptr()),
                   None if lb is None else C.c_void_p(lb.data_ptr()), 1e-5, float(sf), C.c_void_p(y3.data_ptr()),
-                  y3.stride(1), y3.stride(0), None, None, None, None, C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                  y3.stride(1), y3.stride(0), None, None, None, None, None, C.c_void_p(torch.cuda.current_stream().cuda_stream))
         if cluster:   # a different kernel (other summation orders): close, not identical
             assert_close(y, y3, TOL[torch.bfloat16], "cluster kernel vs one-CTA kernel")
         else:         # fragment-order x_proj weights are a pure re-layout: bit-identical result
