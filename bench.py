@@ -710,14 +710,14 @@ def run_train(a, ctx: Ctx, workload: str, main: bool):
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             if exch is not None:
-                exch_desc = exch.attach()      # grads become views of the flat buckets; hooks fire the bucket all-reduces
+                exch_desc = exch.attach()      # flat buckets + hooks that pack and all-reduce them
             else:
                 opt.zero_grad(set_to_none=True)
             g1 = torch.cuda.CUDAGraph()
             _lib.reset_launch_count()
             with torch.cuda.graph(g1):
                 if exch is not None:
-                    exch.begin()               # zero the flat buckets the gradients accumulate into
+                    exch.begin()               # drop the old gradients: autograd assigns, the hooks pack the buckets
                 static_loss = fwd_bwd(model, static_x, static_t)
                 if exch is not None:
                     exch.finish()              # join the side stream (every bucket reduced)
