@@ -44,6 +44,10 @@ SIGNATURES = {
     "fv_selective_scan_fwd": [_I, _I, _I, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P],
     "fv_gemm_bf16_tn": [_L, _I, _I, _P, _L, _P, _L, _P, _P, _L, _P],
     "fv_gemm_supported": [_L, _I, _I],
+    "fv_gemm_out_norm_supported": [_L, _I, _I],
+    "fv_gemm_out_norm": [_L, _I, _I, _P, _L, _P, _L, _P, _L, _P, _P, _F, _P, _L, _P],
+    "fv_gemm_bf16": [_L, _I, _L, _I, _P, _L, _I, _P, _L, _I, _P, _L, _I, _P],
+    "fv_gemm_bf16_splits": [_L, _I, _L],
     "fv_ln_gate_fwd": [_I, _L, _I, _P, _L, _P, _L, _P, _P, _F, _P, _L, _P],
     "fv_peer_header_bytes": [],
     "fv_peer_sum_f32": [_I, _I, _P, _L, _L, _P, _P, _P],
@@ -123,7 +127,7 @@ def call(name: str, *args) -> None:
         rc = getattr(l, name)(*args)
         e1.record()
         tag = name
-        if name in ("fv_gemm_bf16_tn", "fv_gemm_out_norm"):   # several GEMM shapes share one entry point: tag with (M, N, K)
+        if name in ("fv_gemm_bf16_tn", "fv_gemm_out_norm", "fv_gemm_bf16"):   # several GEMM shapes share one entry point: tag with (M, N, K)
             tag = "%s[%dx%dx%d]" % (name, int(args[0]), int(args[1]), int(args[2]))
         _profile.append((tag, e0, e1, int(l.fv_launch_count()) - n0))
     else:

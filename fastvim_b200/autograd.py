@@ -3,8 +3,10 @@
 ``MixerFn`` is the whole SSM mixer between (and including) ``in_proj`` and ``out_proj``; it plays the
 role of the reference's fused autograd functions (``FastVim_MambaInnerFnNoOutProj_withoutZ``,
 ``mamba_ssm/ops/selective_scan_interface.py:452-776``) for the live module branch
-(``mamba_simple_faster.py:269-453``), in token-major layout.  GEMMs are cuBLAS calls through torch
-(as in the reference, ``:698-737``); everything between them runs on ``libfastvim_b200.so``.
+(``mamba_simple_faster.py:269-453``), in token-major layout.  GEMMs fall back to cuBLAS through torch
+(as in the reference, ``:698-737``) only where the tcgen05 GEMM does not apply (fp32 runs, 8-byte row pitches): the dgrad /
+wgrad GEMMs of in_proj / out_proj run on ``fv_gemm_bf16`` (csrc/gemm_tc2.cu), everything between them on the other kernels of
+``libfastvim_b200.so``.
 ``AddNormFn`` is the fused residual-add + norm (``ops/triton/layernorm.py:402-489`` ``LayerNormFn``).
 """
 from __future__ import annotations
@@ -18,6 +20,10 @@ from . import ops
 
 # streaming gate backward from the saved pre-norm value (csrc/gate_bwd_v.cu); "0" = round-1 recomputing kernel
 GATE_BWD_V = os.environ.get("FASTVIM_GATE_BWD_V", "1") != "0"
+# x_proj / dt_proj backward GEMMs (N or K = dt_rank, dt_rank + 2 d_state) on the general tcgen05 GEMM where row pitches
+# allow.  Parity-green, but eight tiny launches per block (one 128-row tile wide, a few k-blocks deep) measured SLOWER than
+# the four cuBLAS bmm calls they replace (FastVim-B step 34.4 vs 33.1 ms), so they are opt-in ("1").
+TC_SMALL_GEMM = os.environ.get("FASTVIM_TC_SMALL_GEMM", "0") == "1"
 
 
 def _mm_f32(a, b):
@@ -38,6 +44,25 @@ def _bmm_f32(a, b):
         return torch.bmm(a, b, out_dtype=torch.float32)
     except (TypeError, RuntimeError):
         return torch.bmm(a, b).float()
+
+
+def _tc():
+    from . import mixer as _mixer
+    return _mixer.TC_GEMM
+
+
+def _dgrad(dy2, w):
+    """dX (M, K') = dY (M, N') @ W (N', K'): tcgen05 GEMM with W read as an MN-major operand (no transpose copy)."""
+    if _tc() and ops.gemm_bf16_ok(dy2, w):
+        return ops.gemm_bf16(dy2, w, b_mn=True)
+    return dy2 @ w
+
+
+def _wgrad(dy2, x2):
+    """dW (N', K') fp32 = dY (M, N').T @ X (M, K'): both operands MN-major, split-K over the tokens, fp32 planes."""
+    if _tc() and ops.gemm_bf16_ok(dy2, x2):
+        return ops.gemm_bf16(dy2, x2, a_mn=True, b_mn=True, out_f32=True)
+    return _mm_f32(dy2.t(), x2)
 
 
 class MixerFn(torch.autograd.Function):
@@ -72,7 +97,7 @@ class MixerFn(torch.autograd.Function):
                 v, pre = vp
         else:
             u = ops.conv_pool_fwd(x, geom, conv_w, conv_b, scale, "mean")
-            xdbl = torch.bmm(u.view(2, B * geom.Lp, D), x_w.transpose(1, 2))
+            xdbl = ops.x_proj(u, x_w, _mixer.TC_GEMM)
             s = ops.scan_fwd(u, xdbl, geom, dt_rank, d_state, dt_w, dt_b, A_log, a_is_log=True)
             y = ops.gate_fwd(x, z, s, geom, conv_w, conv_b, Dk, ln_w, ln_b, eps)
         out = _mixer.linear(y, out_w, out_b)
@@ -92,8 +117,8 @@ class MixerFn(torch.autograd.Function):
         dout = dout.to(dt).contiguous()
         dout2 = dout.view(B * L, dm)
         # out_proj
-        dy = (dout2 @ out_w).view(B, L, D)
-        d_out_w = _mm_f32(dout2.t(), y.view(B * L, D)).to(out_w_dt)
+        dy = _dgrad(dout2, out_w).view(B, L, D)
+        d_out_w = _wgrad(dout2, y.view(B * L, D)).to(out_w_dt)
         d_out_b = dout2.sum(0).to(out_b_dt) if has_out_b else None
         # epilogue
         x, z = xz[..., :D], xz[..., D:]
@@ -106,12 +131,29 @@ class MixerFn(torch.autograd.Function):
         # scan
         du, ddelta, dbc, dA_log, d_dt_b = ops.scan_bwd(ds, u, xdbl, geom, R, N, dt_w, dt_b, A_log, True, pre=pre)
         ddelta2 = ddelta.view(2, B * Lp, D)
-        ddt = torch.bmm(ddelta2, dt_w.to(dt))                                   # (2, B*Lp, R)
-        d_dt_w = _bmm_f32(ddelta2.transpose(1, 2), xdbl[..., :R])               # (2, D, R) fp32
-        dxdbl = torch.cat([ddt, dbc], dim=-1)                                   # (2, B*Lp, R+2N)
         u2 = u.view(2, B * Lp, D)
-        d_x_w = _bmm_f32(dxdbl.transpose(1, 2), u2).to(x_w_dt)                  # (2, R+2N, D)
-        du_total = torch.baddbmm(du.view(2, B * Lp, D), dxdbl, x_w).view(2, B, Lp, D).contiguous()
+        ncols = R + 2 * N
+        dt_w_a = dt_w.to(dt)
+        if (TC_SMALL_GEMM and _tc() and R % 8 == 0 and ops.gemm_bf16_ok(ddelta2[0], u2[0], xdbl[0], x_w[0], dt_w_a[0])):
+            # x_proj / dt_proj backward on the general tcgen05 GEMM (FastVim-S/B: every row pitch is a multiple of 16 bytes)
+            dxdbl = torch.empty((2, B * Lp, ncols), device=u.device, dtype=dt)
+            dxdbl[..., R:] = dbc
+            d_dt_w = torch.empty((2, D, R), device=u.device, dtype=torch.float32)
+            d_x_w = torch.empty((2, ncols, D), device=u.device, dtype=torch.float32)
+            du_total = torch.empty((2, B * Lp, D), device=u.device, dtype=dt)
+            for d in range(2):
+                ops.gemm_bf16(ddelta2[d], dt_w_a[d], b_mn=True, out=dxdbl[d][:, :R])                          # ddt
+                ops.gemm_bf16(ddelta2[d], xdbl[d][:, :R], a_mn=True, b_mn=True, out_f32=True, out=d_dt_w[d])
+                ops.gemm_bf16(dxdbl[d], u2[d], a_mn=True, b_mn=True, out_f32=True, out=d_x_w[d])
+                ops.gemm_bf16(dxdbl[d], x_w[d], b_mn=True, out=du_total[d])
+            d_x_w = d_x_w.to(x_w_dt)
+            du_total = du_total.add_(du.view(2, B * Lp, D)).view(2, B, Lp, D)
+        else:
+            ddt = torch.bmm(ddelta2, dt_w_a)                                        # (2, B*Lp, R)
+            d_dt_w = _bmm_f32(ddelta2.transpose(1, 2), xdbl[..., :R])               # (2, D, R) fp32
+            dxdbl = torch.cat([ddt, dbc], dim=-1)                                   # (2, B*Lp, R+2N)
+            d_x_w = _bmm_f32(dxdbl.transpose(1, 2), u2).to(x_w_dt)                  # (2, R+2N, D)
+            du_total = torch.baddbmm(du.view(2, B * Lp, D), dxdbl, x_w).view(2, B, Lp, D).contiguous()
         # conv + pool (+ D skip)
         if dDk is None:
             d_conv_w, d_conv_b, dDk = ops.conv_pool_bwd(x, e, du_total, geom, conv_w, conv_b, Dk, scale, dxz[..., :D],
@@ -120,8 +162,8 @@ class MixerFn(torch.autograd.Function):
             d_conv_w, d_conv_b = ops.conv_pool_bwd(x, e, du_total, geom, conv_w, conv_b, Dk, scale, dxz[..., :D])
         # in_proj
         dxz2 = dxz.view(B * L, 2 * D)
-        dh = (dxz2 @ in_w).view(B, L, dm)
-        d_in_w = _mm_f32(dxz2.t(), h.view(B * L, dm)).to(in_w_dt)
+        dh = _dgrad(dxz2, in_w).view(B, L, dm)
+        d_in_w = _wgrad(dxz2, h.view(B * L, dm)).to(in_w_dt)
         d_in_b = dxz2.sum(0).to(in_b_dt) if has_in_b else None
         return (dh, d_in_w, d_in_b, d_conv_w, d_conv_b, d_x_w, d_dt_w, d_dt_b, dA_log, dDk, dln_w, dln_b, d_out_w,
                 d_out_b, None, None, None, None, None)

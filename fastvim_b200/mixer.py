@@ -37,6 +37,9 @@ FUSED_BLOCK = os.environ.get("FASTVIM_FUSED_BLOCK", "1") != "0"
 # in_proj / out_proj on the hand-written tcgen05 / TMEM / TMA GEMM (csrc/gemm_tc.cu) when the shape qualifies
 # (bf16, no bias, K % 64 == 0, N % 64 == 0, weight block fits shared memory); cuBLAS through F.linear otherwise.
 TC_GEMM = os.environ.get("FASTVIM_TC_GEMM", "1") != "0"
+# inference: fold the next block's residual add + RMSNorm into this block's out_proj epilogue (fv_gemm_out_norm) when
+# d_model fits one accumulator (FastVim-T); "0" = separate fv_gemm_bf16_tn + fv_add_norm_fwd launches
+FUSED_OUT_NORM = os.environ.get("FASTVIM_FUSED_OUT_NORM", "1") != "0"
 
 
 def linear(x, w, b):
@@ -198,7 +201,27 @@ class Mamba(nn.Module):
             out = out * self.gamma
         return out
 
-    def _forward_inference(self, h, geom, act_dtype):
+    def out_norm_fusable(self, h, act_dtype) -> bool:
+        """Can this mixer's out_proj carry the next residual add + RMSNorm in its epilogue (``fv_gemm_out_norm``)?"""
+        return (FUSED_OUT_NORM and TC_GEMM and act_dtype == torch.bfloat16 and h.is_cuda and self.out_proj.bias is None
+                and self.init_layer_scale is None and not self.training
+                and ops.gemm_out_norm_supported(h.numel() // h.shape[-1], self.d_model, self.d_inner))
+
+    def forward_out_norm(self, hidden_states, rotated, residual, norm_w, eps, want_residual=True):
+        """Inference only: ``(rmsnorm(residual + mixer(h)) * norm_w, residual + mixer(h))`` with the add + norm folded into the
+        out_proj GEMM epilogue.  The caller checks ``out_norm_fusable`` first."""
+        geom = self.geometry(rotated)
+        act_dtype = torch.bfloat16
+        return self._forward_inference(hidden_states.to(act_dtype), geom, act_dtype,
+                                       out_norm=(residual, norm_w, eps, want_residual))
+
+    def _linear_out(self, y, pk, out_norm):
+        if out_norm is None:
+            return linear(y, pk["out_w"], pk["out_b"])
+        residual, norm_w, eps, want_residual = out_norm
+        return ops.gemm_out_norm(y, pk["out_w"], residual, norm_w, eps, want_residual)
+
+    def _forward_inference(self, h, geom, act_dtype, out_norm=None):
         pk = self._packed(act_dtype)
         B, L, _ = h.shape
         D, R, N = self.d_inner, self.dt_rank, self.d_state
@@ -211,11 +234,11 @@ class Mamba(nn.Module):
             y = ops.block_fwd(x, z, geom, pk["conv_w"], pk["conv_b"], pk["x_w"], pk["dt_w"], pk["dt_b"],
                               pk["A_neg"], pk["D"], pk["ln_w"], pk["ln_b"], eps, float(self.scaling_factor), R, N,
                               a_is_log=False, xproj_w_packed=pk.get("x_w_packed"))
-            return linear(y, pk["out_w"], pk["out_b"])                   # [a10]
+            return self._linear_out(y, pk, out_norm)                     # [a10] (+ [a11] of the next block when fused)
         u = ops.conv_pool_fwd(x, geom, pk["conv_w"], pk["conv_b"], float(self.scaling_factor),
                               self.collapse_method)                      # (2, B, Lp, D)         [a3-a5]
-        xdbl = torch.bmm(u.view(2, B * geom.Lp, D), pk["x_w_t"])         # (2, B*Lp, R+2N)        [a6]
+        xdbl = ops.x_proj(u, pk["x_w"], TC_GEMM)                         # (2, B*Lp, R+2N)        [a6]
         s = ops.scan_fwd(u, xdbl, geom, R, N, pk["dt_w"], pk["dt_b"], pk["A_log"], a_is_log=True)  # [a6-a7]
         y = ops.gate_fwd(x, z, s, geom, pk["conv_w"], pk["conv_b"], pk["D"], pk["ln_w"], pk["ln_b"],
                          self.layernorm.eps if self.use_norm_after_ssm else 1e-5)             # [a8-a9]
-        return linear(y, pk["out_w"], pk["out_b"])                       # [a10]
+        return self._linear_out(y, pk, out_norm)                         # [a10]

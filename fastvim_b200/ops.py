@@ -297,6 +297,98 @@ def gemm_bf16_tn(a: Tensor, w: Tensor, out: Optional[Tensor] = None, bias: Optio
     return c.reshape(*a.shape[:-1], N)
 
 
+def gemm_bf16(a: Tensor, b: Tensor, a_mn: bool = False, b_mn: bool = False, out_f32: bool = False,
+              out: Optional[Tensor] = None, splits: Optional[int] = None) -> Tensor:
+    """C (Mo, No) = op(a) @ op(b).T on the tcgen05 tensor cores (csrc/gemm_tc2.cu), bf16 operands, fp32 accumulate.
+
+    ``a_mn=False``: a is (Mo, K); ``a_mn=True``: a is (K, Mo) and is used transposed WITHOUT a copy (MN-major UMMA
+    operand).  ``b`` likewise with No.  ``out_f32``: fp32 result (split-K over the reduction when the output has few
+    tiles: the partial planes are added by ``fv_reduce_planes``), else bf16.
+        dgrad  dX = dY @ W        -> gemm_bf16(dY, W, b_mn=True)
+        wgrad  dW = dY.T @ X      -> gemm_bf16(dY, X, a_mn=True, b_mn=True, out_f32=True)
+    """
+    _check_cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.dim() == 2 and b.dim() == 2
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    K, Mo = (a.shape[0], a.shape[1]) if a_mn else (a.shape[1], a.shape[0])
+    Kb, No = (b.shape[0], b.shape[1]) if b_mn else (b.shape[1], b.shape[0])
+    assert K == Kb, f"reduction lengths differ: {K} vs {Kb}"
+    l = _lib.lib()
+    if not out_f32:
+        c = out if out is not None else torch.empty((Mo, No), device=a.device, dtype=torch.bfloat16)
+        assert c.dtype == torch.bfloat16 and c.stride(1) == 1
+        _lib.call("fv_gemm_bf16", Mo, No, K, int(a_mn), _p(a), a.stride(0), int(b_mn), _p(b), b.stride(0), FV_BF16, _p(c),
+                  c.stride(0), 1, _stream(a))
+        return c
+    if splits is None:
+        splits = int(l.fv_gemm_bf16_splits(Mo, No, K))
+    c = out if out is not None else torch.empty((Mo, No), device=a.device, dtype=torch.float32)
+    assert c.dtype == torch.float32 and c.is_contiguous()
+    if splits == 1:
+        _lib.call("fv_gemm_bf16", Mo, No, K, int(a_mn), _p(a), a.stride(0), int(b_mn), _p(b), b.stride(0), FV_F32, _p(c), No, 1,
+                  _stream(a))
+        return c
+    ws = torch.empty((splits, Mo, No), device=a.device, dtype=torch.float32)
+    _lib.call("fv_gemm_bf16", Mo, No, K, int(a_mn), _p(a), a.stride(0), int(b_mn), _p(b), b.stride(0), FV_F32, _p(ws), No,
+              splits, _stream(a))
+    _lib.call("fv_reduce_planes", FV_F32, _p(ws), splits, Mo * No, _p(c), _stream(a))
+    return c
+
+
+def gemm_bf16_ok(*ts: Tensor) -> bool:
+    """Operands the general tcgen05 GEMM accepts: CUDA bf16 2-D, unit inner stride, 16-byte aligned rows."""
+    for t in ts:
+        if not (t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 8 == 0
+                and t.data_ptr() % 16 == 0):
+            return False
+    return True
+
+
+def gemm_out_norm_supported(M: int, N: int, K: int) -> bool:
+    return bool(_lib.lib().fv_gemm_out_norm_supported(int(M), int(N), int(K)))
+
+
+def gemm_out_norm(a: Tensor, w: Tensor, residual: Tensor, norm_w: Tensor, eps: float, want_residual: bool = True,
+                  inplace: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
+    """out_proj + residual add + RMSNorm in one launch (``fv_gemm_out_norm``): a (..., K) bf16, w (N, K) bf16,
+    residual (..., N) fp32 -> (y (..., N) bf16 = rmsnorm(residual + a @ w.T) * norm_w, new residual fp32 | None)."""
+    _check_cuda(a, w, residual)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and residual.dtype == torch.float32
+    K, N = a.shape[-1], w.shape[0]
+    a2 = a.reshape(-1, K)
+    if a2.stride(1) != 1:
+        a2 = a2.contiguous()
+    M = a2.shape[0]
+    r2 = residual.reshape(M, N)
+    assert r2.is_contiguous() and w.stride(1) == 1
+    y = torch.empty((M, N), device=a.device, dtype=torch.bfloat16)
+    res_out = None
+    if want_residual:
+        res_out = r2 if inplace else torch.empty((M, N), device=a.device, dtype=torch.float32)
+    nw = _f32c(norm_w)
+    _lib.call("fv_gemm_out_norm", M, N, K, _p(a2), a2.stride(0), _p(w), w.stride(0), _p(r2), r2.stride(0), _p(res_out),
+              _p(nw), float(eps), _p(y), y.stride(0), _stream(a))
+    shp = tuple(a.shape[:-1]) + (N,)
+    return y.view(shp), (None if res_out is None else res_out.view(shp))
+
+
+def x_proj(u: Tensor, x_w: Tensor, use_tc: bool = True) -> Tensor:
+    """[dt | B | C] = u W_x^T per direction (``mamba_simple_faster.py:321-323, 377-379``).
+    u (2, B, Lp, D), x_w (2, R+2N, D) -> xdbl (2, B*Lp, R+2N).  bf16 on the GPU: two launches of the general tcgen05 GEMM
+    (ragged N = 44 / 56 / 80) writing into a buffer whose row pitch is rounded up to 16 bytes (the result is a view of it;
+    the scan kernels take the pitch).  Otherwise ``torch.bmm``."""
+    _, B, Lp, D = u.shape
+    M, ncols = B * Lp, x_w.shape[1]
+    if use_tc and u.is_cuda and u.dtype == torch.bfloat16 and x_w.dtype == torch.bfloat16 and D % 8 == 0 \
+            and u.is_contiguous() and x_w.is_contiguous():
+        ld = (ncols + 7) // 8 * 8
+        buf = torch.empty((2, M, ld), device=u.device, dtype=u.dtype)
+        for d in range(2):
+            gemm_bf16(u[d].view(M, D), x_w[d], out=buf[d][:, :ncols])
+        return buf[..., :ncols]
+    return torch.bmm(u.reshape(2, M, D), x_w.transpose(1, 2))
+
+
 _PATCH_DT = {torch.float32: 0, torch.bfloat16: 1, torch.uint8: 2}
 
 

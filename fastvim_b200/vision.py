@@ -306,6 +306,8 @@ class VisionMamba(nn.Module):
             x = self.pos_drop(x)
         outs = []
         residual, hidden_states = None, x
+        if out_indices is None and inference_params is None and self._out_norm_fusable(x):
+            return self._pool(self._forward_blocks_fused_norm(x))
         for layer_idx, layer in enumerate(self.layers):
             hidden_states, residual = layer(hidden_states, residual, inference_params=inference_params)
             if out_indices is not None and layer_idx in out_indices:
@@ -316,6 +318,9 @@ class VisionMamba(nn.Module):
         hidden_states = layer_norm_fn(hidden_states, self.norm_f.weight, self.norm_f.bias, eps=self.norm_f.eps,
                                       residual=residual, prenorm=False,
                                       residual_in_fp32=self.residual_in_fp32, is_rms_norm=is_rms)
+        return self._pool(hidden_states)
+
+    def _pool(self, hidden_states):
         if self.final_pool_type == "none":
             return hidden_states[:, -1, :]
         if self.final_pool_type == "mean":
@@ -323,6 +328,34 @@ class VisionMamba(nn.Module):
         if self.final_pool_type in ("max", "all"):
             return hidden_states
         raise NotImplementedError
+
+    def _out_norm_fusable(self, x) -> bool:
+        """Inference with bf16 activations, RMSNorm, fp32 residual stream and a d_model that fits one tcgen05 accumulator
+        (FastVim-T): every residual add + norm after the first rides in the previous block's out_proj epilogue."""
+        if torch.is_grad_enabled() or self.training or not x.is_cuda:
+            return False
+        act = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+        if act != torch.bfloat16 or not self.residual_in_fp32 or not isinstance(self.norm_f, RMSNorm):
+            return False
+        for layer in self.layers:
+            if not isinstance(layer.norm, RMSNorm) or layer.norm.bias is not None \
+                    or not hasattr(layer.mixer, "out_norm_fusable") or not layer.mixer.out_norm_fusable(x, act):
+                return False
+        return self.norm_f.bias is None
+
+    def _forward_blocks_fused_norm(self, x):
+        """The block stack with add + RMSNorm folded into the preceding out_proj (``fv_gemm_out_norm``): same arithmetic as
+        the loop of ``forward_features`` (reference models/fastvim.py:497-527), 24 launches fewer."""
+        first = self.layers[0]
+        hidden, residual = layer_norm_fn(x, first.norm.weight, None, residual=None, prenorm=True,
+                                         residual_in_fp32=True, eps=first.norm.eps, is_rms_norm=True)
+        n = len(self.layers)
+        for i, layer in enumerate(self.layers):
+            nxt = self.layers[i + 1].norm if i + 1 < n else self.norm_f
+            rotated = layer.rotate_every_block is True and layer.layer_idx % 2 != 0
+            hidden, residual = layer.mixer.forward_out_norm(hidden, rotated, residual, nxt.weight, nxt.eps,
+                                                            want_residual=i + 1 < n)
+        return hidden
 
     def forward(self, x, return_features=False, inference_params=None):
         x = self.forward_features(x, inference_params)

@@ -199,6 +199,30 @@ int fv_peer_error(const void* local_buf);
 int fv_gemm_supported(int64_t M, int N, int K);
 int fv_gemm_bf16_tn(int64_t M, int N, int K, const void* A, int64_t lda, const void* W, int64_t ldw,
                     const float* bias /* (N) fp32 or NULL */, void* C, int64_t ldc, void* stream);
+/* out_proj with the NEXT block's residual add + RMSNorm folded into its epilogue (one launch instead of fv_gemm_bf16_tn +
+ * fv_add_norm_fwd; the GEMM result never goes to HBM): C = A . W^T stays in tensor memory, res_new = res_in + C is written
+ * to res_out (fp32, may alias res_in, may be NULL for the model's final norm) and parked back in tensor memory, then
+ * Y = res_new * rsqrt(mean(res_new^2) + eps) * norm_w (bf16).  Reference: F.linear (mamba_simple_faster.py:442-444) followed
+ * by layer_norm_fn(..., residual, prenorm=True, is_rms_norm=True) (models/fastvim.py:175-190; ops/triton/layernorm.py:66-121).
+ * N in {64, 128, 192, 256} (the whole row sits in one accumulator; FastVim-T: d_model = 192), K % 64 == 0. */
+int fv_gemm_out_norm_supported(int64_t M, int N, int K);
+int fv_gemm_out_norm(int64_t M, int N, int K, const void* A, int64_t lda, const void* W, int64_t ldw,
+                     const float* res_in, int64_t ldr, float* res_out, const float* norm_w, float eps, void* Y,
+                     int64_t ldy, void* stream);
+/* General form for the backward GEMMs and ragged shapes (csrc/gemm_tc2.cu): C (Mo x No) = op(A) . op(B)^T over a
+ * reduction of length K, bf16 operands, fp32 accumulation in tensor memory.
+ *   a_mn = 0: A stored (Mo x K) row-major;  a_mn = 1: A stored (K x Mo) row-major (used transposed, not copied)
+ *   b_mn = 0: B stored (No x K) row-major;  b_mn = 1: B stored (K x No) row-major
+ *   out_dtype FV_BF16: C (Mo x No) bf16, splits = 1;  FV_F32: C = `splits` fp32 planes of (Mo x ldc), plane s holding
+ *   the partial sum over its own K range (add them with fv_reduce_planes; splits = 1 writes the result itself).
+ * Replaces the cuBLAS calls of the reference's backward (selective_scan_interface.py:698-737 and autograd through
+ * in_proj / out_proj): dgrad dX = dY . W (a_mn 0, b_mn 1), wgrad dW = dY^T . X (a_mn 1, b_mn 1, fp32 planes), and the
+ * x_proj GEMM with N = dt_rank + 2 d_state (mamba_simple_faster.py:321-323).  Sizes need no padding: TMA zero-fills
+ * out-of-range reads and clips writes; row pitches must be multiples of 16 bytes, bases 16-byte aligned.
+ * fv_gemm_bf16_splits() returns the split count that fills the SMs for a shape. */
+int fv_gemm_bf16_splits(int64_t Mo, int No, int64_t K);
+int fv_gemm_bf16(int64_t Mo, int No, int64_t K, int a_mn, const void* A, int64_t lda, int b_mn, const void* B,
+                 int64_t ldb, int out_dtype, void* C, int64_t ldc, int splits, void* stream);
 /* ---- operator API helpers on (batch, dim, L), L contiguous ---------------------------------
  * The reference's fused autograd functions (selective_scan_interface.py:208-330, 452-605) call, on
  * (B, D, L) tensors: causal_conv1d_cuda.causal_conv1d_fwd(x, w, bias, None, True) (:496-498; third-party

@@ -1,0 +1,122 @@
+"""General tcgen05 GEMM (csrc/gemm_tc2.cu: MN-major operands, split-K fp32 planes, ragged shapes) against fp64 matmuls
+of the same bf16 operands -- the backward GEMMs the reference leaves to cuBLAS (selective_scan_interface.py:698-737)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(rows, cols, scale):
+    return (torch.randn(rows, cols) * scale).bfloat16().cuda()
+
+
+CASES = [  # (Mo, No, K, a_mn, b_mn, out_f32)
+    (1000, 768, 1536, False, False, False),    # TN, ragged M
+    (392, 44, 384, False, False, False),       # x_proj: ragged N (bf16 output with a padded row pitch)
+    (1792, 80, 1536, False, False, True),      # x_proj, fp32 out
+    (3000, 768, 3072, False, True, False),     # dgrad in_proj (FastVim-B): dX = dY . W
+    (2000, 384, 192, False, True, False),      # dgrad out_proj (FastVim-T)
+    (768, 192, 6000, True, True, True),        # wgrad in_proj (FastVim-T), split-K, ragged K
+    (3072, 768, 2500, True, True, True),       # wgrad in_proj (FastVim-B)
+    (44, 1536, 1792, True, True, True),        # wgrad x_proj: 44 output rows
+    (1536, 12, 1792, True, True, True),        # wgrad dt_proj: 12 output columns... (No = 12 -> fp32 pitch 48 B)
+    (200, 136, 72, True, False, False),        # A transposed only, everything ragged
+]
+
+
+@pytest.mark.parametrize("Mo,No,K,a_mn,b_mn,out_f32", CASES)
+def test_gemm_general_vs_fp64(Mo, No, K, a_mn, b_mn, out_f32):
+    from fastvim_b200 import ops
+
+    torch.manual_seed(Mo + No + K)
+    A = _mk(Mo, K, 0.5)
+    B = _mk(No, K, K ** -0.5)
+    want = A.double() @ B.double().t()
+    a_in = A.t().contiguous() if a_mn else A
+    b_in = B.t().contiguous() if b_mn else B
+    # 16-byte row pitches: pad the stored matrices where the logical width is not a multiple of 8
+    def pad(t):
+        if t.shape[1] % 8 == 0:
+            return t
+        buf = torch.zeros(t.shape[0], (t.shape[1] + 7) // 8 * 8, dtype=t.dtype, device=t.device)
+        buf[:, :t.shape[1]] = t
+        return buf[:, :t.shape[1]]
+    a_in, b_in = pad(a_in), pad(b_in)
+    out = None
+    if not out_f32 and No % 8:
+        out = torch.full((Mo, (No + 7) // 8 * 8), 7.0, dtype=torch.bfloat16, device="cuda")[:, :No]
+    c = ops.gemm_bf16(a_in, b_in, a_mn=a_mn, b_mn=b_mn, out_f32=out_f32, out=out)
+    assert c.shape == (Mo, No) and c.dtype == (torch.float32 if out_f32 else torch.bfloat16)
+    err = (c.double() - want).abs().max().item() / want.abs().max().item()
+    assert err < (2e-5 if out_f32 else 4e-3), err
+    if out is not None:    # padding columns up to the 16-byte boundary are either untouched or zero (TMA clips in 16-byte units)
+        padc = out._base[:, No:]
+        assert torch.all((padc == 7.0) | (padc == 0.0))
+
+
+def test_gemm_general_split_counts_agree():
+    """Every split count gives the same fp32 result up to summation order."""
+    from fastvim_b200 import ops
+
+    torch.manual_seed(3)
+    dy, x = _mk(4096, 256, 0.5), _mk(4096, 192, 0.1)
+    want = dy.double().t() @ x.double()
+    for splits in (1, 2, 7, 16):
+        c = ops.gemm_bf16(dy, x, a_mn=True, b_mn=True, out_f32=True, splits=splits)
+        err = (c.double() - want).abs().max().item() / want.abs().max().item()
+        assert err < 2e-5, (splits, err)
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 192, 384), (392, 64, 128), (50176, 192, 384), (300, 256, 768), (129, 128, 1536)])
+def test_gemm_out_norm_vs_fp64(M, N, K):
+    """out_proj + residual add + RMSNorm in the GEMM epilogue (fv_gemm_out_norm) against fp64: the new residual is
+    res + A W^T from the fp32 accumulator (never rounded to bf16), y its RMS normalisation (layernorm.py:66-121 semantics)."""
+    from fastvim_b200 import ops
+
+    torch.manual_seed(M + N)
+    a = (torch.randn(M, K) * 0.5).bfloat16().cuda()
+    w = (torch.randn(N, K) * K ** -0.5).bfloat16().cuda()
+    res = torch.randn(M, N).cuda()
+    nw = (1.0 + 0.2 * torch.randn(N)).cuda()
+    eps = 1e-5
+    assert ops.gemm_out_norm_supported(M, N, K) and not ops.gemm_out_norm_supported(M, 384, K)
+    want_res = res.double() + a.double() @ w.double().t()
+    want_y = want_res * torch.rsqrt(want_res.pow(2).mean(-1, keepdim=True) + eps) * nw.double()
+    res_in = res.clone()
+    y, r = ops.gemm_out_norm(a, w, res_in, nw, eps)
+    assert torch.equal(res_in, res)                       # not in place unless asked
+    assert y.dtype == torch.bfloat16 and r.dtype == torch.float32
+    assert (r.double() - want_res).abs().max().item() / want_res.abs().max().item() < 2e-5
+    assert (y.double() - want_y).abs().max().item() / want_y.abs().max().item() < 4e-3
+    # final-norm form (no residual out) and the in-place form give the same numbers
+    y2, r2 = ops.gemm_out_norm(a, w, res_in, nw, eps, want_residual=False)
+    assert r2 is None and torch.equal(y2, y)
+    y3, r3 = ops.gemm_out_norm(a, w, res_in, nw, eps, inplace=True)
+    assert torch.equal(y3, y) and torch.equal(r3, r) and r3.data_ptr() == res_in.data_ptr()
+    # against the two-launch path it replaces: same y up to the bf16 rounding of the GEMM output that path carries
+    c = ops.gemm_bf16_tn(a, w)
+    y_two, r_two, _, _ = ops.add_norm_fwd(c, res, nw, None, eps, True, want_residual=True)
+    assert (y.float() - y_two.float()).abs().max().item() / want_y.abs().max().item() < 1e-2
+    assert (r - r_two).abs().max().item() / want_res.abs().max().item() < 4e-3
+
+
+def test_fastvim_tiny_fused_out_norm_matches_unfused(monkeypatch):
+    """FastVim-T inference: the model with add + RMSNorm folded into the out_proj epilogue against the same model with
+    separate launches (and both against each other's launch counts)."""
+    from fastvim_b200 import _lib, mixer as M
+    from fastvim_b200.vision import fastvim_tiny
+
+    torch.manual_seed(0)
+    model = fastvim_tiny(num_classes=10).cuda().eval()
+    img = torch.randn(2, 3, 224, 224).cuda()
+    outs, launches = {}, {}
+    for fused in (True, False):
+        monkeypatch.setattr(M, "FUSED_OUT_NORM", fused)
+        with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+            model(img)
+            _lib.reset_launch_count()
+            outs[fused] = model(img).float()
+            launches[fused] = _lib.launch_count()
+    assert launches[False] - launches[True] == 24         # one add_norm launch per block folded away
+    err = (outs[True] - outs[False]).abs().max().item() / outs[False].abs().max().item()
+    assert err < 2e-2, err

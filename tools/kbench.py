@@ -143,6 +143,31 @@ def main():
             rep("in_proj(tcgen05)", t, Bt * L * (dm + 2 * D) * s)
             t = timeit(lambda i: ops.gemm_bf16_tn(y[i], w_out), nrot, a.iters)
             rep("out_proj(tcgen05)", t, Bt * L * (dm + D) * s)
+        if dt == torch.bfloat16 and (not only or "bwdgemm" in only or "gemm" in only):
+            # backward GEMMs of in_proj / out_proj: dgrad (bf16 out) and wgrad (fp32 out), cuBLAS vs csrc/gemm_tc2.cu
+            M = Bt * L
+            dxz = [torch.randn(M, 2 * D, device=dev).to(dt) for _ in range(nrot)]
+            dout = [torch.randn(M, dm, device=dev).to(dt) for _ in range(nrot)]
+            h2 = [t.view(M, dm) for t in hs]
+            y2 = [t.reshape(M, D) for t in y]
+            fl = 2.0 * M * dm * 2 * D
+            t = timeit(lambda i: dxz[i] @ w_in, nrot, a.iters); rep("in_proj_dgrad(cublas)", t, M * (dm + 2 * D) * s); print(json.dumps({"tflops": fl / t * 1e-12}))
+            t = timeit(lambda i: ops.gemm_bf16(dxz[i], w_in, b_mn=True), nrot, a.iters); rep("in_proj_dgrad(tcgen05)", t, M * (dm + 2 * D) * s); print(json.dumps({"tflops": fl / t * 1e-12}))
+            t = timeit(lambda i: torch.mm(dxz[i].t(), h2[i], out_dtype=torch.float32), nrot, a.iters); rep("in_proj_wgrad(cublas)", t, M * (dm + 2 * D) * s); print(json.dumps({"tflops": fl / t * 1e-12}))
+            t = timeit(lambda i: ops.gemm_bf16(dxz[i], h2[i], a_mn=True, b_mn=True, out_f32=True), nrot, a.iters); rep("in_proj_wgrad(tcgen05)", t, M * (dm + 2 * D) * s); print(json.dumps({"tflops": fl / t * 1e-12}))
+            fl = 2.0 * M * dm * D
+            t = timeit(lambda i: dout[i] @ w_out, nrot, a.iters); rep("out_proj_dgrad(cublas)", t, M * (dm + D) * s); print(json.dumps({"tflops": fl / t * 1e-12}))
+            t = timeit(lambda i: ops.gemm_bf16(dout[i], w_out, b_mn=True), nrot, a.iters); rep("out_proj_dgrad(tcgen05)", t, M * (dm + D) * s); print(json.dumps({"tflops": fl / t * 1e-12}))
+            t = timeit(lambda i: torch.mm(dout[i].t(), y2[i], out_dtype=torch.float32), nrot, a.iters); rep("out_proj_wgrad(cublas)", t, M * (dm + D) * s); print(json.dumps({"tflops": fl / t * 1e-12}))
+            t = timeit(lambda i: ops.gemm_bf16(dout[i], y2[i], a_mn=True, b_mn=True, out_f32=True), nrot, a.iters); rep("out_proj_wgrad(tcgen05)", t, M * (dm + D) * s); print(json.dumps({"tflops": fl / t * 1e-12}))
+        if dt == torch.bfloat16 and ops.gemm_out_norm_supported(Bt * L, dm, D):
+            # out_proj + residual add + RMSNorm: one launch (epilogue fusion) vs the two launches it replaces
+            yz = [torch.randn(Bt, L, D, device=dev).to(dt) for _ in range(nrot)]
+            nb = Bt * L * (D * s + dm * 10)
+            t = timeit(lambda i: ops.gemm_out_norm(yz[i], w_out, res[i], nw, 1e-5), nrot, a.iters)
+            rep("out_proj+add_norm(fused epilogue)", t, nb)
+            t = timeit(lambda i: ops.add_norm_fwd(ops.gemm_bf16_tn(yz[i], w_out), res[i], nw, None, 1e-5, True), nrot, a.iters)
+            rep("out_proj+add_norm(two launches)", t, nb + 2 * Bt * L * dm * s)
         pe_in = [torch.randn(Bt * L, 768, device=dev).to(dt) for _ in range(nrot)]
         w_pe, b_pe = torch.randn(dm, 768, device=dev).to(dt), torch.randn(dm, device=dev)
         t = timeit(lambda i: torch.nn.functional.linear(pe_in[i], w_pe, b_pe.to(dt)), nrot, a.iters)
