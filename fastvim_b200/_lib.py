@@ -44,6 +44,11 @@ SIGNATURES = {
     "fv_selective_scan_fwd": [_I, _I, _I, _L, _I, _I, _P, _P, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P],
     "fv_gemm_bf16_tn": [_L, _I, _I, _P, _L, _P, _L, _P, _P, _L, _P],
     "fv_gemm_supported": [_L, _I, _I],
+    "fv_set_pdl": [_I],
+    "fv_block_fwd_signal_supported": [_G, _I, _I, _I],
+    "fv_block_fwd_signal": [_G, _I, _P, _P, _L, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _F, _F, _P, _L, _L,
+                            _P, _I, _P],
+    "fv_gemm_out_norm_flow": [_L, _I, _I, _P, _L, _P, _L, _P, _L, _P, _P, _F, _P, _L, _P, _I, _I, _P],
     "fv_gemm_out_norm_supported": [_L, _I, _I],
     "fv_gemm_out_norm": [_L, _I, _I, _P, _L, _P, _L, _P, _L, _P, _P, _F, _P, _L, _P],
     "fv_gemm_bf16": [_L, _I, _L, _I, _P, _L, _I, _P, _L, _I, _P, _L, _I, _P],
@@ -127,7 +132,7 @@ def call(name: str, *args) -> None:
         rc = getattr(l, name)(*args)
         e1.record()
         tag = name
-        if name in ("fv_gemm_bf16_tn", "fv_gemm_out_norm", "fv_gemm_bf16"):   # several GEMM shapes share one entry point: tag with (M, N, K)
+        if name in ("fv_gemm_bf16_tn", "fv_gemm_out_norm", "fv_gemm_out_norm_flow", "fv_gemm_bf16"):   # several GEMM shapes share one entry point: tag with (M, N, K)
             tag = "%s[%dx%dx%d]" % (name, int(args[0]), int(args[1]), int(args[2]))
         _profile.append((tag, e0, e1, int(l.fv_launch_count()) - n0))
     else:

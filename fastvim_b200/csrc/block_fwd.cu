@@ -69,6 +69,8 @@ struct BlockArgs {
     float* s_out;     // (2, B, Lp, dim) or null
     int R, ncols, xld, uld;
     int off_u, off_s, off_xdbl, off_tab;  // byte offsets into dynamic smem (slab at 0)
+    int* done_flags;  // (B) or null: done_flags[img] = done_epoch once every y row of the image is written (release, gpu scope)
+    int done_epoch;   //   -> a dependent kernel launched early (PDL) consumes images as they complete (fv_gemm_out_norm_flow)
 };
 
 template <int POOL_T, bool NORM, bool FULL, int RT>
@@ -99,6 +101,8 @@ __global__ void __launch_bounds__(BK_THREADS, 1) block_fwd_kernel(const BlockArg
         ytab[t] = (uint32_t)(row * a.ldy);
     }
     __syncthreads();
+    pdl_wait();     // the pad rows and row tables above overlapped the in_proj GEMM's tail; x / z are read from here on
+    pdl_trigger();
     int img = blockIdx.x;
     const int cpr = D >> 3;  // 16-byte chunks per token row
     if (img < g.B) {         // first image: every thread fetches its share of the slab
@@ -124,6 +128,10 @@ __global__ void __launch_bounds__(BK_THREADS, 1) block_fwd_kernel(const BlockArg
         const bool has_next = img_next < g.B;
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();  // S0: this image's x rows (issued by all threads) have landed
+        if (a.done_flags && it_img > 0 && tid == 0) {  // every warp has fenced its y rows of the previous image before S0
+            __threadfence();
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.done_flags + (img - (int)gridDim.x)), "r"(a.done_epoch) : "memory");
+        }
 
         // ================= pass 1: conv (both directions) + SiLU + mean pool, w in place ===============
         uint32_t hl0 = 0, hl1 = 0, hl2 = 0;
@@ -483,6 +491,15 @@ __global__ void __launch_bounds__(BK_THREADS, 1) block_fwd_kernel(const BlockArg
 #pragma unroll
                 for (int i = 0; i < BK_NCG; ++i) zc[i] = zn[i];
             }
+            if (a.done_flags) __threadfence();  // this warp's y rows are visible device-wide before the image is published
+        }
+    }
+    if (a.done_flags) {  // last image of this CTA
+        __syncthreads();
+        const int last = img - (int)gridDim.x;
+        if (tid == 0 && last >= 0 && last < g.B) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.done_flags + last), "r"(a.done_epoch) : "memory");
         }
     }
 }
@@ -619,16 +636,60 @@ extern "C" int fv_block_pack_xproj(int dim, int ncols, const void* xproj_w, void
     return 0;
 }
 
+static int block_fwd_impl(const fv_geom* g_, int dtype, const void* x, const void* z, int64_t ldxz,
+                            int64_t xz_bstride, const float* conv_w, const float* conv_b, const void* xproj_w,
+                            const void* xproj_w_packed, const float* dt_w, const float* dt_bias, const float* A, int a_is_log,
+                            int dt_rank, int dstate, const float* Dskip, const float* ln_w, const float* ln_b,
+                            float eps, float scale, void* y, int64_t ldy, int64_t y_bstride,
+                            void* u_out, void* xdbl_out, float* s_out, void* v_out, float* pre_out, int* done_flags,
+                            int done_epoch, void* stream);
+
 extern "C" int fv_block_fwd(const fv_geom* g_, int dtype, const void* x, const void* z, int64_t ldxz,
                             int64_t xz_bstride, const float* conv_w, const float* conv_b, const void* xproj_w,
                             const void* xproj_w_packed, const float* dt_w, const float* dt_bias, const float* A, int a_is_log,
                             int dt_rank, int dstate, const float* Dskip, const float* ln_w, const float* ln_b,
                             float eps, float scale, void* y, int64_t ldy, int64_t y_bstride,
                             void* u_out, void* xdbl_out, float* s_out, void* v_out, float* pre_out, void* stream) {
+    return block_fwd_impl(g_, dtype, x, z, ldxz, xz_bstride, conv_w, conv_b, xproj_w, xproj_w_packed, dt_w, dt_bias, A, a_is_log,
+                          dt_rank, dstate, Dskip, ln_w, ln_b, eps, scale, y, ldy, y_bstride, u_out, xdbl_out, s_out, v_out,
+                          pre_out, nullptr, 0, stream);
+}
+
+// Inference form that also publishes per-image completion: done_flags[img] = done_epoch (release) once the image's y rows
+// are written, so that fv_gemm_out_norm_flow -- launched programmatically dependent, resident on the SMs this kernel has
+// already left -- starts on finished images while the rest are still being computed.  One-CTA-per-image kernel only.
+extern "C" int fv_block_fwd_signal_supported(const fv_geom* g, int dtype, int dt_rank, int dstate) {
+    if (!g || g->batch <= 0 || g->dim <= 0 || g->outer <= 0 || g->pool <= 0) return 0;
+    const int64_t ld = 2 * (int64_t)g->dim;
+    if (fv::cluster_enabled() && fv::prefer_cluster(g, dtype, dt_rank, dstate, ld, g->dim)) return 0;
+    return fv::plan_block(g, dtype, dt_rank, dstate, ld, g->dim).ok;
+}
+
+extern "C" int fv_block_fwd_signal(const fv_geom* g_, int dtype, const void* x, const void* z, int64_t ldxz,
+                                   int64_t xz_bstride, const float* conv_w, const float* conv_b, const void* xproj_w,
+                                   const void* xproj_w_packed, const float* dt_w, const float* dt_bias, const float* A,
+                                   int a_is_log, int dt_rank, int dstate, const float* Dskip, const float* ln_w,
+                                   const float* ln_b, float eps, float scale, void* y, int64_t ldy, int64_t y_bstride,
+                                   int* done_flags, int done_epoch, void* stream) {
+    FV_REQUIRE(done_flags && done_epoch > 0, "fv_block_fwd_signal: done_flags must be given and done_epoch positive");
+    FV_REQUIRE(g_ && fv_block_fwd_signal_supported(g_, dtype, dt_rank, dstate),
+               "fv_block_fwd_signal: configuration is not served by the one-CTA-per-image kernel");
+    return block_fwd_impl(g_, dtype, x, z, ldxz, xz_bstride, conv_w, conv_b, xproj_w, xproj_w_packed, dt_w, dt_bias, A, a_is_log,
+                          dt_rank, dstate, Dskip, ln_w, ln_b, eps, scale, y, ldy, y_bstride, nullptr, nullptr, nullptr, nullptr,
+                          nullptr, done_flags, done_epoch, stream);
+}
+
+static int block_fwd_impl(const fv_geom* g_, int dtype, const void* x, const void* z, int64_t ldxz,
+                            int64_t xz_bstride, const float* conv_w, const float* conv_b, const void* xproj_w,
+                            const void* xproj_w_packed, const float* dt_w, const float* dt_bias, const float* A, int a_is_log,
+                            int dt_rank, int dstate, const float* Dskip, const float* ln_w, const float* ln_b,
+                            float eps, float scale, void* y, int64_t ldy, int64_t y_bstride,
+                            void* u_out, void* xdbl_out, float* s_out, void* v_out, float* pre_out, int* done_flags,
+                            int done_epoch, void* stream) {
     using namespace fv;
     if (int rc = check_geom(g_, "fv_block_fwd")) return rc;
     FV_REQUIRE(x && z && conv_w && xproj_w && dt_w && dt_bias && A && Dskip && y, "fv_block_fwd: null pointer");
-    if (cluster_enabled() && xproj_w_packed) {
+    if (cluster_enabled() && xproj_w_packed && !done_flags) {
         const ClusterPlan cp = plan_cluster(g_, dtype, dt_rank, dstate, ldxz, ldy);
         // the pre-norm value v (saved for the streaming gate backward) only exists in the cluster kernel
         if (cp.ok && (v_out || prefer_cluster(g_, dtype, dt_rank, dstate, ldxz, ldy)))
@@ -656,6 +717,7 @@ extern "C" int fv_block_fwd(const fv_geom* g_, int dtype, const void* x, const v
     a.u_out = (bf16*)u_out; a.xdbl_out = (bf16*)xdbl_out; a.s_out = s_out;
     a.R = dt_rank; a.ncols = dt_rank + 2 * dstate; a.xld = p.xld; a.uld = p.uld;
     a.off_u = p.off_u; a.off_s = p.off_s; a.off_xdbl = p.off_xdbl; a.off_tab = p.off_tab;
+    a.done_flags = done_flags; a.done_epoch = done_epoch;
 
     void (*kern)(const BlockArgs) = nullptr;
     const bool full = g_->dim == 128 * BK_NCG;  // every lane owns exactly BK_NCG channel groups: no predicates
@@ -672,6 +734,7 @@ extern "C" int fv_block_fwd(const fv_geom* g_, int dtype, const void* x, const v
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
     FV_REQUIRE(e == cudaSuccess, "fv_block_fwd: cudaFuncSetAttribute(%zu): %s", p.smem, cudaGetErrorString(e));
     const int grid = g_->batch < sm_count() ? g_->batch : sm_count();
-    kern<<<grid, BK_THREADS, p.smem, (cudaStream_t)stream>>>(a);
+    e = launch_pdl(kern, dim3(grid), dim3(BK_THREADS), p.smem, (cudaStream_t)stream, (const BlockArgs)a);
+    FV_REQUIRE(e == cudaSuccess, "fv_block_fwd: launch: %s", cudaGetErrorString(e));
     return finish_launch("block_fwd");
 }

@@ -271,6 +271,26 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------
+// Kernels of the inference chain (in_proj GEMM -> fv_block_fwd -> out_proj GEMM (+ add + norm) -> ...) are launched with the
+// programmatic-stream-serialization attribute: a kernel's CTAs may become resident and run their prologue (barrier init,
+// TMEM allocation, tables, parameter loads) while the previous kernel drains; pdl_wait() blocks until the previous grid has
+// completed and its memory is visible, and must precede the first read of its output AND the first global write.
+// pdl_trigger() lets the NEXT kernel start launching (it fires once every CTA of this grid has called it or exited).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+bool pdl_enabled();  // core.cu: FASTVIM_PDL != "0"
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+
 // Both conv directions at one token from a 7-row window w[k] = x[t-3+k]:
 //   f: silu(b_f + sum_k w_f[k] x[t-3+k])      b: silu(b_b + sum_k w_b[k] x[t+3-k])
 template <bool FAST>

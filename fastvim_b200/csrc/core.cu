@@ -1,6 +1,7 @@
 // fastvim_b200 -- error reporting, launch accounting, argument checks (host side of the C ABI).
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -44,6 +45,15 @@ int sm_count() {
     return cache[dev];
 }
 
+static int g_pdl = -1;
+bool pdl_enabled() {
+    if (g_pdl < 0) {
+        const char* e = getenv("FASTVIM_PDL");
+        g_pdl = (e && e[0] == '0') ? 0 : 1;
+    }
+    return g_pdl != 0;
+}
+
 int check_geom(const fv_geom* g, const char* who) {
     FV_REQUIRE(g != nullptr, "%s: null geometry", who);
     FV_REQUIRE(g->batch > 0 && g->dim > 0 && g->outer > 0 && g->pool > 0 && g->inner > 0,
@@ -57,6 +67,11 @@ int check_geom(const fv_geom* g, const char* who) {
 }  // namespace fv
 
 extern "C" const char* fv_last_error(void) { return fv::g_err; }
+extern "C" int fv_set_pdl(int on) {
+    const int prev = fv::pdl_enabled() ? 1 : 0;
+    fv::g_pdl = on ? 1 : 0;
+    return prev;
+}
 extern "C" int fv_version(void) { return 100; }
 extern "C" int64_t fv_launch_count(void) { return fv::g_launches; }
 extern "C" void fv_reset_launch_count(void) { fv::g_launches = 0; }

@@ -32,15 +32,47 @@ constexpr uint32_t ON_A_BYTES = ON_BM * ON_BK * 2;  // 16 KB
 constexpr uint32_t ON_T_BYTES = 128 * 128;          // one staged / residual tile: 128 rows x 128 B
 constexpr int ON_RS = 3;                            // residual chunk ring
 constexpr int ON_CS = 2;                            // output staging tiles
+constexpr int ON_TQ = 4;                            // tile queue depth (flow mode)
 
 struct OutNormArgs {
     int M, KB, ntiles, nstage;
     int has_res_out;
     const float* norm_w;
     float eps;
+    // flow mode (gemm_out_norm_kernel<BN, true>): A is being produced by fv_block_fwd_signal WHILE this kernel runs
+    const int* flags;   // flags[i] >= epoch  <=>  rows [i * rows_per_flag, (i + 1) * rows_per_flag) of A are complete
+    int epoch, rows_per_flag;
+    int* tile_ctr;      // device counter, zeroed once per forward; this launch owns values [ctr_base, ctr_base + ntiles + grid)
+    int ctr_base;
 };
 
-template <int BN>
+// Tile order.  Static: tile = blockIdx.x + i * gridDim.x.  Flow: the TMA producer thread draws tiles from a device-wide
+// counter (CTAs that become resident early -- on SMs the producing kernel has already left -- keep drawing) and hands them
+// to the other roles through a small shared-memory queue (mbarrier full / empty pairs).
+struct TileQ {
+    int* slots;
+    uint64_t* full;
+    uint64_t* empty;
+};
+template <bool FLOW>
+struct TileIter {
+    int it = 0, slot = 0;
+    uint32_t ph = 0;
+    __device__ __forceinline__ int next(const OutNormArgs& a, const TileQ& q) {
+        if (!FLOW) {
+            const int t = blockIdx.x + it * gridDim.x;
+            ++it;
+            return t < a.ntiles ? t : -1;
+        }
+        gt_mbar_wait(&q.full[slot], ph);
+        const int t = *reinterpret_cast<volatile int*>(&q.slots[slot]);
+        gt_mbar_arrive(&q.empty[slot]);
+        if (++slot == ON_TQ) { slot = 0; ph ^= 1u; }
+        return t;
+    }
+};
+
+template <int BN, bool FLOW>
 __global__ void __launch_bounds__(ON_THREADS, 1)
 gemm_out_norm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                      const __grid_constant__ CUtensorMap tmRin, const __grid_constant__ CUtensorMap tmRout,
@@ -64,7 +96,11 @@ gemm_out_norm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     uint64_t* acc_empty = acc_full + 2;
     uint64_t* r_full = acc_empty + 2;
     uint64_t* r_empty = r_full + ON_RS;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(r_empty + ON_RS);
+    TileQ tq;
+    tq.full = r_empty + ON_RS;
+    tq.empty = tq.full + ON_TQ;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tq.empty + ON_TQ);
+    tq.slots = reinterpret_cast<int*>(tmem_ptr + 2);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NS; ++i) {
@@ -79,6 +115,10 @@ gemm_out_norm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             mbar_init(&r_full[i], 1);
             mbar_init(&r_empty[i], 128);
         }
+        for (int i = 0; i < ON_TQ; ++i) {
+            mbar_init(&tq.full[i], 1);
+            mbar_init(&tq.empty[i], 130);  // MMA issuer + residual producer + 128 epilogue threads
+        }
         fence_mbar_init();
     }
     if (warp == 1) {
@@ -89,14 +129,45 @@ gemm_out_norm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    // Static mode: the previous grid (the producer of A) must have completed.  Flow mode: no grid-level wait -- every
+    // input other than A was complete before the producer of A started (it waited for ITS predecessor), and A is
+    // consumed image by image behind the per-image flags.
+    if (!FLOW) pdl_wait();
+    pdl_trigger();
 
     if (warp == 0) {
         // ================= TMA producer: A and W k-blocks =================
         if (lane == 0) {
-            int st = 0;
-            uint32_t ph = 0;
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            int st = 0, it = 0, ps = 0;
+            uint32_t ph = 0, pph = 0;
+            for (;;) {
+                int tile;
+                if (FLOW) {
+                    gt_mbar_wait(&tq.empty[ps], pph ^ 1u);
+                    tile = atomicAdd(a.tile_ctr, 1) - a.ctr_base;
+                    if (tile >= a.ntiles) tile = -1;
+                    tq.slots[ps] = tile;
+                    gt_mbar_arrive(&tq.full[ps]);
+                    if (++ps == ON_TQ) { ps = 0; pph ^= 1u; }
+                } else {
+                    tile = blockIdx.x + it * gridDim.x;
+                    ++it;
+                    if (tile >= a.ntiles) tile = -1;
+                }
+                if (tile < 0) break;
                 const int m0 = tile * ON_BM;
+                if (FLOW) {  // the images this tile's rows belong to must be published
+                    const int last_row = min(a.M - 1, m0 + ON_BM - 1);
+                    for (int f = m0 / a.rows_per_flag; f <= last_row / a.rows_per_flag; ++f) {
+                        int v, spins = 0;
+                        for (;;) {
+                            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(a.flags + f) : "memory");
+                            if (v >= a.epoch || ++spins > (1 << 22)) break;  // bounded: a lost flag must not hang the GPU
+                            __nanosleep(100);
+                        }
+                    }
+                    asm volatile("fence.proxy.async;" ::: "memory");  // generic-proxy writes of A -> TMA (async proxy) reads
+                }
                 for (int kb = 0; kb < KB; ++kb) {
                     gt_mbar_wait(&empty[st], ph ^ 1u);
                     unsigned char* stg = sAB + (size_t)st * STAGE;
@@ -114,7 +185,8 @@ gemm_out_norm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
             int st = 0, as = 0;
             uint32_t ph = 0, aph = 0;
             const uint32_t s_u = smem_u32(sAB);
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            TileIter<FLOW> ti;
+            while (ti.next(a, tq) >= 0) {
                 gt_mbar_wait(&acc_empty[as], aph ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
@@ -138,7 +210,8 @@ gemm_out_norm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         if (lane == 0) {
             int rs = 0;
             uint32_t rph = 0;
-            for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+            TileIter<FLOW> ti;
+            for (int tile; (tile = ti.next(a, tq)) >= 0;) {
                 const int m0 = tile * ON_BM;
                 for (int c = 0; c < NCH; ++c) {
                     gt_mbar_wait(&r_empty[rs], rph ^ 1u);
@@ -157,7 +230,8 @@ gemm_out_norm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
         const uint32_t sw = (uint32_t)(trow & 7);
         int as = 0, cs = 0, rs = 0;
         uint32_t aph = 0, rph = 0;
-        for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        TileIter<FLOW> ti;
+        for (int tile; (tile = ti.next(a, tq)) >= 0;) {
             const int m0 = tile * ON_BM;
             gt_mbar_wait(&acc_full[as], aph);
             tc_fence_after();
@@ -258,7 +332,7 @@ gemm_out_norm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 static bool plan_out_norm(int BN, int* ns, size_t* bytes) {
-    const size_t stage = ON_A_BYTES + (size_t)BN * ON_BK * 2, fixed = 32 * 8 + 16 + 1024, cap = 227 * 1024;
+    const size_t stage = ON_A_BYTES + (size_t)BN * ON_BK * 2, fixed = 48 * 8 + 64 + 1024, cap = 227 * 1024;
     for (int n = 4; n >= 2; --n) {
         const size_t tot = (size_t)n * stage + (size_t)(ON_RS + ON_CS) * ON_T_BYTES + fixed;
         if (tot <= cap) {
@@ -269,15 +343,19 @@ static bool plan_out_norm(int BN, int* ns, size_t* bytes) {
     return false;
 }
 
-template <int BN>
+template <int BN, bool FLOW>
 static int launch_out_norm(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUtensorMap& tmRin, const CUtensorMap& tmRout,
-                           const CUtensorMap& tmY, const OutNormArgs& a, size_t smem, cudaStream_t st) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_out_norm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                           const CUtensorMap& tmY, const OutNormArgs& a, int grid, size_t smem, cudaStream_t st) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_out_norm_kernel<BN, FLOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     FV_REQUIRE(e == cudaSuccess, "fv_gemm_out_norm: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
-    const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();
-    gemm_out_norm_kernel<BN><<<grid, ON_THREADS, smem, st>>>(tmA, tmW, tmRin, tmRout, tmY, a);
+    e = launch_pdl(gemm_out_norm_kernel<BN, FLOW>, dim3(grid), dim3(ON_THREADS), smem, st, tmA, tmW, tmRin, tmRout, tmY, a);
+    FV_REQUIRE(e == cudaSuccess, "fv_gemm_out_norm: launch: %s", cudaGetErrorString(e));
     return finish_launch("gemm_out_norm");
 }
+
+static int out_norm_impl(int64_t M, int N, int K, const void* A, int64_t lda, const void* W, int64_t ldw, const float* res_in,
+                         int64_t ldr, float* res_out, const float* norm_w, float eps, void* Y, int64_t ldy, const int* flags,
+                         int epoch, int rows_per_flag, int* tile_ctr, int launch_index, cudaStream_t st);
 
 }  // namespace fv
 
@@ -293,7 +371,28 @@ extern "C" int fv_gemm_out_norm_supported(int64_t M, int N, int K) {
 extern "C" int fv_gemm_out_norm(int64_t M, int N, int K, const void* A, int64_t lda, const void* W, int64_t ldw,
                                 const float* res_in, int64_t ldr, float* res_out, const float* norm_w, float eps, void* Y,
                                 int64_t ldy, void* stream) {
+    return fv::out_norm_impl(M, N, K, A, lda, W, ldw, res_in, ldr, res_out, norm_w, eps, Y, ldy, nullptr, 0, 0, nullptr, 0,
+                             (cudaStream_t)stream);
+}
+
+// Flow form: A (the gated y of fv_block_fwd_signal) is consumed image by image behind `flags` while that kernel is still
+// running -- launch this right after it on the same stream.  sync[0] is the tile counter, sync[1 + i] the flag of image i
+// (rows_per_flag = tokens per image); the caller zeroes `sync` once per forward and numbers the launches that share it
+// launch_index = 0, 1, ... with epoch = launch_index + 1 on both kernels.
+extern "C" int fv_gemm_out_norm_flow(int64_t M, int N, int K, const void* A, int64_t lda, const void* W, int64_t ldw,
+                                     const float* res_in, int64_t ldr, float* res_out, const float* norm_w, float eps, void* Y,
+                                     int64_t ldy, int* sync, int rows_per_flag, int launch_index, void* stream) {
     using namespace fv;
+    FV_REQUIRE(sync && rows_per_flag > 0 && launch_index >= 0 && M % rows_per_flag == 0,
+               "fv_gemm_out_norm_flow: sync buffer / rows_per_flag (%d) / launch_index (%d) invalid", rows_per_flag, launch_index);
+    return out_norm_impl(M, N, K, A, lda, W, ldw, res_in, ldr, res_out, norm_w, eps, Y, ldy, sync + 1, launch_index + 1,
+                         rows_per_flag, sync, launch_index, (cudaStream_t)stream);
+}
+
+namespace fv {
+static int out_norm_impl(int64_t M, int N, int K, const void* A, int64_t lda, const void* W, int64_t ldw, const float* res_in,
+                         int64_t ldr, float* res_out, const float* norm_w, float eps, void* Y, int64_t ldy, const int* flags,
+                         int epoch, int rows_per_flag, int* tile_ctr, int launch_index, cudaStream_t st) {
     FV_REQUIRE(A && W && Y && res_in && norm_w, "fv_gemm_out_norm: null pointer");
     FV_REQUIRE(fv_gemm_out_norm_supported(M, N, K),
                "fv_gemm_out_norm: unsupported shape (%lld x %d x %d): N must be 64 / 128 / 192 / 256, K %% 64 == 0", (long long)M, N, K);
@@ -306,6 +405,9 @@ extern "C" int fv_gemm_out_norm(int64_t M, int N, int K, const void* A, int64_t 
     OutNormArgs a;
     a.M = (int)M; a.KB = K / ON_BK; a.norm_w = norm_w; a.eps = eps; a.has_res_out = res_out ? 1 : 0;
     a.ntiles = (int)((M + ON_BM - 1) / ON_BM);
+    const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();
+    a.flags = flags; a.epoch = epoch; a.rows_per_flag = rows_per_flag; a.tile_ctr = tile_ctr;
+    a.ctr_base = launch_index * (a.ntiles + grid);   // every CTA draws until it gets a value >= ntiles: ntiles + grid draws
     size_t smem = 0;
     FV_REQUIRE(plan_out_norm(N, &a.nstage, &smem), "fv_gemm_out_norm: no shared-memory plan");
     CUtensorMap tmA, tmW, tmRin, tmRout, tmY;
@@ -314,9 +416,12 @@ extern "C" int fv_gemm_out_norm(int64_t M, int N, int K, const void* A, int64_t 
     if (int rc = get_tmap(&tmRin, res_in, 4, N, M, 0, ldr, 32, ON_BM)) return rc;
     if (int rc = get_tmap(&tmRout, res_out ? res_out : res_in, 4, N, M, 0, ldr, 32, ON_BM)) return rc;
     if (int rc = get_tmap(&tmY, Y, 2, N, M, 0, ldy, 64, ON_BM)) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    if (N == 256) return launch_out_norm<256>(tmA, tmW, tmRin, tmRout, tmY, a, smem, st);
-    if (N == 192) return launch_out_norm<192>(tmA, tmW, tmRin, tmRout, tmY, a, smem, st);
-    if (N == 128) return launch_out_norm<128>(tmA, tmW, tmRin, tmRout, tmY, a, smem, st);
-    return launch_out_norm<64>(tmA, tmW, tmRin, tmRout, tmY, a, smem, st);
+#define FV_ON(BN_)                                                                                             \
+    if (N == BN_)                                                                                              \
+        return flags ? launch_out_norm<BN_, true>(tmA, tmW, tmRin, tmRout, tmY, a, grid, smem, st)              \
+                     : launch_out_norm<BN_, false>(tmA, tmW, tmRin, tmRout, tmY, a, grid, smem, st);
+    FV_ON(256) FV_ON(192) FV_ON(128) FV_ON(64)
+#undef FV_ON
+    return fail("fv_gemm_out_norm: internal error");
 }
+}  // namespace fv

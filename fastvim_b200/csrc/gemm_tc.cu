@@ -83,6 +83,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_wait();     // everything above overlapped the previous kernel's tail; A (and C) belong to the stream order from here
+    pdl_trigger();
     const int nblk = a.nblocks;
     // resident mode: this CTA's column block is blockIdx.y and a tile is a row tile; stream mode: tile = (row tile, block)
 #define GT_TILE_M(tile_) (stream ? (tile_) / nblk : (tile_))
@@ -317,7 +319,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmW, const CUt
         if (gx > a.ntiles) gx = a.ntiles;
         grid = dim3((unsigned)gx, (unsigned)nblocks);
     }
-    gemm_tc_kernel<BN><<<grid, GT_THREADS, smem, st>>>(tmA, tmW, tmC, a);
+    e = launch_pdl(gemm_tc_kernel<BN>, grid, dim3(GT_THREADS), smem, st, tmA, tmW, tmC, (const GemmArgs)a);
+    FV_REQUIRE(e == cudaSuccess, "fv_gemm: launch: %s", cudaGetErrorString(e));
     return finish_launch("gemm_tc");
 }
 

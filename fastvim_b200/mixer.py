@@ -40,6 +40,9 @@ TC_GEMM = os.environ.get("FASTVIM_TC_GEMM", "1") != "0"
 # inference: fold the next block's residual add + RMSNorm into this block's out_proj epilogue (fv_gemm_out_norm) when
 # d_model fits one accumulator (FastVim-T); "0" = separate fv_gemm_bf16_tn + fv_add_norm_fwd launches
 FUSED_OUT_NORM = os.environ.get("FASTVIM_FUSED_OUT_NORM", "1") != "0"
+# inference: fv_block_fwd_signal + fv_gemm_out_norm_flow (the out_proj GEMM starts on finished images while the block kernel's
+# second round is still running); "0" = the plain pair
+FLOW = os.environ.get("FASTVIM_FLOW", "1") != "0"
 
 
 def linear(x, w, b):
@@ -207,21 +210,21 @@ class Mamba(nn.Module):
                 and self.init_layer_scale is None and not self.training
                 and ops.gemm_out_norm_supported(h.numel() // h.shape[-1], self.d_model, self.d_inner))
 
-    def forward_out_norm(self, hidden_states, rotated, residual, norm_w, eps, want_residual=True):
+    def forward_out_norm(self, hidden_states, rotated, residual, norm_w, eps, want_residual=True, flow=None):
         """Inference only: ``(rmsnorm(residual + mixer(h)) * norm_w, residual + mixer(h))`` with the add + norm folded into the
         out_proj GEMM epilogue.  The caller checks ``out_norm_fusable`` first."""
         geom = self.geometry(rotated)
         act_dtype = torch.bfloat16
         return self._forward_inference(hidden_states.to(act_dtype), geom, act_dtype,
-                                       out_norm=(residual, norm_w, eps, want_residual))
+                                       out_norm=(residual, norm_w, eps, want_residual), flow=flow)
 
-    def _linear_out(self, y, pk, out_norm):
+    def _linear_out(self, y, pk, out_norm, flow=None):
         if out_norm is None:
             return linear(y, pk["out_w"], pk["out_b"])
         residual, norm_w, eps, want_residual = out_norm
-        return ops.gemm_out_norm(y, pk["out_w"], residual, norm_w, eps, want_residual)
+        return ops.gemm_out_norm(y, pk["out_w"], residual, norm_w, eps, want_residual, flow=flow)
 
-    def _forward_inference(self, h, geom, act_dtype, out_norm=None):
+    def _forward_inference(self, h, geom, act_dtype, out_norm=None, flow=None):
         pk = self._packed(act_dtype)
         B, L, _ = h.shape
         D, R, N = self.d_inner, self.dt_rank, self.d_state
@@ -231,10 +234,14 @@ class Mamba(nn.Module):
         if (FUSED_BLOCK and self.collapse_method == "mean"
                 and ops.block_fwd_supported(geom, B, D, xz.dtype, R, N)):
             # one launch for [a3-a9]: the image's x stays resident in shared memory (csrc/block_fwd.cu)
+            # flow = (sync, launch_index): the block kernel publishes images as they complete and the out_proj GEMM, launched
+            # programmatically dependent, consumes them while the second round of images is still being computed
+            use_flow = (flow is not None and out_norm is not None and FLOW
+                        and ops.block_fwd_signal_supported(geom, B, D, R, N))
             y = ops.block_fwd(x, z, geom, pk["conv_w"], pk["conv_b"], pk["x_w"], pk["dt_w"], pk["dt_b"],
                               pk["A_neg"], pk["D"], pk["ln_w"], pk["ln_b"], eps, float(self.scaling_factor), R, N,
-                              a_is_log=False, xproj_w_packed=pk.get("x_w_packed"))
-            return self._linear_out(y, pk, out_norm)                     # [a10] (+ [a11] of the next block when fused)
+                              a_is_log=False, xproj_w_packed=pk.get("x_w_packed"), signal=flow if use_flow else None)
+            return self._linear_out(y, pk, out_norm, (flow[0], L, flow[1]) if use_flow else None)   # [a10] (+ next [a11])
         u = ops.conv_pool_fwd(x, geom, pk["conv_w"], pk["conv_b"], float(self.scaling_factor),
                               self.collapse_method)                      # (2, B, Lp, D)         [a3-a5]
         xdbl = ops.x_proj(u, pk["x_w"], TC_GEMM)                         # (2, B*Lp, R+2N)        [a6]

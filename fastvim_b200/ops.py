@@ -158,6 +158,11 @@ def block_fwd_supported(geom: Geometry, batch: int, dim: int, dtype: torch.dtype
     return bool(_lib.lib().fv_block_fwd_supported(C.byref(g), FV_BF16, int(dt_rank), int(d_state)))
 
 
+def block_fwd_signal_supported(geom: Geometry, batch: int, dim: int, dt_rank: int, d_state: int) -> bool:
+    g = geom.c_struct(batch, dim)
+    return bool(_lib.lib().fv_block_fwd_signal_supported(C.byref(g), FV_BF16, int(dt_rank), int(d_state)))
+
+
 def block_pack_xproj(xproj_w: Tensor) -> Optional[Tensor]:
     """(2, R+2N, D) bf16 x_proj weights -> MMA-fragment order for ``block_fwd`` (None when D % 64 != 0)."""
     _check_cuda(xproj_w)
@@ -174,7 +179,7 @@ def block_pack_xproj(xproj_w: Tensor) -> Optional[Tensor]:
 def block_fwd(x: Tensor, z: Tensor, geom: Geometry, conv_w: Tensor, conv_b: Optional[Tensor], xproj_w: Tensor,
               dt_w: Tensor, dt_bias: Tensor, A: Tensor, Dskip: Tensor, ln_w: Optional[Tensor], ln_b: Optional[Tensor],
               eps: float, scale: float, dt_rank: int, d_state: int, a_is_log: bool = True, save: bool = False,
-              xproj_w_packed: Optional[Tensor] = None, save_v: Optional[bool] = None):
+              xproj_w_packed: Optional[Tensor] = None, save_v: Optional[bool] = None, signal=None):
     """K-fused.  x, z (B, L, D) bf16 halves of the in_proj output -> y (B, L, D) bf16 (the out_proj input).
     xproj_w (2, R+2N, D) bf16, dt_w (2, D, R) fp32.  With ``save`` also returns the pooled intermediates
     (u (2, B, Lp, D) bf16, xdbl (2, B*Lp, R+2N) bf16, s (2, B, Lp, D) fp32) the backward kernels need.  With ``save_v``
@@ -205,6 +210,16 @@ def block_fwd(x: Tensor, z: Tensor, geom: Geometry, conv_w: Tensor, conv_b: Opti
             pre = torch.empty((2, B * geom.Lp, D), device=x.device, dtype=torch.float32)   # dt_proj pre-activation
         else:
             s = torch.empty((2, B, geom.Lp, D), device=x.device, dtype=torch.float32)
+    if signal is not None:
+        # inference dataflow form: publish each image's completion for fv_gemm_out_norm_flow (signal = (sync, launch_index))
+        assert not save
+        sync, launch_index = signal
+        assert sync.dtype == torch.int32 and sync.numel() >= B + 1 and sync.is_contiguous()
+        _lib.call("fv_block_fwd_signal", C.byref(g), FV_BF16, _p(x), _p(z), ldx, bs, _p(conv_w), _p(conv_b), _p(xproj_w),
+                  _p(xproj_w_packed), _p(dt_w), _p(dt_bias), _p(A), int(a_is_log), int(dt_rank), int(d_state), _p(Dskip),
+                  _p(ln_w), _p(ln_b), float(eps), float(scale), _p(y), y.stride(1), y.stride(0),
+                  C.c_void_p(sync.data_ptr() + 4), int(launch_index) + 1, _stream(x))
+        return y
     _lib.call("fv_block_fwd", C.byref(g), FV_BF16, _p(x), _p(z), ldx, bs, _p(conv_w), _p(conv_b), _p(xproj_w), _p(xproj_w_packed),
               _p(dt_w), _p(dt_bias), _p(A), int(a_is_log), int(dt_rank), int(d_state), _p(Dskip), _p(ln_w), _p(ln_b), float(eps),
               float(scale), _p(y), y.stride(1), y.stride(0), _p(u), _p(xdbl), _p(s), _p(v), _p(pre), _stream(x))
@@ -349,7 +364,7 @@ def gemm_out_norm_supported(M: int, N: int, K: int) -> bool:
 
 
 def gemm_out_norm(a: Tensor, w: Tensor, residual: Tensor, norm_w: Tensor, eps: float, want_residual: bool = True,
-                  inplace: bool = False) -> Tuple[Tensor, Optional[Tensor]]:
+                  inplace: bool = False, flow=None) -> Tuple[Tensor, Optional[Tensor]]:
     """out_proj + residual add + RMSNorm in one launch (``fv_gemm_out_norm``): a (..., K) bf16, w (N, K) bf16,
     residual (..., N) fp32 -> (y (..., N) bf16 = rmsnorm(residual + a @ w.T) * norm_w, new residual fp32 | None)."""
     _check_cuda(a, w, residual)
@@ -366,8 +381,14 @@ def gemm_out_norm(a: Tensor, w: Tensor, residual: Tensor, norm_w: Tensor, eps: f
     if want_residual:
         res_out = r2 if inplace else torch.empty((M, N), device=a.device, dtype=torch.float32)
     nw = _f32c(norm_w)
-    _lib.call("fv_gemm_out_norm", M, N, K, _p(a2), a2.stride(0), _p(w), w.stride(0), _p(r2), r2.stride(0), _p(res_out),
-              _p(nw), float(eps), _p(y), y.stride(0), _stream(a))
+    if flow is not None:   # (sync, rows_per_flag, launch_index): `a` is being written by block_fwd(..., signal=) right now
+        sync, rows_per_flag, launch_index = flow
+        _lib.call("fv_gemm_out_norm_flow", M, N, K, _p(a2), a2.stride(0), _p(w), w.stride(0), _p(r2), r2.stride(0),
+                  _p(res_out), _p(nw), float(eps), _p(y), y.stride(0), _p(sync), int(rows_per_flag), int(launch_index),
+                  _stream(a))
+    else:
+        _lib.call("fv_gemm_out_norm", M, N, K, _p(a2), a2.stride(0), _p(w), w.stride(0), _p(r2), r2.stride(0), _p(res_out),
+                  _p(nw), float(eps), _p(y), y.stride(0), _stream(a))
     shp = tuple(a.shape[:-1]) + (N,)
     return y.view(shp), (None if res_out is None else res_out.view(shp))
 

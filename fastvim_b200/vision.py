@@ -350,11 +350,14 @@ class VisionMamba(nn.Module):
         hidden, residual = layer_norm_fn(x, first.norm.weight, None, residual=None, prenorm=True,
                                          residual_in_fp32=True, eps=first.norm.eps, is_rms_norm=True)
         n = len(self.layers)
+        # [0] tile counter, [1 + b] completion flag of image b: shared by the n (block kernel, out_proj GEMM) pairs of this
+        # forward, zeroed here once (fv_block_fwd_signal / fv_gemm_out_norm_flow)
+        sync = torch.zeros(x.shape[0] + 1, dtype=torch.int32, device=x.device)
         for i, layer in enumerate(self.layers):
             nxt = self.layers[i + 1].norm if i + 1 < n else self.norm_f
             rotated = layer.rotate_every_block is True and layer.layer_idx % 2 != 0
             hidden, residual = layer.mixer.forward_out_norm(hidden, rotated, residual, nxt.weight, nxt.eps,
-                                                            want_residual=i + 1 < n)
+                                                            want_residual=i + 1 < n, flow=(sync, i))
         return hidden
 
     def forward(self, x, return_features=False, inference_params=None):

@@ -51,6 +51,11 @@ const char* fv_last_error(void);
 int fv_version(void);
 /* Number of kernels launched by this library on the calling thread since the last reset
  * (bench.py's `gpu_launches`). */
+/* Programmatic dependent launch of the inference-chain kernels (in_proj GEMM, fv_block_fwd, out_proj GEMM): on by default
+ * (FASTVIM_PDL=0 disables it); fv_set_pdl() switches it at run time (process-wide) and returns the previous setting -- bench.py
+ * captures a second, serialised graph with it off to read per-kernel durations that do not include the wait for the
+ * predecessor. */
+int fv_set_pdl(int on);
 int64_t fv_launch_count(void);
 void fv_reset_launch_count(void);
 
@@ -209,6 +214,23 @@ int fv_gemm_out_norm_supported(int64_t M, int N, int K);
 int fv_gemm_out_norm(int64_t M, int N, int K, const void* A, int64_t lda, const void* W, int64_t ldw,
                      const float* res_in, int64_t ldr, float* res_out, const float* norm_w, float eps, void* Y,
                      int64_t ldy, void* stream);
+/* Dataflow between fv_block_fwd and the out_proj GEMM (inference, one-CTA-per-image kernel).  At batch 256 on 148 SMs the block
+ * kernel runs two rounds and leaves 40 SMs idle in the second; fv_block_fwd_signal publishes done_flags[img] = done_epoch
+ * (release) as each image's y rows complete, and fv_gemm_out_norm_flow -- launched right after it on the same stream, with
+ * programmatic dependent launch, so its CTAs become resident on the SMs the block kernel has already left -- draws
+ * 128-row tiles from a device counter and waits only for the flags of the images a tile covers.  `sync` is an int32 buffer
+ * of 1 + batch entries ([0] tile counter, [1 + i] flag of image i) that the caller zeroes once per forward; the launch pairs
+ * sharing it are numbered launch_index = 0, 1, ... (done_epoch = launch_index + 1).  Same arithmetic as fv_block_fwd /
+ * fv_gemm_out_norm; with FASTVIM_PDL=0 the pair simply runs back to back. */
+int fv_block_fwd_signal_supported(const fv_geom* g, int dtype, int dt_rank, int dstate);
+int fv_block_fwd_signal(const fv_geom* g, int dtype, const void* x, const void* z, int64_t ldxz, int64_t xz_bstride,
+                        const float* conv_w, const float* conv_b, const void* xproj_w, const void* xproj_w_packed,
+                        const float* dt_w, const float* dt_bias, const float* A, int a_is_log, int dt_rank, int dstate,
+                        const float* Dskip, const float* ln_w, const float* ln_b, float eps, float scale, void* y,
+                        int64_t ldy, int64_t y_bstride, int* done_flags, int done_epoch, void* stream);
+int fv_gemm_out_norm_flow(int64_t M, int N, int K, const void* A, int64_t lda, const void* W, int64_t ldw,
+                          const float* res_in, int64_t ldr, float* res_out, const float* norm_w, float eps, void* Y,
+                          int64_t ldy, int* sync, int rows_per_flag, int launch_index, void* stream);
 /* General form for the backward GEMMs and ragged shapes (csrc/gemm_tc2.cu): C (Mo x No) = op(A) . op(B)^T over a
  * reduction of length K, bf16 operands, fp32 accumulation in tensor memory.
  *   a_mn = 0: A stored (Mo x K) row-major;  a_mn = 1: A stored (K x Mo) row-major (used transposed, not copied)
