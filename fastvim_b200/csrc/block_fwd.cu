@@ -128,7 +128,10 @@ __global__ void __launch_bounds__(BK_THREADS, 1) block_fwd_kernel(const BlockArg
         const bool has_next = img_next < g.B;
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();  // S0: this image's x rows (issued by all threads) have landed
-        if (a.done_flags && it_img > 0 && tid == 0) {  // every warp has fenced its y rows of the previous image before S0
+        // Publish the previous image.  The barrier orders every warp's y stores before this thread (CTA scope); its
+        // gpu-scope fence + release store is cumulative over them (PTX memory model: causality order is transitive), so the
+        // consumer's ld.acquire of the flag observes the whole image.
+        if (a.done_flags && it_img > 0 && tid == 0) {
             __threadfence();
             asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(a.done_flags + (img - (int)gridDim.x)), "r"(a.done_epoch) : "memory");
         }
@@ -491,7 +494,6 @@ __global__ void __launch_bounds__(BK_THREADS, 1) block_fwd_kernel(const BlockArg
 #pragma unroll
                 for (int i = 0; i < BK_NCG; ++i) zc[i] = zn[i];
             }
-            if (a.done_flags) __threadfence();  // this warp's y rows are visible device-wide before the image is published
         }
     }
     if (a.done_flags) {  // last image of this CTA
