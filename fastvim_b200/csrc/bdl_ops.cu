@@ -19,6 +19,8 @@ __global__ void __launch_bounds__(256)
 causal_conv1d_bdl_kernel(int64_t nrows, int dim, int64_t L, int64_t chunks, const T* __restrict__ x, int64_t xbs,
                          int64_t xds, const float* __restrict__ w, const float* __restrict__ bias, int silu,
                          T* __restrict__ out) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (item >= nrows * chunks) return;
     const int64_t row = item / chunks, l0 = (item - row * chunks) * E;
@@ -49,6 +51,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 pool_bdl_kernel(int64_t nrows, int outer, int pool, int inner, const T* __restrict__ x, int is_max, float scale,
                 T* __restrict__ out) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     const int Lp = outer * inner;
     const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (item >= nrows * Lp) return;
@@ -68,6 +72,8 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 bcast_skip_bdl_kernel(int64_t nrows, int dim, int outer, int pool, int inner, const T* __restrict__ s,
                       const T* __restrict__ xc, const float* __restrict__ Dskip, T* __restrict__ out) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     const int64_t L = (int64_t)outer * pool * inner;
     const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (item >= nrows * L) return;
@@ -92,6 +98,8 @@ causal_conv1d_bdl_bwd_kernel(int64_t nrows, int dim, int64_t L, const T* __restr
                              const float* __restrict__ w, const float* __restrict__ bias, int silu,
                              const T* __restrict__ dout, T* __restrict__ dx, int64_t dxbs, int64_t dxds,
                              float* __restrict__ dw, float* __restrict__ db) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= nrows) return;
@@ -148,6 +156,8 @@ template <typename T>
 __global__ void __launch_bounds__(128)
 rowdot_bdl_kernel(int64_t nrows, int dim, int64_t L, const T* __restrict__ a, const T* __restrict__ c,
                   float* __restrict__ out) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5);
     if (row >= nrows) return;
@@ -171,11 +181,11 @@ extern "C" int fv_causal_conv1d_fwd(int dtype, int batch, int dim, int64_t L, co
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == FV_F32) {
         const int64_t chunks = (L + 3) / 4;
-        causal_conv1d_bdl_kernel<float, 4><<<grid_for(nrows * chunks), 256, 0, st>>>(
+        FV_LAUNCH_PDL((causal_conv1d_bdl_kernel<float, 4>), grid_for(nrows * chunks), 256, 0, st, 
             nrows, dim, L, chunks, (const float*)x, x_bstride, x_dstride, w, bias, silu, (float*)out);
     } else if (dtype == FV_BF16) {
         const int64_t chunks = (L + 7) / 8;
-        causal_conv1d_bdl_kernel<bf16, 8><<<grid_for(nrows * chunks), 256, 0, st>>>(
+        FV_LAUNCH_PDL((causal_conv1d_bdl_kernel<bf16, 8>), grid_for(nrows * chunks), 256, 0, st, 
             nrows, dim, L, chunks, (const bf16*)x, x_bstride, x_dstride, w, bias, silu, (bf16*)out);
     } else {
         return fail("fv_causal_conv1d_fwd: unsupported dtype %d", dtype);
@@ -192,10 +202,10 @@ extern "C" int fv_pool_bdl_fwd(int dtype, int batch, int dim, int outer, int poo
     cudaStream_t st = (cudaStream_t)stream;
     const float sc = scale / (float)pool;
     if (dtype == FV_F32)
-        pool_bdl_kernel<float><<<grid_for(items), 256, 0, st>>>(nrows, outer, pool, inner, (const float*)x,
+        FV_LAUNCH_PDL((pool_bdl_kernel<float>), grid_for(items), 256, 0, st, nrows, outer, pool, inner, (const float*)x,
                                                                 pool_mode == FV_POOL_MAX, sc, (float*)out);
     else if (dtype == FV_BF16)
-        pool_bdl_kernel<bf16><<<grid_for(items), 256, 0, st>>>(nrows, outer, pool, inner, (const bf16*)x,
+        FV_LAUNCH_PDL((pool_bdl_kernel<bf16>), grid_for(items), 256, 0, st, nrows, outer, pool, inner, (const bf16*)x,
                                                                pool_mode == FV_POOL_MAX, sc, (bf16*)out);
     else
         return fail("fv_pool_bdl_fwd: unsupported dtype %d", dtype);
@@ -210,10 +220,10 @@ extern "C" int fv_bcast_skip_bdl_fwd(int dtype, int batch, int dim, int outer, i
     const int64_t nrows = (int64_t)batch * dim, items = nrows * outer * pool * inner;
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == FV_F32)
-        bcast_skip_bdl_kernel<float><<<grid_for(items), 256, 0, st>>>(nrows, dim, outer, pool, inner, (const float*)s,
+        FV_LAUNCH_PDL((bcast_skip_bdl_kernel<float>), grid_for(items), 256, 0, st, nrows, dim, outer, pool, inner, (const float*)s,
                                                                       (const float*)xc, Dskip, (float*)out);
     else if (dtype == FV_BF16)
-        bcast_skip_bdl_kernel<bf16><<<grid_for(items), 256, 0, st>>>(nrows, dim, outer, pool, inner, (const bf16*)s,
+        FV_LAUNCH_PDL((bcast_skip_bdl_kernel<bf16>), grid_for(items), 256, 0, st, nrows, dim, outer, pool, inner, (const bf16*)s,
                                                                      (const bf16*)xc, Dskip, (bf16*)out);
     else
         return fail("fv_bcast_skip_bdl_fwd: unsupported dtype %d", dtype);
@@ -231,11 +241,11 @@ extern "C" int fv_causal_conv1d_bwd(int dtype, int batch, int dim, int64_t L, co
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = (unsigned)((nrows + 3) / 4);
     if (dtype == FV_F32)
-        causal_conv1d_bdl_bwd_kernel<float, 4><<<grid, 128, 0, st>>>(nrows, dim, L, (const float*)x, x_bstride, x_dstride, w, bias,
+        FV_LAUNCH_PDL((causal_conv1d_bdl_bwd_kernel<float, 4>), grid, 128, 0, st, nrows, dim, L, (const float*)x, x_bstride, x_dstride, w, bias,
                                                                      silu, (const float*)dout, (float*)dx, dx_bstride,
                                                                      dx_dstride, dw, dbias);
     else if (dtype == FV_BF16)
-        causal_conv1d_bdl_bwd_kernel<bf16, 8><<<grid, 128, 0, st>>>(nrows, dim, L, (const bf16*)x, x_bstride, x_dstride, w, bias,
+        FV_LAUNCH_PDL((causal_conv1d_bdl_bwd_kernel<bf16, 8>), grid, 128, 0, st, nrows, dim, L, (const bf16*)x, x_bstride, x_dstride, w, bias,
                                                                     silu, (const bf16*)dout, (bf16*)dx, dx_bstride, dx_dstride,
                                                                     dw, dbias);
     else
@@ -252,9 +262,9 @@ extern "C" int fv_rowdot_bdl(int dtype, int batch, int dim, int64_t L, const voi
     cudaStream_t st = (cudaStream_t)stream;
     const unsigned grid = (unsigned)((nrows + 3) / 4);
     if (dtype == FV_F32)
-        rowdot_bdl_kernel<float><<<grid, 128, 0, st>>>(nrows, dim, L, (const float*)a, (const float*)c, out);
+        FV_LAUNCH_PDL((rowdot_bdl_kernel<float>), grid, 128, 0, st, nrows, dim, L, (const float*)a, (const float*)c, out);
     else if (dtype == FV_BF16)
-        rowdot_bdl_kernel<bf16><<<grid, 128, 0, st>>>(nrows, dim, L, (const bf16*)a, (const bf16*)c, out);
+        FV_LAUNCH_PDL((rowdot_bdl_kernel<bf16>), grid, 128, 0, st, nrows, dim, L, (const bf16*)a, (const bf16*)c, out);
     else
         return fail("fv_rowdot_bdl: unsupported dtype %d", dtype);
     return finish_launch("rowdot_bdl");

@@ -100,6 +100,8 @@ __device__ __forceinline__ float4 xd_ld4(const unsigned char* xd, uint32_t idx) 
 // F14: 14 x 14 token grid (pool 14, 14 pooled rows: every loop unrolled);  XDB: xd held as bf16.
 template <int RT, bool NORM, bool F14, bool XDB>
 __global__ void __launch_bounds__(BC_THREADS, 2) block_cluster_kernel(const ClusterArgs a) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     extern __shared__ __align__(128) unsigned char smem[];
     constexpr int N = BK_NSTATE, DC = BC_DC, T = BC_THREADS;
     const Geom& g = a.g;
@@ -694,13 +696,14 @@ int launch_block_cluster(const fv_geom* g_, const ClusterPlan& p, const void* x,
     cfg.blockDim = dim3(BC_THREADS, 1, 1);
     cfg.dynamicSmemBytes = p.smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
+    pdl_attr(&attr[1]);
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)p.C;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     e = cudaLaunchKernelEx(&cfg, kern, a);
     FV_REQUIRE(e == cudaSuccess, "fv_block_fwd: cluster launch (%d CTAs / image): %s", p.C, cudaGetErrorString(e));
     return finish_launch("block_fwd[cluster]");

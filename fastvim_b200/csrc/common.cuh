@@ -279,16 +279,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // pdl_trigger() lets the NEXT kernel start launching (it fires once every CTA of this grid has called it or exited).
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-bool pdl_enabled();  // core.cu: FASTVIM_PDL != "0"
+bool pdl_enabled();      // core.cu: FASTVIM_PDL != "0" -- the FastVim-T inference chain kernels
+bool pdl_all_enabled();  // core.cu: FASTVIM_PDL_ALL == "1" -- every other kernel (FV_LAUNCH_PDL)
 template <typename... KArgs, typename... Args>
-static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+static inline cudaError_t launch_pdl_if(bool on, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                        Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    at[0].val.programmaticStreamSerializationAllowed = on ? 1 : 0;
     cfg.attrs = at; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    return launch_pdl_if(pdl_enabled(), kern, grid, block, smem, st, args...);
+}
+
+// kernel<<<grid, block, smem, st>>>(args...) with the PDL attribute; the kernel name goes in parentheses (template commas)
+#define FV_LAUNCH_PDL(kern, grid, block, smem, st, ...) \
+    ((void)::fv::launch_pdl_if(::fv::pdl_all_enabled(), kern, dim3(grid), dim3(block), (size_t)(smem), (cudaStream_t)(st), __VA_ARGS__))
+// second attribute for cudaLaunchKernelEx launches that already carry a cluster dimension
+static inline void pdl_attr(cudaLaunchAttribute* at) {
+    at->id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at->val.programmaticStreamSerializationAllowed = pdl_all_enabled() ? 1 : 0;
 }
 
 // Both conv directions at one token from a 7-row window w[k] = x[t-3+k]:

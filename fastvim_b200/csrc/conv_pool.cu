@@ -33,6 +33,8 @@ __global__ void __launch_bounds__(256)
 conv_pool_fwd_kernel(Geom g, const T* __restrict__ x, int64_t ldx, int64_t xbs,
                      const float* __restrict__ cw, const float* __restrict__ cb, float scale,
                      T* __restrict__ u) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     constexpr bool FAST = is_fast<T>::value;
     const int nvec = g.D >> 2;
     int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -115,6 +117,8 @@ __global__ void __launch_bounds__(MAXT)
 conv_pool_staged_kernel(Geom g, int TP, int nbuf, int vec16, const T* __restrict__ x, int64_t ldx, int64_t xbs,
                         const float* __restrict__ cw, const float* __restrict__ cb, float scale,
                         T* __restrict__ u) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     constexpr bool FAST = is_fast<T>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* xs = reinterpret_cast<T*>(smem_raw);
@@ -191,6 +195,8 @@ __global__ void __launch_bounds__(MAXT)
 conv_pool_cluster_kernel(Geom g, int NS, int np_seg, int vec16, const T* __restrict__ x, int64_t ldx, int64_t xbs,
                          const float* __restrict__ cw, const float* __restrict__ cb, float scale,
                          T* __restrict__ u) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     constexpr bool FAST = is_fast<T>::value;
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -279,13 +285,14 @@ static int launch_conv_pool_cluster(const Geom& g, int NS, const T* x, int64_t l
     cfg.blockDim = dim3((unsigned)threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
+    pdl_attr(&attr[1]);
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)NS;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     const int vec16 = (int)rows_vec16<T>(g.D, x, ldx, xbs);
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, g, NS, np_seg, vec16, x, ldx, xbs, cw, cb, scale, u);
     FV_REQUIRE(e == cudaSuccess, "fv_conv_pool_fwd: cluster launch failed: %s", cudaGetErrorString(e));
@@ -313,7 +320,7 @@ static int launch_conv_pool_staged(const Geom& g, const T* x, int64_t ldx, int64
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         FV_REQUIRE(e == cudaSuccess, "fv_conv_pool_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    kern<<<grid, block, smem, st>>>(g, TP, nbuf, (int)rows_vec16<T>(g.D, x, ldx, xbs), x, ldx, xbs, cw, cb, scale, u);
+    FV_LAUNCH_PDL((kern), grid, block, smem, st, g, TP, nbuf, (int)rows_vec16<T>(g.D, x, ldx, xbs), x, ldx, xbs, cw, cb, scale, u);
     return finish_launch("conv_pool_fwd");
 }
 
@@ -336,11 +343,11 @@ static int launch_conv_pool(const Geom& g, const T* x, int64_t ldx, int64_t xbs,
     dim3 grid((unsigned)blocks), block(threads);
     const bool in1 = g.inner == 1;
     if (pool_mode == FV_POOL_MAX) {
-        if (in1) conv_pool_fwd_kernel<T, true, true><<<grid, block, 0, st>>>(g, x, ldx, xbs, cw, cb, scale, u);
-        else conv_pool_fwd_kernel<T, true, false><<<grid, block, 0, st>>>(g, x, ldx, xbs, cw, cb, scale, u);
+        if (in1) FV_LAUNCH_PDL((conv_pool_fwd_kernel<T, true, true>), grid, block, 0, st, g, x, ldx, xbs, cw, cb, scale, u);
+        else FV_LAUNCH_PDL((conv_pool_fwd_kernel<T, true, false>), grid, block, 0, st, g, x, ldx, xbs, cw, cb, scale, u);
     } else {
-        if (in1) conv_pool_fwd_kernel<T, false, true><<<grid, block, 0, st>>>(g, x, ldx, xbs, cw, cb, scale, u);
-        else conv_pool_fwd_kernel<T, false, false><<<grid, block, 0, st>>>(g, x, ldx, xbs, cw, cb, scale, u);
+        if (in1) FV_LAUNCH_PDL((conv_pool_fwd_kernel<T, false, true>), grid, block, 0, st, g, x, ldx, xbs, cw, cb, scale, u);
+        else FV_LAUNCH_PDL((conv_pool_fwd_kernel<T, false, false>), grid, block, 0, st, g, x, ldx, xbs, cw, cb, scale, u);
     }
     return finish_launch("conv_pool_fwd");
 }

@@ -32,6 +32,8 @@ conv_pool_bwd_kernel(Geom g, int64_t ntiles, int tiles_per_img, int tiles_per_gr
                      const T* __restrict__ du, const float* __restrict__ cw, const float* __restrict__ cb,
                      const float* __restrict__ Dskip, float scale, T* __restrict__ dx,
                      float* __restrict__ dcw, float* __restrict__ dcb) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int D = g.D;
     constexpr int NR = TT + 6;
@@ -213,6 +215,8 @@ conv_pool_bwd_stream_kernel(Geom g, int nseg, int seg_len, int64_t nitems, int n
                             const T* __restrict__ du, const float* __restrict__ cw, const float* __restrict__ cb,
                             const float* __restrict__ Dskip, float scale, T* __restrict__ dx,
                             float* __restrict__ dcw, float* __restrict__ dcb, float* __restrict__ dDs) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     typedef Pair<T> P;
     typedef typename P::type PT;
     constexpr bool FAST = is_fast<T>::value;
@@ -361,7 +365,7 @@ static int launch_conv_bwd_stream(const Geom& g, const T* x, int64_t ldx, int64_
     // even number of runs per slot where possible (no ragged last round)
     const int64_t rounds = (nitems + nslots - 1) / nslots;
     nslots = (nitems + rounds - 1) / rounds;
-    kern<<<(unsigned)(nslots * chunks), threads, 0, st>>>(g, nseg, seg_len, nitems, (int)nslots, chunks, x, ldx, xbs, e, du, cw,
+    FV_LAUNCH_PDL((kern), (unsigned)(nslots * chunks), threads, 0, st, g, nseg, seg_len, nitems, (int)nslots, chunks, x, ldx, xbs, e, du, cw,
                                                           cb, Dskip, scale, dx, dcw, dcb, dDs);
     return finish_launch("conv_pool_bwd");
 }
@@ -398,7 +402,7 @@ static int launch_conv_bwd(const Geom& g, int tpg, int tile_len, const T* x, int
     const int64_t resident = (int64_t)sm_count() * occ;
     dim3 grid((unsigned)(ntiles < resident ? ntiles : resident)), block(threads);
     const int vec16 = (rows_vec16<T>(g.D, x, ldx, xbs) ? 1 : 0) | (rows_vec16<T>(g.D, e, g.D, (int64_t)g.L * g.D) ? 2 : 0);
-    kern<<<grid, block, smem, st>>>(g, ntiles, tiles_per_img, tpg, tile_len, vec16, x, ldx, xbs, e, du, cw, cb, Dskip,
+    FV_LAUNCH_PDL((kern), grid, block, smem, st, g, ntiles, tiles_per_img, tpg, tile_len, vec16, x, ldx, xbs, e, du, cw, cb, Dskip,
                                     scale, dx, dcw, dcb);
     return finish_launch("conv_pool_bwd");
 }

@@ -54,6 +54,19 @@ bool pdl_enabled() {
     return g_pdl != 0;
 }
 
+// The attribute is set by default only on the FastVim-T inference chain (fv_gemm_bf16_tn, fv_block_fwd, fv_gemm_out_norm), where it
+// was measured to pay (+2.8 %, and the block -> out_proj dataflow needs it).  Every other kernel of the library is PDL-correct
+// (griddepcontrol.wait before its first global access) but launches in plain stream order unless FASTVIM_PDL_ALL=1: with the
+// multi-wave, non-persistent kernels of the wider models the early-resident dependents cost 1-2 % (FastVim-S/B, FastChannelVim).
+static int g_pdl_all = -1;
+bool pdl_all_enabled() {
+    if (g_pdl_all < 0) {
+        const char* e = getenv("FASTVIM_PDL_ALL");
+        g_pdl_all = (e && e[0] == '1') ? 1 : 0;
+    }
+    return g_pdl_all != 0 && pdl_enabled();
+}
+
 int check_geom(const fv_geom* g, const char* who) {
     FV_REQUIRE(g != nullptr, "%s: null geometry", who);
     FV_REQUIRE(g->batch > 0 && g->dim > 0 && g->outer > 0 && g->pool > 0 && g->inner > 0,

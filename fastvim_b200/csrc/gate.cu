@@ -78,6 +78,8 @@ gate_fwd_kernel(Geom g, int64_t ntiles, int tiles_per_img, int tiles_per_group, 
                 const float* __restrict__ s, const float* __restrict__ cw, const float* __restrict__ cb,
                 const float* __restrict__ Dskip, const float* __restrict__ lnw, const float* __restrict__ lnb,
                 float eps, T* __restrict__ y, int64_t ldy, int64_t ybs, float* __restrict__ stats) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     constexpr bool FAST = is_fast<T>::value;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nthreads = blockDim.x, nwarps = nthreads >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -270,6 +272,8 @@ norm_gate_apply_kernel(Geom g, int full_dim, T* __restrict__ y, int64_t ldy, int
                        const T* __restrict__ z, int64_t ldz, int64_t zbs,
                        const float* __restrict__ stats, const float* __restrict__ lnw,
                        const float* __restrict__ lnb, float eps) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     constexpr bool FAST = is_fast<T>::value;
     const int nvec = g.D >> 2;
     const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -330,7 +334,7 @@ static int launch_gate_tt(const Geom& g, int tpg, int tile_len, int nbuf, const 
     const int64_t resident = (int64_t)sm_count() * occ;  // persistent grid: one wave
     dim3 grid((unsigned)(ntiles < resident ? ntiles : resident)), block(threads);
     const int vec16 = rows_vec16<T>(g.D, x, ldxz, xzbs) && ((uintptr_t)z % 16) == 0;
-    kern<<<grid, block, smem, st>>>(g, ntiles, tiles_per_img, tpg, tile_len, vec16, nbuf, x, z, ldxz, xzbs, s, cw, cb,
+    FV_LAUNCH_PDL((kern), grid, block, smem, st, g, ntiles, tiles_per_img, tpg, tile_len, vec16, nbuf, x, z, ldxz, xzbs, s, cw, cb,
                                     Dskip, lnw, lnb, eps, y, ldy, ybs, stats);
     return finish_launch("gate_fwd");
 }
@@ -404,9 +408,9 @@ extern "C" int fv_norm_gate_apply(const fv_geom* g_, int dtype, int full_dim, vo
     dim3 grid((unsigned)((items + 255) / 256)), block(256);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == FV_F32)
-        norm_gate_apply_kernel<float><<<grid, block, 0, st>>>(g, full_dim, (float*)y, ldy, y_bstride, (const float*)z, ldz, z_bstride, stats, ln_w, ln_b, eps);
+        FV_LAUNCH_PDL((norm_gate_apply_kernel<float>), grid, block, 0, st, g, full_dim, (float*)y, ldy, y_bstride, (const float*)z, ldz, z_bstride, stats, ln_w, ln_b, eps);
     else if (dtype == FV_BF16)
-        norm_gate_apply_kernel<bf16><<<grid, block, 0, st>>>(g, full_dim, (bf16*)y, ldy, y_bstride, (const bf16*)z, ldz, z_bstride, stats, ln_w, ln_b, eps);
+        FV_LAUNCH_PDL((norm_gate_apply_kernel<bf16>), grid, block, 0, st, g, full_dim, (bf16*)y, ldy, y_bstride, (const bf16*)z, ldz, z_bstride, stats, ln_w, ln_b, eps);
     else
         return fail("fv_norm_gate_apply: unsupported dtype %d", dtype);
     return finish_launch("norm_gate_apply");

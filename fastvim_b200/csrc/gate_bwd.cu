@@ -62,6 +62,8 @@ gate_bwd_kernel(Geom g, int64_t ntiles, int tiles_per_img, int tiles_per_group, 
                 const float* __restrict__ lnw, const float* __restrict__ lnb, float eps, T* __restrict__ dz,
                 T* __restrict__ e_out, float* __restrict__ ds_planes, float* __restrict__ dDskip,
                 float* __restrict__ dlnw, float* __restrict__ dlnb) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nthreads = blockDim.x;
     const int D = g.D;
@@ -242,7 +244,7 @@ static int launch_gate_bwd(const Geom& g, int tpg, int tile_len, const T* x, con
     dim3 grid((unsigned)(ntiles < resident ? ntiles : resident)), block(threads);
     const int vec16 = (rows_vec16<T>(g.D, x, ldxz, xzbs) && ((uintptr_t)z % 16) == 0 ? 1 : 0) |
                       (rows_vec16<T>(g.D, dy, lddy, dybs) ? 2 : 0);
-    kern<<<grid, block, smem, st>>>(g, ntiles, tiles_per_img, tpg, tile_len, vec16, x, z, ldxz, xzbs, dy, lddy, dybs, s,
+    FV_LAUNCH_PDL((kern), grid, block, smem, st, g, ntiles, tiles_per_img, tpg, tile_len, vec16, x, z, ldxz, xzbs, dy, lddy, dybs, s,
                                     cw, cb, Dskip, lnw, lnb, eps, dz, e_out, ds_planes, dDskip, dlnw, dlnb);
     return finish_launch("gate_bwd");
 }

@@ -81,6 +81,8 @@ gate_bwd_stream_kernel(Geom g, int nseg, int seg_len, int64_t nitems, int nslots
                        const float* __restrict__ lnw, const float* __restrict__ lnb, float eps,
                        float* __restrict__ stats, T* __restrict__ dz, T* __restrict__ e_out, float* __restrict__ ds,
                        float* __restrict__ dDskip, float* __restrict__ dlnw, float* __restrict__ dlnb) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     typedef Pair<T> P;
     typedef typename P::type PT;
     constexpr bool FAST = is_fast<T>::value;
@@ -258,7 +260,7 @@ static int launch_gbs(const Geom& g, const T* x, const T* z, int64_t ldxz, int64
     if (nslots > nitems) nslots = nitems;
     const int64_t rounds = (nitems + nslots - 1) / nslots;
     nslots = (nitems + rounds - 1) / rounds;
-    kern<<<(unsigned)(nslots * chunks), threads, 0, st>>>(g, nseg, seg_len, nitems, (int)nslots, chunks, x, z, ldxz, xzbs, dy, lddy,
+    FV_LAUNCH_PDL((kern), (unsigned)(nslots * chunks), threads, 0, st, g, nseg, seg_len, nitems, (int)nslots, chunks, x, z, ldxz, xzbs, dy, lddy,
                                                           dybs, s, cw, cb, Dskip, lnw, lnb, eps, stats, dz, e_out, ds, dDskip,
                                                           dlnw, dlnb);
     return finish_launch(MODE == 0 ? "gate_bwd_stats" : "gate_bwd_apply");

@@ -62,6 +62,8 @@ __device__ __forceinline__ void silu_grad2(float2 zv, float2& sl, float2& dsl) {
 // NWG: warps per token group (d_inner / 384)
 template <bool NORM, int NWG>
 __global__ void __launch_bounds__(GV_THREADS, 2) gate_bwd_v_kernel(const GateBwdVArgs a) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     extern __shared__ __align__(16) unsigned char gv_smem[];
     constexpr int NGRP = GV_WARPS / NWG;   // token groups per CTA
     const Geom& g = a.g;
@@ -290,6 +292,6 @@ extern "C" int fv_gate_bwd_v(const fv_geom* g_, int dtype, const void* v, const 
     int64_t want = (a.nitems + ngrp - 1) / ngrp;
     const int64_t resident = (int64_t)sm_count() * 2;
     const int grid = (int)(want < resident ? want : resident);
-    kern<<<grid, GV_THREADS, smem, (cudaStream_t)stream>>>(a);
+    FV_LAUNCH_PDL((kern), grid, GV_THREADS, smem, (cudaStream_t)stream, a);
     return finish_launch("gate_bwd_v");
 }

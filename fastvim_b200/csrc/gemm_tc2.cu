@@ -46,6 +46,8 @@ template <int BN, bool A_MN, bool B_MN, bool OUT_F32>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmC, const Gemm2Args a) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     extern __shared__ unsigned char g2_smem_raw[];
     const uint32_t raw = smem_u32(g2_smem_raw);
     unsigned char* smem = g2_smem_raw + (((raw + 1023u) & ~1023u) - raw);
@@ -297,7 +299,7 @@ static int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CU
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     FV_REQUIRE(e == cudaSuccess, "fv_gemm_bf16: cudaFuncSetAttribute(%zu): %s", smem, cudaGetErrorString(e));
     const int grid = a.ntiles < sm_count() ? a.ntiles : sm_count();
-    kern<<<grid, G2_THREADS, smem, st>>>(tmA, tmB, tmC, a);
+    FV_LAUNCH_PDL((kern), grid, G2_THREADS, smem, st, tmA, tmB, tmC, a);
     return finish_launch("gemm_tc2");
 }
 

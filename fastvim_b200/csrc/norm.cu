@@ -20,6 +20,8 @@ add_norm_fwd_kernel(int64_t rows, int cols, const T* __restrict__ x, int64_t ldx
                     const float* __restrict__ bias, float eps, T* __restrict__ y, int64_t ldy,
                     float* __restrict__ res_out, float* __restrict__ mean_out,
                     float* __restrict__ rstd_out) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * NORM_WARPS + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -88,6 +90,8 @@ add_norm_bwd_kernel(int64_t rows, int cols, const T* __restrict__ dy, int64_t ld
                     const float* __restrict__ dres_out, const float* __restrict__ res_out,
                     const float* __restrict__ w, float eps, T* __restrict__ dx, int64_t lddx,
                     float* __restrict__ dres_in, float* __restrict__ dw, float* __restrict__ db) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int nvec = cols >> 2;
     const float inv = 1.f / (float)cols;
@@ -193,8 +197,8 @@ static int launch_add_norm_bwd(int64_t rows, int cols, const T* dy, int64_t lddy
     const int nvec = cols / 4;
 #define FV_NB_CASE(NV_)                                                                                                 \
     if (nvec <= NV_ * 32) {                                                                                             \
-        if (is_rms) add_norm_bwd_kernel<T, NV_, true><<<grid, block, 0, st>>>(rows, cols, dy, lddy, dres_out, res_out, w, eps, dx, lddx, dres_in, dw, db); \
-        else add_norm_bwd_kernel<T, NV_, false><<<grid, block, 0, st>>>(rows, cols, dy, lddy, dres_out, res_out, w, eps, dx, lddx, dres_in, dw, db);       \
+        if (is_rms) FV_LAUNCH_PDL((add_norm_bwd_kernel<T, NV_, true>), grid, block, 0, st, rows, cols, dy, lddy, dres_out, res_out, w, eps, dx, lddx, dres_in, dw, db); \
+        else FV_LAUNCH_PDL((add_norm_bwd_kernel<T, NV_, false>), grid, block, 0, st, rows, cols, dy, lddy, dres_out, res_out, w, eps, dx, lddx, dres_in, dw, db);       \
         return finish_launch("add_norm_bwd");                                                                           \
     }
     FV_NB_CASE(2) FV_NB_CASE(3) FV_NB_CASE(4) FV_NB_CASE(6) FV_NB_CASE(8) FV_NB_CASE(12) FV_NB_CASE(16)
@@ -210,8 +214,8 @@ static int launch_add_norm(int64_t rows, int cols, const T* x, int64_t ldx, cons
     const int nvec = cols / 4;
 #define FV_NORM_CASE(NV_)                                                                                   \
     if (nvec <= NV_ * 32) {                                                                                 \
-        if (is_rms) add_norm_fwd_kernel<T, NV_, true><<<grid, block, 0, st>>>(rows, cols, x, ldx, res_in, w, bias, eps, y, ldy, res_out, mean_out, rstd_out); \
-        else add_norm_fwd_kernel<T, NV_, false><<<grid, block, 0, st>>>(rows, cols, x, ldx, res_in, w, bias, eps, y, ldy, res_out, mean_out, rstd_out);       \
+        if (is_rms) FV_LAUNCH_PDL((add_norm_fwd_kernel<T, NV_, true>), grid, block, 0, st, rows, cols, x, ldx, res_in, w, bias, eps, y, ldy, res_out, mean_out, rstd_out); \
+        else FV_LAUNCH_PDL((add_norm_fwd_kernel<T, NV_, false>), grid, block, 0, st, rows, cols, x, ldx, res_in, w, bias, eps, y, ldy, res_out, mean_out, rstd_out);       \
         return finish_launch("add_norm_fwd");                                                               \
     }
     FV_NORM_CASE(2) FV_NORM_CASE(4) FV_NORM_CASE(8) FV_NORM_CASE(16)
@@ -265,6 +269,8 @@ template <typename T, int NV>
 __global__ void __launch_bounds__(NORM_WARPS * 32)
 ln_gate_fwd_kernel(int64_t rows, int cols, const T* __restrict__ v, int64_t ldv, const T* __restrict__ z, int64_t ldz,
                    const float* __restrict__ w, const float* __restrict__ bias, float eps, T* __restrict__ y, int64_t ldy) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * NORM_WARPS + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -315,7 +321,7 @@ static int launch_ln_gate(int64_t rows, int cols, const T* v, int64_t ldv, const
                           const float* b, float eps, T* y, int64_t ldy, cudaStream_t st) {
     const int nv = (cols / 4 + 31) / 32;
     const unsigned grid = (unsigned)((rows + NORM_WARPS - 1) / NORM_WARPS);
-#define FV_LG(NV_) ln_gate_fwd_kernel<T, NV_><<<grid, NORM_WARPS * 32, 0, st>>>(rows, cols, v, ldv, z, ldz, w, b, eps, y, ldy)
+#define FV_LG(NV_) FV_LAUNCH_PDL((ln_gate_fwd_kernel<T, NV_>), grid, NORM_WARPS * 32, 0, st, rows, cols, v, ldv, z, ldz, w, b, eps, y, ldy)
     if (nv <= 1) FV_LG(1);
     else if (nv <= 2) FV_LG(2);
     else if (nv <= 3) FV_LG(3);

@@ -47,6 +47,8 @@ template <typename TI, bool BF16_PASSTHROUGH>
 __global__ void __launch_bounds__(256)
 patchify_kernel(const TI* __restrict__ img, int C, int H, int W, int p, int per_channel, int64_t total8,
                 bf16* __restrict__ out) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     const int W8 = W >> 3, p8 = p >> 3;
     const int gh = H / p, gw = W / p;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (int64_t)gridDim.x * blockDim.x) {
@@ -108,11 +110,11 @@ extern "C" int fv_patchify(int in_dtype, int batch, int C, int H, int W, int pat
     const int grid = (int)(want < (int64_t)sm_count() * 16 ? want : (int64_t)sm_count() * 16);
     cudaStream_t st = (cudaStream_t)stream;
     if (in_dtype == 0)
-        patchify_kernel<float, false><<<grid, 256, 0, st>>>((const float*)img, C, H, W, patch, per_channel, total8, (bf16*)out);
+        FV_LAUNCH_PDL((patchify_kernel<float, false>), grid, 256, 0, st, (const float*)img, C, H, W, patch, per_channel, total8, (bf16*)out);
     else if (in_dtype == 1)
-        patchify_kernel<bf16, true><<<grid, 256, 0, st>>>((const bf16*)img, C, H, W, patch, per_channel, total8, (bf16*)out);
+        FV_LAUNCH_PDL((patchify_kernel<bf16, true>), grid, 256, 0, st, (const bf16*)img, C, H, W, patch, per_channel, total8, (bf16*)out);
     else
-        patchify_kernel<uint8_t, false><<<grid, 256, 0, st>>>((const uint8_t*)img, C, H, W, patch, per_channel, total8,
+        FV_LAUNCH_PDL((patchify_kernel<uint8_t, false>), grid, 256, 0, st, (const uint8_t*)img, C, H, W, patch, per_channel, total8,
                                                               (bf16*)out);
     return finish_launch("patchify");
 }

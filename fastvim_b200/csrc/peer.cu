@@ -101,6 +101,8 @@ struct PeerSumArgs {
 };
 
 __global__ void __launch_bounds__(256) peer_sum_kernel(const PeerSumArgs a) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     peer_sync(a.pb);
     const int64_t n4 = a.n >> 2;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -130,6 +132,8 @@ struct PeerCopyArgs {
 };
 
 __global__ void __launch_bounds__(256) peer_copy_kernel(const PeerCopyArgs a) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     peer_sync(a.pb);
     const int64_t per_peer = (int64_t)a.nparts * a.rows * a.seg16;
     const int64_t total = per_peer * a.pb.world;
@@ -190,7 +194,7 @@ extern "C" int fv_peer_sum_f32(int world, int rank, const void* const* bufs, int
     a.off = off; a.n = n; a.out32 = out32; a.out16 = (bf16*)out16;
     int64_t want = (n / 4 + 255) / 256;
     const int grid = (int)(want < 1 ? 1 : (want > 64 ? 64 : want));
-    peer_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    FV_LAUNCH_PDL((peer_sum_kernel), grid, 256, 0, (cudaStream_t)stream, a);
     return finish_launch("peer_sum_f32");
 }
 
@@ -218,7 +222,7 @@ extern "C" int fv_peer_copy2d(int world, int rank, const void* const* bufs, int 
     const int64_t total = (int64_t)world * nparts * rows * a.seg16;
     int64_t want = (total + 256 * 8 - 1) / (256 * 8);
     const int grid = (int)(want < 1 ? 1 : (want > PEER_MAX_CTAS ? PEER_MAX_CTAS : want));
-    peer_copy_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    FV_LAUNCH_PDL((peer_copy_kernel), grid, 256, 0, (cudaStream_t)stream, a);
     return finish_launch("peer_copy2d");
 }
 

@@ -50,6 +50,8 @@ __global__ void __launch_bounds__(SCAN_THREADS)
 scan_fwd_kernel(Geom g, const T* __restrict__ u, const T* __restrict__ xdbl, int64_t ldxd, int R,
                 const float* __restrict__ dtw, const float* __restrict__ dtb,
                 const float* __restrict__ A, int a_is_log, float* __restrict__ s) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     constexpr int WROW = RT + 2 * N;
     __shared__ __align__(16) float tile[2][SCAN_LC][WROW];
     const int dir = blockIdx.z;
@@ -150,6 +152,8 @@ __global__ void __launch_bounds__(SCK_CH * 16)
 scan_fwd_chunked_kernel(Geom g, int nch, const T* __restrict__ u, const T* __restrict__ xdbl, int64_t ldxd, int R,
                         const float* __restrict__ dtw, const float* __restrict__ dtb,
                         const float* __restrict__ A, int a_is_log, float* __restrict__ s) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     constexpr int WROW = RT + 2 * N;
     extern __shared__ __align__(16) float sck_smem[];
     float* tile = sck_smem;                                    // [Lp][WROW]   dt | B | C rows of this image / direction
@@ -294,7 +298,7 @@ static int launch_scan_chunked(const Geom& g, const T* u, const T* xdbl, int64_t
                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
             FV_REQUIRE(e == cudaSuccess, "fv_scan_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));             \
         }                                                                                                             \
-        scan_fwd_chunked_kernel<T, RT_, N><<<grid, block, smem, st>>>(g, nch, u, xdbl, ldxd, R, dtw, dtb, A, a_is_log, s); \
+        FV_LAUNCH_PDL((scan_fwd_chunked_kernel<T, RT_, N>), grid, block, smem, st, g, nch, u, xdbl, ldxd, R, dtw, dtb, A, a_is_log, s); \
     }
     FV_SCK_CASE(8) FV_SCK_CASE(12) FV_SCK_CASE(16)
 #undef FV_SCK_CASE
@@ -314,7 +318,7 @@ static int launch_scan(const Geom& g, const T* u, const T* xdbl, int64_t ldxd, i
     dim3 grid(ceil_div(g.D, SCAN_THREADS), g.B, 2), block(SCAN_THREADS);
 #define FV_SCAN_CASE(RT_)                                                                          \
     if (R <= RT_) {                                                                                \
-        scan_fwd_kernel<T, RT_, N><<<grid, block, 0, st>>>(g, u, xdbl, ldxd, R, dtw, dtb, A, a_is_log, s); \
+        FV_LAUNCH_PDL((scan_fwd_kernel<T, RT_, N>), grid, block, 0, st, g, u, xdbl, ldxd, R, dtw, dtb, A, a_is_log, s); \
         return finish_launch("scan_fwd");                                                          \
     }
     FV_SCAN_CASE(8) FV_SCAN_CASE(12) FV_SCAN_CASE(16) FV_SCAN_CASE(24) FV_SCAN_CASE(32) FV_SCAN_CASE(48) FV_SCAN_CASE(64)

@@ -81,6 +81,8 @@ scan_bwd_kernel(Geom g, int nplanes_ds, const T* __restrict__ u, const T* __rest
                 const float* __restrict__ dtw, const float* __restrict__ dtb, const float* __restrict__ A,
                 int a_is_log, const float* __restrict__ ds, T* __restrict__ du, T* __restrict__ ddelta,
                 float* __restrict__ dbc_planes, float* __restrict__ dA, float* __restrict__ dbias) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     static_assert(N == 16, "butterfly reduction is written for 16 states");
     constexpr int WROW = RT + 2 * N;
     extern __shared__ __align__(16) float smem[];
@@ -287,6 +289,8 @@ scan_bwd_small_kernel(Geom g, int nplanes_ds, const T* __restrict__ u, const T* 
                       const float* __restrict__ dtw, const float* __restrict__ dtb, const float* __restrict__ A,
                       int a_is_log, const float* __restrict__ ds, T* __restrict__ du, T* __restrict__ ddelta,
                       float* __restrict__ dbc_planes, float* __restrict__ dA, float* __restrict__ dbias) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     constexpr int N = 16, WROW = RT + 2 * N;
     extern __shared__ __align__(16) float sbs[];
     float* tile = sbs;                                   // [SBS_LP][WROW]      dt | B | C rows
@@ -646,6 +650,8 @@ scan_bwd_short_kernel(Geom g, int nplanes_ds, const T* __restrict__ u, const T* 
                       const float* __restrict__ pre, const float* __restrict__ A, int a_is_log,
                       const float* __restrict__ ds, T* __restrict__ du, T* __restrict__ ddelta,
                       float* __restrict__ dbc_planes, float* __restrict__ dA, float* __restrict__ dbias) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     if (blockIdx.z)
         scan_bwd_short_body<T, LPT, 1>(g, nplanes_ds, u, xdbl, ldxd, R, pre, A, a_is_log, ds, du, ddelta, dbc_planes, dA, dbias);
     else
@@ -655,6 +661,8 @@ scan_bwd_short_kernel(Geom g, int nplanes_ds, const T* __restrict__ u, const T* 
 // sums `nplanes` planes of `n` floats: out[i] = sum_p in[p*n + i] (adds to the cast when `accumulate`)
 template <typename TO>
 __global__ void reduce_planes_kernel(const float* __restrict__ in, int nplanes, int64_t n, TO* __restrict__ out) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float acc = 0.f;
@@ -678,7 +686,7 @@ static int launch_scan_bwd(const Geom& g, int nplanes_ds, const T* u, const T* x
         auto kern = scan_bwd_small_kernel<T, RT_>;                                                                   \
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
         FV_REQUIRE(e == cudaSuccess, "fv_scan_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));                \
-        kern<<<grid, block, smem, st>>>(g, nplanes_ds, u, xdbl, ldxd, R, dtw, dtb, A, a_is_log, ds, du, ddelta, dbc, \
+        FV_LAUNCH_PDL((kern), grid, block, smem, st, g, nplanes_ds, u, xdbl, ldxd, R, dtw, dtb, A, a_is_log, ds, du, ddelta, dbc, \
                                         dA, dbias);                                                                  \
         return finish_launch("scan_bwd");                                                                            \
     }
@@ -698,7 +706,7 @@ static int launch_scan_bwd(const Geom& g, int nplanes_ds, const T* u, const T* x
             cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);      \
             FV_REQUIRE(e == cudaSuccess, "fv_scan_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));            \
         }                                                                                                            \
-        kern<<<grid, block, smem, st>>>(g, nplanes_ds, u, xdbl, ldxd, R, dtw, dtb, A, a_is_log, ds, du, ddelta, dbc, \
+        FV_LAUNCH_PDL((kern), grid, block, smem, st, g, nplanes_ds, u, xdbl, ldxd, R, dtw, dtb, A, a_is_log, ds, du, ddelta, dbc, \
                                         dA, dbias);                                                                  \
         return finish_launch("scan_bwd");                                                                            \
     }
@@ -742,8 +750,8 @@ extern "C" int fv_reduce_planes(int out_dtype, const float* in, int nplanes, int
     FV_REQUIRE(in && out && nplanes >= 1 && n > 0, "fv_reduce_planes: bad arguments");
     dim3 grid((unsigned)((n + 255) / 256)), block(256);
     cudaStream_t st = (cudaStream_t)stream;
-    if (out_dtype == FV_F32) reduce_planes_kernel<float><<<grid, block, 0, st>>>(in, nplanes, n, (float*)out);
-    else if (out_dtype == FV_BF16) reduce_planes_kernel<bf16><<<grid, block, 0, st>>>(in, nplanes, n, (bf16*)out);
+    if (out_dtype == FV_F32) FV_LAUNCH_PDL((reduce_planes_kernel<float>), grid, block, 0, st, in, nplanes, n, (float*)out);
+    else if (out_dtype == FV_BF16) FV_LAUNCH_PDL((reduce_planes_kernel<bf16>), grid, block, 0, st, in, nplanes, n, (bf16*)out);
     else return fail("fv_reduce_planes: unsupported dtype %d", out_dtype);
     return finish_launch("reduce_planes");
 }
@@ -773,7 +781,7 @@ extern "C" int fv_scan_bwd_short(const fv_geom* g_, int dtype, int nplanes_ds, c
         auto kern = g.Lp == 14 ? scan_bwd_short_kernel<float, 14> : scan_bwd_short_kernel<float, 0>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         FV_REQUIRE(e == cudaSuccess, "fv_scan_bwd_short: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        kern<<<grid, block, smem, st>>>(g, nplanes_ds, (const float*)u, (const float*)xdbl, ld_xdbl, dt_rank, delta_pre, A, a_is_log,
+        FV_LAUNCH_PDL((kern), grid, block, smem, st, g, nplanes_ds, (const float*)u, (const float*)xdbl, ld_xdbl, dt_rank, delta_pre, A, a_is_log,
                                         ds, (float*)du, (float*)ddelta, dbc_planes, dA, d_dt_bias);
         return finish_launch("scan_bwd_short");
     }
@@ -781,7 +789,7 @@ extern "C" int fv_scan_bwd_short(const fv_geom* g_, int dtype, int nplanes_ds, c
         auto kern = g.Lp == 14 ? scan_bwd_short_kernel<bf16, 14> : scan_bwd_short_kernel<bf16, 0>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         FV_REQUIRE(e == cudaSuccess, "fv_scan_bwd_short: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        kern<<<grid, block, smem, st>>>(g, nplanes_ds, (const bf16*)u, (const bf16*)xdbl, ld_xdbl, dt_rank, delta_pre, A, a_is_log,
+        FV_LAUNCH_PDL((kern), grid, block, smem, st, g, nplanes_ds, (const bf16*)u, (const bf16*)xdbl, ld_xdbl, dt_rank, delta_pre, A, a_is_log,
                                         ds, (bf16*)du, (bf16*)ddelta, dbc_planes, dA, d_dt_bias);
         return finish_launch("scan_bwd_short");
     }

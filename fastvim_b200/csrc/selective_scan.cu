@@ -46,6 +46,8 @@ selective_scan_fwd_kernel(int batch, int dim, int64_t L, int N, int groups, cons
                           const float* __restrict__ Dp, const T* __restrict__ z,
                           const float* __restrict__ dbias, int softplus, T* __restrict__ out,
                           float* __restrict__ last_state) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int d = blockIdx.x * SS_WARPS + (threadIdx.x >> 5);
     const int b = blockIdx.y;
@@ -162,6 +164,8 @@ selective_scan_bwd_kernel(int batch, int dim, int64_t L, int N, int groups, cons
                           T* __restrict__ du, T* __restrict__ ddelta, float* __restrict__ dA, float* __restrict__ dB,
                           float* __restrict__ dC, float* __restrict__ dD, T* __restrict__ dz,
                           float* __restrict__ ddbias, float* __restrict__ ws) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     constexpr int CH = 32 * SS_ITEMS;
     const int lane = threadIdx.x & 31;
     const int d = blockIdx.x * SS_WARPS + (threadIdx.x >> 5);
@@ -401,9 +405,9 @@ extern "C" int fv_selective_scan_fwd(int dtype, int batch, int dim, int64_t L, i
     }
     dim3 grid(ceil_div(dim, SS_WARPS), batch), block(SS_WARPS * 32);
     if (dtype == FV_F32)
-        selective_scan_fwd_kernel<float><<<grid, block, 0, st>>>(batch, dim, L, dstate, groups, (const float*)u, (const float*)delta, A, (const float*)B, (const float*)C, D, (const float*)z, delta_bias, delta_softplus, (float*)out, last_state);
+        FV_LAUNCH_PDL((selective_scan_fwd_kernel<float>), grid, block, 0, st, batch, dim, L, dstate, groups, (const float*)u, (const float*)delta, A, (const float*)B, (const float*)C, D, (const float*)z, delta_bias, delta_softplus, (float*)out, last_state);
     else if (dtype == FV_BF16)
-        selective_scan_fwd_kernel<bf16><<<grid, block, 0, st>>>(batch, dim, L, dstate, groups, (const bf16*)u, (const bf16*)delta, A, (const bf16*)B, (const bf16*)C, D, (const bf16*)z, delta_bias, delta_softplus, (bf16*)out, last_state);
+        FV_LAUNCH_PDL((selective_scan_fwd_kernel<bf16>), grid, block, 0, st, batch, dim, L, dstate, groups, (const bf16*)u, (const bf16*)delta, A, (const bf16*)B, (const bf16*)C, D, (const bf16*)z, delta_bias, delta_softplus, (bf16*)out, last_state);
     else
         return fail("fv_selective_scan_fwd: unsupported dtype %d", dtype);
     return finish_launch("selective_scan_fwd");
@@ -446,9 +450,9 @@ extern "C" int fv_selective_scan_bwd(int dtype, int batch, int dim, int64_t L, i
     }
     dim3 grid(ceil_div(dim, SS_WARPS), batch), block(SS_WARPS * 32);
     if (dtype == FV_F32)
-        selective_scan_bwd_kernel<float><<<grid, block, 0, st>>>(batch, dim, L, dstate, groups, (const float*)u, (const float*)delta, A, (const float*)B, (const float*)C, D, (const float*)z, delta_bias, delta_softplus, (const float*)dout, (float*)du, (float*)ddelta, dA, dB, dC, dD, (float*)dz, ddelta_bias, (float*)workspace);
+        FV_LAUNCH_PDL((selective_scan_bwd_kernel<float>), grid, block, 0, st, batch, dim, L, dstate, groups, (const float*)u, (const float*)delta, A, (const float*)B, (const float*)C, D, (const float*)z, delta_bias, delta_softplus, (const float*)dout, (float*)du, (float*)ddelta, dA, dB, dC, dD, (float*)dz, ddelta_bias, (float*)workspace);
     else if (dtype == FV_BF16)
-        selective_scan_bwd_kernel<bf16><<<grid, block, 0, st>>>(batch, dim, L, dstate, groups, (const bf16*)u, (const bf16*)delta, A, (const bf16*)B, (const bf16*)C, D, (const bf16*)z, delta_bias, delta_softplus, (const bf16*)dout, (bf16*)du, (bf16*)ddelta, dA, dB, dC, dD, (bf16*)dz, ddelta_bias, (float*)workspace);
+        FV_LAUNCH_PDL((selective_scan_bwd_kernel<bf16>), grid, block, 0, st, batch, dim, L, dstate, groups, (const bf16*)u, (const bf16*)delta, A, (const bf16*)B, (const bf16*)C, D, (const bf16*)z, delta_bias, delta_softplus, (const bf16*)dout, (bf16*)du, (bf16*)ddelta, dA, dB, dC, dD, (bf16*)dz, ddelta_bias, (float*)workspace);
     else
         return fail("fv_selective_scan_bwd: unsupported dtype %d", dtype);
     return finish_launch("selective_scan_bwd");

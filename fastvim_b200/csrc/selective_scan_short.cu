@@ -39,6 +39,8 @@ ss_short_fwd_kernel(int dim, int L, int groups, const T* __restrict__ u, const T
                     const float* __restrict__ A, const T* __restrict__ Bm, const T* __restrict__ Cm,
                     const float* __restrict__ Dp, const T* __restrict__ z, const float* __restrict__ dbias, int softplus,
                     T* __restrict__ out, float* __restrict__ last_state) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     constexpr int N = SSS_N;
     __shared__ __align__(16) float sB[SSS_LMAX * N], sC[SSS_LMAX * N];   // [l][n]
     __shared__ T su[ROWS * SSS_LMAX], sd[ROWS * SSS_LMAX], sz[ROWS * SSS_LMAX];
@@ -112,6 +114,8 @@ ss_short_bwd_kernel(int dim, int L, int groups, const T* __restrict__ u, const T
                     const T* __restrict__ dout, T* __restrict__ du, T* __restrict__ ddelta, float* __restrict__ dA,
                     float* __restrict__ dB, float* __restrict__ dC, float* __restrict__ dD, T* __restrict__ dz,
                     float* __restrict__ ddbias) {
+    pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
+    pdl_trigger();
     constexpr int N = SSS_N, LM = SSS_LMAX, R = SSB_ROWS;
     __shared__ __align__(16) float sB[LM * N], sC[LM * N];            // [l][n]
     __shared__ float su[R * LM], sdl[R * LM], sraw[R * LM], sdy[R * LM], sgo[R * LM], szv[R * LM];   // [r][l] (stride LM)
@@ -278,9 +282,9 @@ int launch_ss_short_fwd(int rows, int batch, int dim, int L, int groups, const T
                         cudaStream_t st) {
     dim3 grid((dim + rows - 1) / rows, batch);
     if (rows == 128)
-        ss_short_fwd_kernel<T, 128><<<grid, 128, 0, st>>>(dim, L, groups, u, delta, A, B, C, D, z, dbias, softplus, out, last);
+        FV_LAUNCH_PDL((ss_short_fwd_kernel<T, 128>), grid, 128, 0, st, dim, L, groups, u, delta, A, B, C, D, z, dbias, softplus, out, last);
     else
-        ss_short_fwd_kernel<T, 32><<<grid, 32, 0, st>>>(dim, L, groups, u, delta, A, B, C, D, z, dbias, softplus, out, last);
+        FV_LAUNCH_PDL((ss_short_fwd_kernel<T, 32>), grid, 32, 0, st, dim, L, groups, u, delta, A, B, C, D, z, dbias, softplus, out, last);
     return finish_launch("selective_scan_fwd[short]");
 }
 template <typename T>
@@ -288,7 +292,7 @@ int launch_ss_short_bwd(int batch, int dim, int L, int groups, const T* u, const
                         const float* D, const T* z, const float* dbias, int softplus, const T* dout, T* du, T* ddelta,
                         float* dA, float* dB, float* dC, float* dD, T* dz, float* ddbias, cudaStream_t st) {
     dim3 grid((dim + SSB_ROWS - 1) / SSB_ROWS, batch);
-    ss_short_bwd_kernel<T><<<grid, SSB_THREADS, 0, st>>>(dim, L, groups, u, delta, A, B, C, D, z, dbias, softplus, dout, du,
+    FV_LAUNCH_PDL((ss_short_bwd_kernel<T>), grid, SSB_THREADS, 0, st, dim, L, groups, u, delta, A, B, C, D, z, dbias, softplus, dout, du,
                                                           ddelta, dA, dB, dC, dD, dz, ddbias);
     return finish_launch("selective_scan_bwd[short]");
 }
