@@ -13,8 +13,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OBJ = os.path.join(ROOT, "fastvim_b200", "build")
 TARGETS = [   # (object file, kernel-name regex, mnemonics of interest)
     ("gemm_tc.cu.o", r"gemm_tc_kernelILi256E", ["UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "UTCBAR", "SYNCS"]),
+    ("gemm_tc2.cu.o", r"gemm_tc2_kernelILi256ELb1ELb1ELb1E", ["UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "UTCBAR"]),
+    ("gemm_out_norm.cu.o", r"gemm_out_norm_kernelILi192ELb1E", ["UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "ATOMG", "LD.E.STRONG.GPU", "LDG.E.STRONG.GPU", "ACQBULK", "UTCBAR"]),
     ("block_cluster.cu.o", r"block_cluster_kernelILi12ELb1ELb1ELb0E", ["HMMA", "LDGSTS", "UCGABAR_ARV", "UCGABAR_WAIT", "MUFU.TANH", "MUFU.EX2", "FFMA2", "CCTL.E.PF2"]),
-    ("block_fwd.cu.o", r"block_fwd_kernelILi14ELb1ELb1ELi12E", ["HMMA", "LDGSTS", "MUFU.TANH", "MUFU.EX2", "FFMA2"]),
+    ("block_fwd.cu.o", r"block_fwd_kernelILi14ELb1ELb1ELi12E", ["HMMA", "LDGSTS", "MUFU.TANH", "MUFU.EX2", "FFMA2", "ACQBULK", "ST.E.STRONG.GPU", "STG.E.STRONG.GPU"]),
     ("gate_bwd_v.cu.o", r"gate_bwd_v_kernelILb1ELi4E", ["MUFU.TANH", "FFMA2", "SHFL", "LDG.E.64", "STG.E.64"]),
     ("peer.cu.o", r"peer_copy_kernel", ["RED.E.ADD", "LDG.E.128", "MEMBAR", "NANOSLEEP"]),
     ("gate.cu.o", r"gate_fwd_kernel.*bf16", ["UBLKCP", "SYNCS"]),
