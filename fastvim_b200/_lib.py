@@ -45,6 +45,9 @@ SIGNATURES = {
     "fv_gemm_bf16_tn": [_L, _I, _I, _P, _L, _P, _L, _P, _P, _L, _P],
     "fv_gemm_supported": [_L, _I, _I],
     "fv_set_pdl": [_I],
+    "fv_conv_pool_w_supported": [_G, _I],
+    "fv_conv_pool_w_fwd": [_G, _I, _P, _L, _L, _P, _P, _F, _I, _P, _P, _P, _P],
+    "fv_gate_w_fwd": [_G, _I, _P, _P, _L, _L, _P, _P, _P, _F, _P, _L, _L, _P],
     "fv_block_fwd_signal_supported": [_G, _I, _I, _I],
     "fv_block_fwd_signal": [_G, _I, _P, _P, _L, _L, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _F, _F, _P, _L, _L,
                             _P, _I, _P],

@@ -107,9 +107,18 @@ __global__ void __launch_bounds__(BK_THREADS, 1) block_fwd_kernel(const BlockArg
     const int cpr = D >> 3;  // 16-byte chunks per token row
     if (img < g.B) {         // first image: every thread fetches its share of the slab
         const bf16* xb = a.x + (int64_t)img * a.xzbs;
-        for (int i = tid; i < L * cpr; i += BK_THREADS) {
-            const int t = i / cpr, c = i - t * cpr;
-            cp_async16(slab + (uint32_t)(t + 3) * rowB + c * 16, xb + ztab[t] + c * 8, true);
+        if (BK_THREADS % cpr == 0) {
+            // a thread keeps its 16-byte column and walks the token rows with a fixed stride: no division in the loop
+            // (the generic form below costs ~50 instructions per chunk, 3 % of the kernel's instructions at 224^2)
+            const int rstep = BK_THREADS / cpr, c = tid % cpr;
+            unsigned char* dst = slab + (uint32_t)(tid / cpr + 3) * rowB + c * 16;
+            const bf16* src = xb + c * 8;
+            for (int t = tid / cpr; t < L; t += rstep, dst += (uint32_t)rstep * rowB) cp_async16(dst, src + ztab[t], true);
+        } else {
+            for (int i = tid; i < L * cpr; i += BK_THREADS) {
+                const int t = i / cpr, c = i - t * cpr;
+                cp_async16(slab + (uint32_t)(t + 3) * rowB + c * 16, xb + ztab[t] + c * 8, true);
+            }
         }
     }
 

@@ -40,6 +40,8 @@ TC_GEMM = os.environ.get("FASTVIM_TC_GEMM", "1") != "0"
 # inference: fold the next block's residual add + RMSNorm into this block's out_proj epilogue (fv_gemm_out_norm) when
 # d_model fits one accumulator (FastVim-T); "0" = separate fv_gemm_bf16_tn + fv_add_norm_fwd launches
 FUSED_OUT_NORM = os.environ.get("FASTVIM_FUSED_OUT_NORM", "1") != "0"
+# channel layouts (inner > 1): fv_conv_pool_w_fwd + fv_gate_w_fwd instead of the generic K1 / K2b; "0" = generic kernels
+GROUP_KERNELS = os.environ.get("FASTVIM_GROUP_KERNELS", "1") != "0"
 # inference: fv_block_fwd_signal + fv_gemm_out_norm_flow (the out_proj GEMM starts on finished images while the block kernel's
 # second round is still running); "0" = the plain pair
 FLOW = os.environ.get("FASTVIM_FLOW", "1") != "0"
@@ -242,6 +244,14 @@ class Mamba(nn.Module):
                               pk["A_neg"], pk["D"], pk["ln_w"], pk["ln_b"], eps, float(self.scaling_factor), R, N,
                               a_is_log=False, xproj_w_packed=pk.get("x_w_packed"), signal=flow if use_flow else None)
             return self._linear_out(y, pk, out_norm, (flow[0], L, flow[1]) if use_flow else None)   # [a10] (+ next [a11])
+        if GROUP_KERNELS and ops.conv_pool_w_supported(geom, B, D, xz.dtype):
+            # channel layouts (inner > 1): staged conv + pool that also writes the D-skip term, streaming gate
+            u, w = ops.conv_pool_w_fwd(x, geom, pk["conv_w"], pk["conv_b"], pk["D"], float(self.scaling_factor),
+                                       self.collapse_method)
+            xdbl = ops.x_proj(u, pk["x_w"], TC_GEMM)
+            s = ops.scan_fwd(u, xdbl, geom, R, N, pk["dt_w"], pk["dt_b"], pk["A_log"], a_is_log=True)
+            y = ops.gate_w_fwd(w, z, s, geom, pk["ln_w"], pk["ln_b"], eps)
+            return self._linear_out(y, pk, out_norm)
         u = ops.conv_pool_fwd(x, geom, pk["conv_w"], pk["conv_b"], float(self.scaling_factor),
                               self.collapse_method)                      # (2, B, Lp, D)         [a3-a5]
         xdbl = ops.x_proj(u, pk["x_w"], TC_GEMM)                         # (2, B*Lp, R+2N)        [a6]

@@ -119,6 +119,44 @@ def conv_pool_fwd(x: Tensor, geom: Geometry, conv_w: Tensor, conv_b: Optional[Te
     return u
 
 
+def conv_pool_w_supported(geom: Geometry, batch: int, dim: int, dtype: torch.dtype) -> bool:
+    """Channel layouts (inner > 1), bf16: the staged conv + pool kernel that also writes the D-skip term."""
+    if dtype != torch.bfloat16:
+        return False
+    g = geom.c_struct(batch, dim)
+    return bool(_lib.lib().fv_conv_pool_w_supported(C.byref(g), FV_BF16))
+
+
+def conv_pool_w_fwd(x: Tensor, geom: Geometry, conv_w: Tensor, conv_b: Optional[Tensor], Dskip: Tensor,
+                    scale: float = 1.0, mode: str = "mean", want_w: bool = True):
+    """K1 for channel layouts.  x (B, L, D) bf16 -> (u (2, B, Lp, D), w (B, L, D) | None): pooled conv output and the
+    D-skip term w = (D_f xc_f + D_b xc_b) / 2 of every token (memory-row order), for ``gate_w_fwd``."""
+    _check_cuda(x, conv_w)
+    B, L, D = x.shape
+    assert L == geom.L and x.dtype == torch.bfloat16
+    ldx, bs = _tokmajor(x, "x")
+    u = torch.empty((2, B, geom.Lp, D), device=x.device, dtype=x.dtype)
+    w = torch.empty((B, L, D), device=x.device, dtype=x.dtype) if want_w else None
+    g = geom.c_struct(B, D)
+    _lib.call("fv_conv_pool_w_fwd", C.byref(g), FV_BF16, _p(x), ldx, bs, _p(conv_w), _p(conv_b), float(scale),
+              FV_POOL_MAX if mode == "max" else FV_POOL_MEAN, _p(Dskip), _p(u), _p(w), _stream(x))
+    return u, w
+
+
+def gate_w_fwd(w: Tensor, z: Tensor, s: Tensor, geom: Geometry, ln_w: Optional[Tensor], ln_b: Optional[Tensor],
+               eps: float = 1e-5) -> Tensor:
+    """K2b from the saved D-skip term: y (B, L, D) = LayerNorm(w + (s_f[j] + s_b[j]) / 2) * silu(z)."""
+    _check_cuda(w, z, s)
+    B, L, D = w.shape
+    assert w.is_contiguous() and w.dtype == torch.bfloat16 and s.dtype == torch.float32 and s.is_contiguous()
+    ldz, bsz = _tokmajor(z, "z")
+    y = torch.empty((B, L, D), device=w.device, dtype=w.dtype)
+    g = geom.c_struct(B, D)
+    _lib.call("fv_gate_w_fwd", C.byref(g), FV_BF16, _p(w), _p(z), ldz, bsz, _p(s), _p(ln_w), _p(ln_b), float(eps), _p(y),
+              y.stride(1), y.stride(0), _stream(w))
+    return y
+
+
 def scan_fwd(u: Tensor, xdbl: Tensor, geom: Geometry, dt_rank: int, d_state: int, dt_w: Tensor,
              dt_bias: Tensor, A: Tensor, a_is_log: bool = False) -> Tensor:
     """K2a.  u (2, B, Lp, D), xdbl (2, B*Lp, >=R+2N) -> s (2, B, Lp, D) fp32 (one plane per direction)."""

@@ -72,6 +72,20 @@ int fv_conv_pool_fwd(const fv_geom* g, int dtype, const void* x, int64_t ldx, in
                      const float* conv_w, const float* conv_b, float scale, int pool_mode,
                      void* u_out, void* stream);
 
+/* K1 / K2b for channel layouts (inner > 1; FastChannelVim Channel-First, mamba_simple_channel_faster.py:225-289, 325-340,
+ * 400-420), bf16: fv_conv_pool_w_fwd = fv_conv_pool_fwd that stages each (image, outer) group of pool*inner consecutive
+ * sequence positions through shared memory and ALSO writes the D-skip term w = (D_f xc_f + D_b xc_b) / 2 of every token
+ * (w_out (B, L, dim) bf16 in memory-row order, or NULL); fv_gate_w_fwd then is a streaming pass
+ * y = LayerNorm(w + (s_f[j] + s_b[j]) / 2) * silu(z) with one warp per token (no convolution is re-evaluated).
+ * Dskip (2, dim) fp32.  fv_conv_pool_w_supported(): bf16, inner >= 2, dim % 8 == 0, dim <= 2048, inner slots fit. */
+int fv_conv_pool_w_supported(const fv_geom* g, int dtype);
+int fv_conv_pool_w_fwd(const fv_geom* g, int dtype, const void* x, int64_t ldx, int64_t x_bstride, const float* conv_w,
+                       const float* conv_b, float scale, int pool_mode, const float* Dskip, void* u_out, void* w_out,
+                       void* stream);
+int fv_gate_w_fwd(const fv_geom* g, int dtype, const void* w, const void* z, int64_t ldz, int64_t z_bstride,
+                  const float* s, const float* ln_w, const float* ln_b, float eps, void* y, int64_t ldy,
+                  int64_t y_bstride, void* stream);
+
 /* ---- K2a: bidirectional selective scan over the pooled sequence, dt_proj fused -----
  * Replaces dt_proj matmul + 2x selective_scan_fn(D=None, z=None, delta_softplus=True)
  * (mamba_simple_faster.py:328-354, 384-410; kernel csrc/selective_scan/selective_scan_fwd_kernel.cuh:67-303).
