@@ -17,6 +17,8 @@ namespace fv {
 
 int sm_count();
 int check_geom(const fv_geom* g, const char* who);
+int conv_pool_plain_w(const Geom& g, const bf16* x, int64_t ldx, int64_t xbs, const float* cw, const float* cb, float scale,
+                      int pool_mode, bf16* u, const float* Dskip, bf16* wout, cudaStream_t st);   // conv_pool.cu
 
 constexpr int CG_MAX_NI = 4;  // inner slots per thread (inner / IH): pool accumulators stay in registers
 
@@ -139,7 +141,9 @@ gate_w_fwd_kernel(Geom g, const bf16* __restrict__ w, const bf16* __restrict__ z
         }
     }
     __syncthreads();
-    const int ntok = g.pool * inner, tbase = o * ntok;
+    // a group may be split over gridDim.z CTAs (few images, long groups: 2048^2 has 128 groups of 128 tokens)
+    const int ntok_all = g.pool * inner, per = (ntok_all + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int lt0 = (int)blockIdx.z * per, ntok = min(ntok_all, lt0 + per), tbase = o * ntok_all;
     const bf16* wimg = w + (int64_t)b * g.L * D;
     const bf16* zimg = z + (int64_t)b * zbs;
     bf16* yimg = y + (int64_t)b * ybs;
@@ -162,8 +166,8 @@ gate_w_fwd_kernel(Geom g, const bf16* __restrict__ w, const bf16* __restrict__ z
             }
         }
     };
-    if (warp < ntok) fetch(warp);
-    for (int lt = warp; lt < ntok; lt += nwarp) {
+    if (lt0 + warp < ntok) fetch(lt0 + warp);
+    for (int lt = lt0 + warp; lt < ntok; lt += nwarp) {
         const int i = lt % inner;
         const float* srow = gw_ssum + i * D;
         const int64_t row_cur = row;
@@ -258,6 +262,7 @@ static GroupPlan plan_group(const fv_geom* g, int dtype) {
 
 extern "C" int fv_conv_pool_w_supported(const fv_geom* g, int dtype) {
     if (!g || g->batch <= 0 || g->dim <= 0 || g->outer <= 0 || g->pool <= 0 || g->inner <= 0 || g->batch > 65535) return 0;
+    if (dtype == FV_BF16 && g->inner == 1) return g->dim % 8 == 0 && g->dim <= 3072;   // staged / cluster kernels of conv_pool.cu
     return fv::plan_group(g, dtype).ok;
 }
 
@@ -267,6 +272,12 @@ extern "C" int fv_conv_pool_w_fwd(const fv_geom* g_, int dtype, const void* x, i
     using namespace fv;
     if (int rc = check_geom(g_, "fv_conv_pool_w_fwd")) return rc;
     FV_REQUIRE(x && conv_w && u_out && (!w_out || Dskip), "fv_conv_pool_w_fwd: null pointer (w_out needs Dskip)");
+    FV_REQUIRE(fv_conv_pool_w_supported(g_, dtype), "fv_conv_pool_w_fwd: unsupported configuration (bf16, dim %% 8 == 0)");
+    if (g_->inner == 1) {
+        FV_REQUIRE(ldx % 8 == 0 && x_bstride % 8 == 0 && ((uintptr_t)x % 16) == 0, "fv_conv_pool_w_fwd: x rows must be 16-byte aligned");
+        return conv_pool_plain_w(make_geom(g_), (const bf16*)x, ldx, x_bstride, conv_w, conv_b, scale, pool_mode, (bf16*)u_out,
+                                 Dskip, (bf16*)w_out, (cudaStream_t)stream);
+    }
     const GroupPlan p = plan_group(g_, dtype);
     FV_REQUIRE(p.ok && g_->batch <= 65535, "fv_conv_pool_w_fwd: unsupported configuration (bf16, inner >= 2, dim %% 8 == 0, dim <= 2048)");
     FV_REQUIRE(ldx % 8 == 0 && x_bstride % 8 == 0 && ((uintptr_t)x % 16) == 0, "fv_conv_pool_w_fwd: x rows must be 16-byte aligned");
@@ -305,7 +316,11 @@ extern "C" int fv_gate_w_fwd(const fv_geom* g_, int dtype, const void* w, const 
     FV_REQUIRE(smem <= 200 * 1024, "fv_gate_w_fwd: inner * dim too large for the staged pooled rows");
     const int ntok = g.pool * g.inner;
     const int warps = ntok >= 16 ? 8 : 4;
-    dim3 grid(g.outer, g.B);
+    int nsplit = (int)((4ll * sm_count() + (int64_t)g.outer * g.B - 1) / ((int64_t)g.outer * g.B));
+    if (nsplit > ntok / (2 * warps)) nsplit = ntok / (2 * warps);   // at least two tokens per warp
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > 64) nsplit = 64;
+    dim3 grid(g.outer, g.B, nsplit);
     const int nv = (g.D / 4 + 31) / 32;
 #define FV_GW2(NV_, NORM_)                                                                                             \
     {                                                                                                                  \

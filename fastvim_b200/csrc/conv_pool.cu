@@ -116,7 +116,7 @@ template <typename T, bool MAXPOOL, int MAXT>
 __global__ void __launch_bounds__(MAXT)
 conv_pool_staged_kernel(Geom g, int TP, int nbuf, int vec16, const T* __restrict__ x, int64_t ldx, int64_t xbs,
                         const float* __restrict__ cw, const float* __restrict__ cb, float scale,
-                        T* __restrict__ u) {
+                        T* __restrict__ u, const float* __restrict__ Dskip, T* __restrict__ wout) {
     pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
     pdl_trigger();
     constexpr bool FAST = is_fast<T>::value;
@@ -142,6 +142,10 @@ conv_pool_staged_kernel(Geom g, int TP, int nbuf, int vec16, const T* __restrict
     const Taps tf = load_taps(cw, cb, g.D, 0, dd, PRE), tb = load_taps(cw, cb, g.D, 1, dd, PRE);
     float4 accf = MAXPOOL ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : zero4();
     float4 accb = accf;
+    // optional second output: the D-skip term w = (D_f xc_f + D_b xc_b) / 2 of every token, for fv_gate_w_fwd
+    const bool want_w = wout != nullptr && live;
+    const float4 Df = want_w ? scale4(ld4(Dskip + dd), 0.5f) : zero4(), Db = want_w ? scale4(ld4(Dskip + g.D + dd), 0.5f) : zero4();
+    T* wimg = want_w ? wout + (int64_t)b * g.L * g.D + dd : nullptr;
     for (int c = 0; c < nchunk; ++c) {
         const int p_lo = c * TP, np = min(TP, g.pool - p_lo);
         if (c + 1 < nchunk) {
@@ -168,6 +172,10 @@ conv_pool_staged_kernel(Geom g, int TP, int nbuf, int vec16, const T* __restrict
                     conv_both_pre<FAST>(r[i], r[i + 1], r[i + 2], r[i + 3], r[i + 4], r[i + 5], r[i + 6], tf, tb, xf, xr);
                     accf = MAXPOOL ? max4(accf, xf) : accf + xf;
                     accb = MAXPOOL ? max4(accb, xr) : accb + xr;
+                    if (want_w)
+                        st4(wimg + (int64_t)rowtab[p_lo + p0 + i + 3] * g.D,
+                            make_float4(fmaf(Db.x, xr.x, Df.x * xf.x), fmaf(Db.y, xr.y, Df.y * xf.y), fmaf(Db.z, xr.z, Df.z * xf.z),
+                                        fmaf(Db.w, xr.w, Df.w * xf.w)));
                 }
             }
         }
@@ -194,7 +202,7 @@ template <typename T, bool MAXPOOL, int MAXT>
 __global__ void __launch_bounds__(MAXT)
 conv_pool_cluster_kernel(Geom g, int NS, int np_seg, int vec16, const T* __restrict__ x, int64_t ldx, int64_t xbs,
                          const float* __restrict__ cw, const float* __restrict__ cb, float scale,
-                         T* __restrict__ u) {
+                         T* __restrict__ u, const float* __restrict__ Dskip, T* __restrict__ wout) {
     pdl_wait();  // PDL: launched while the previous kernel drains; its output is visible from here
     pdl_trigger();
     constexpr bool FAST = is_fast<T>::value;
@@ -223,6 +231,9 @@ conv_pool_cluster_kernel(Geom g, int NS, int np_seg, int vec16, const T* __restr
     const Taps tf = load_taps(cw, cb, g.D, 0, dd, PRE), tb = load_taps(cw, cb, g.D, 1, dd, PRE);
     float4 accf = MAXPOOL ? make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY) : zero4();
     float4 accb = accf;
+    const bool want_w = wout != nullptr && live;
+    const float4 Df = want_w ? scale4(ld4(Dskip + dd), 0.5f) : zero4(), Db = want_w ? scale4(ld4(Dskip + g.D + dd), 0.5f) : zero4();
+    T* wimg = want_w ? wout + (int64_t)b * g.L * g.D + dd : nullptr;
     cp_async_wait<0>();
     __syncthreads();
     for (int p0 = 0; p0 < np; p0 += G) {
@@ -238,6 +249,10 @@ conv_pool_cluster_kernel(Geom g, int NS, int np_seg, int vec16, const T* __restr
                 conv_both_pre<FAST>(r[i], r[i + 1], r[i + 2], r[i + 3], r[i + 4], r[i + 5], r[i + 6], tf, tb, xf, xr);
                 accf = MAXPOOL ? max4(accf, xf) : accf + xf;
                 accb = MAXPOOL ? max4(accb, xr) : accb + xr;
+                if (want_w)
+                    st4(wimg + (int64_t)rowtab[p0 + i + 3] * g.D,
+                        make_float4(fmaf(Db.x, xr.x, Df.x * xf.x), fmaf(Db.y, xr.y, Df.y * xf.y), fmaf(Db.z, xr.z, Df.z * xf.z),
+                                    fmaf(Db.w, xr.w, Df.w * xf.w)));
             }
         }
     }
@@ -266,11 +281,12 @@ conv_pool_cluster_kernel(Geom g, int NS, int np_seg, int vec16, const T* __restr
 
 template <typename T>
 static int launch_conv_pool_cluster(const Geom& g, int NS, const T* x, int64_t ldx, int64_t xbs, const float* cw,
-                                    const float* cb, float scale, int pool_mode, T* u, cudaStream_t st) {
+                                    const float* cb, float scale, int pool_mode, T* u, cudaStream_t st,
+                                    const float* Dskip = nullptr, T* wout = nullptr) {
     const int threads = ((g.D / 4) + 31) / 32 * 32;
     const int np_seg = (g.pool + NS - 1) / NS;
     const size_t smem = (size_t)2 * threads * sizeof(float4) + (size_t)(np_seg + 6) * g.D * sizeof(T) + (size_t)(np_seg + 6) * 4;
-    void (*kern)(Geom, int, int, int, const T*, int64_t, int64_t, const float*, const float*, float, T*);
+    void (*kern)(Geom, int, int, int, const T*, int64_t, int64_t, const float*, const float*, float, T*, const float*, T*);
     const bool mx = pool_mode == FV_POOL_MAX;
     if (threads <= 128) kern = mx ? conv_pool_cluster_kernel<T, true, 128> : conv_pool_cluster_kernel<T, false, 128>;
     else if (threads <= 256) kern = mx ? conv_pool_cluster_kernel<T, true, 256> : conv_pool_cluster_kernel<T, false, 256>;
@@ -294,14 +310,15 @@ static int launch_conv_pool_cluster(const Geom& g, int NS, const T* x, int64_t l
     cfg.attrs = attr;
     cfg.numAttrs = 2;
     const int vec16 = (int)rows_vec16<T>(g.D, x, ldx, xbs);
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, g, NS, np_seg, vec16, x, ldx, xbs, cw, cb, scale, u);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, g, NS, np_seg, vec16, x, ldx, xbs, cw, cb, scale, u, Dskip, wout);
     FV_REQUIRE(e == cudaSuccess, "fv_conv_pool_fwd: cluster launch failed: %s", cudaGetErrorString(e));
     return finish_launch("conv_pool_fwd");
 }
 
 template <typename T>
 static int launch_conv_pool_staged(const Geom& g, const T* x, int64_t ldx, int64_t xbs, const float* cw,
-                                   const float* cb, float scale, int pool_mode, T* u, cudaStream_t st) {
+                                   const float* cb, float scale, int pool_mode, T* u, cudaStream_t st,
+                                   const float* Dskip = nullptr, T* wout = nullptr) {
     const int threads = ((g.D / 4) + 31) / 32 * 32;
     int TP = g.pool < 32 ? g.pool : 32;
     while (TP > 4 && (size_t)2 * (TP + 6) * g.D * sizeof(T) > 96 * 1024) TP /= 2;
@@ -310,7 +327,7 @@ static int launch_conv_pool_staged(const Geom& g, const T* x, int64_t ldx, int64
     const size_t smem = (size_t)nbuf * (TP + 6) * g.D * sizeof(T) + (size_t)(g.pool + 6) * 4;
     FV_REQUIRE(g.Lp <= 2147483647 && g.B <= 65535, "fv_conv_pool_fwd: batch > 65535");
     dim3 grid(g.Lp, g.B), block(threads);
-    void (*kern)(Geom, int, int, int, const T*, int64_t, int64_t, const float*, const float*, float, T*);
+    void (*kern)(Geom, int, int, int, const T*, int64_t, int64_t, const float*, const float*, float, T*, const float*, T*);
     const bool mx = pool_mode == FV_POOL_MAX;
     if (threads <= 128) kern = mx ? conv_pool_staged_kernel<T, true, 128> : conv_pool_staged_kernel<T, false, 128>;
     else if (threads <= 256) kern = mx ? conv_pool_staged_kernel<T, true, 256> : conv_pool_staged_kernel<T, false, 256>;
@@ -320,22 +337,25 @@ static int launch_conv_pool_staged(const Geom& g, const T* x, int64_t ldx, int64
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         FV_REQUIRE(e == cudaSuccess, "fv_conv_pool_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     }
-    FV_LAUNCH_PDL((kern), grid, block, smem, st, g, TP, nbuf, (int)rows_vec16<T>(g.D, x, ldx, xbs), x, ldx, xbs, cw, cb, scale, u);
+    FV_LAUNCH_PDL((kern), grid, block, smem, st, g, TP, nbuf, (int)rows_vec16<T>(g.D, x, ldx, xbs), x, ldx, xbs, cw, cb, scale, u,
+                  Dskip, wout);
     return finish_launch("conv_pool_fwd");
 }
 
 template <typename T>
 static int launch_conv_pool(const Geom& g, const T* x, int64_t ldx, int64_t xbs, const float* cw,
-                            const float* cb, float scale, int pool_mode, T* u, cudaStream_t st) {
+                            const float* cb, float scale, int pool_mode, T* u, cudaStream_t st,
+                            const float* Dskip = nullptr, T* wout = nullptr) {
     if (g.inner == 1 && g.D <= 4096) {
         // long pooled groups, too few (image, pooled position) pairs to fill the GPU: one cluster per position
         if (g.pool >= 32 && (int64_t)g.Lp * g.B < 2 * sm_count() && g.B <= 65535) {
             int NS = 8;
             while (NS > 2 && g.pool / NS < 8) NS >>= 1;
-            return launch_conv_pool_cluster<T>(g, NS, x, ldx, xbs, cw, cb, scale, pool_mode, u, st);
+            return launch_conv_pool_cluster<T>(g, NS, x, ldx, xbs, cw, cb, scale, pool_mode, u, st, Dskip, wout);
         }
-        return launch_conv_pool_staged<T>(g, x, ldx, xbs, cw, cb, scale, pool_mode, u, st);
+        return launch_conv_pool_staged<T>(g, x, ldx, xbs, cw, cb, scale, pool_mode, u, st, Dskip, wout);
     }
+    if (wout) return fail("fv_conv_pool_w_fwd: the D-skip output needs the plain geometry here (inner == 1, dim <= 4096)");
     const int64_t items = (int64_t)g.B * g.Lp * (g.D / 4);
     const int threads = 256;
     const int64_t blocks = (items + threads - 1) / threads;
@@ -353,6 +373,12 @@ static int launch_conv_pool(const Geom& g, const T* x, int64_t ldx, int64_t xbs,
 }
 
 int check_geom(const fv_geom* g, const char* who);
+
+// plain geometry (inner == 1), bf16: the staged / cluster kernels with the D-skip output (fv_conv_pool_w_fwd, conv_gate_w.cu)
+int conv_pool_plain_w(const Geom& g, const bf16* x, int64_t ldx, int64_t xbs, const float* cw, const float* cb, float scale,
+                      int pool_mode, bf16* u, const float* Dskip, bf16* wout, cudaStream_t st) {
+    return launch_conv_pool<bf16>(g, x, ldx, xbs, cw, cb, scale, pool_mode, u, st, Dskip, wout);
+}
 
 }  // namespace fv
 

@@ -34,7 +34,7 @@ def test_conv_pool_w_vs_generic_and_torch(rows, cols, tpp, D, Bt, mode):
 
     geom = ops.Geometry(rows, cols, tpp, cols * tpp, tpp, 1)      # Channel-First: memory order == sequence order
     assert ops.conv_pool_w_supported(geom, Bt, D, torch.bfloat16)
-    assert not ops.conv_pool_w_supported(ops.Geometry.grid(rows, cols), Bt, D, torch.bfloat16)     # inner == 1: other kernels
+    assert not ops.conv_pool_w_supported(geom, Bt, D, torch.float32)                                # bf16 only
     xz, cw, cb, Dk = _inputs(Bt, geom, D)
     x = xz[..., :D]
     u, w = ops.conv_pool_w_fwd(x, geom, cw, cb, Dk, 1.5, mode)
@@ -97,3 +97,25 @@ def test_scan_fwd_chunked_rank24_matches_plain_kernel():
     s_chunk = ops.scan_fwd(u32, x32, geom, R, N, dtw, dtb, A_log, a_is_log=True)
     err = (s_chunk - s_plain).abs().max().item() / s_plain.abs().max().item()
     assert err < 1e-4, err
+
+
+@pytest.mark.parametrize("rows,cols,D,Bt,rot", [(14, 14, 384, 4, False), (14, 14, 384, 3, True), (16, 64, 384, 1, False),
+                                                (128, 128, 384, 1, False), (6, 10, 72, 2, False)])
+def test_plain_geometry_w_path_matches_generic_path(rows, cols, D, Bt, rot):
+    """inner == 1 (FastVim; 2048^2 takes the cluster conv + pool): conv_pool_w -> gate_w against conv_pool -> gate."""
+    from fastvim_b200 import ops
+
+    geom = ops.Geometry.grid(rows, cols, rot)
+    assert ops.conv_pool_w_supported(geom, Bt, D, torch.bfloat16)
+    xz, cw, cb, Dk = _inputs(Bt, geom, D, seed=3)
+    x, z = xz[..., :D], xz[..., D:]
+    u, w = ops.conv_pool_w_fwd(x, geom, cw, cb, Dk, 2.0)
+    u_ref = ops.conv_pool_fwd(x, geom, cw, cb, 2.0)
+    assert torch.equal(u, u_ref)                         # same kernel, one more output
+    torch.manual_seed(4)
+    s = torch.randn(2, Bt, geom.Lp, D).cuda()
+    lw, lb = (1.0 + 0.2 * torch.randn(D)).cuda(), (0.2 * torch.randn(D)).cuda()
+    y = ops.gate_w_fwd(w, z, s, geom, lw, lb, 1e-5)
+    y_ref = ops.gate_fwd(x, z, s, geom, cw, cb, Dk, lw, lb, 1e-5)
+    err = (y.float() - y_ref.float()).abs().max().item() / y_ref.float().abs().max().item()
+    assert err < 2e-2, err
