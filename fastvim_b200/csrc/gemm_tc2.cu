@@ -32,6 +32,7 @@ constexpr uint32_t G2_C_BYTES = 128 * 128;          // staged store: 128 rows x 
 
 struct Gemm2Args {
     int Mo, No, KB, kb_per_split, ntm, ntn, ntiles, nstage, ncstage;
+    int red;   // fp32 output: every split adds its partial sum into the ONE output plane (TMA reduction store) instead of writing its own
 };
 
 // MN-major operand tile, 128-byte swizzle (cute::UMMA canonical layout ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units):
@@ -204,7 +205,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 gt_epi_barrier();
                 if (issuer) {
-                    gt_tma_store_3d(&tmC, stage, n0 + c * CH, m0, split);
+                    if (OUT_F32 && a.red) gt_tma_red_add_3d(&tmC, stage, n0 + c * CH, m0, 0);
+                    else gt_tma_store_3d(&tmC, stage, n0 + c * CH, m0, split);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 if (++cs == NC) cs = 0;
@@ -336,7 +338,10 @@ extern "C" int fv_gemm_bf16(int64_t Mo, int No, int64_t K, int a_mn, const void*
     FV_REQUIRE(A && B && C, "fv_gemm_bf16: null pointer");
     FV_REQUIRE(Mo > 0 && No > 0 && K > 0 && Mo < (1ll << 31) && K < (1ll << 31), "fv_gemm_bf16: bad sizes (%lld x %d x %lld)",
                (long long)Mo, No, (long long)K);
-    FV_REQUIRE(out_dtype == FV_BF16 || out_dtype == FV_F32, "fv_gemm_bf16: out_dtype must be FV_BF16 or FV_F32");
+    FV_REQUIRE(out_dtype == FV_BF16 || out_dtype == FV_F32 || out_dtype == FV_F32_ACC,
+               "fv_gemm_bf16: out_dtype must be FV_BF16, FV_F32 or FV_F32_ACC");
+    const bool red = out_dtype == FV_F32_ACC;
+    if (red) out_dtype = FV_F32;
     const int es_c = out_dtype == FV_F32 ? 4 : 2;
     FV_REQUIRE(lda % 8 == 0 && ldb % 8 == 0 && (ldc * es_c) % 16 == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)B % 16) == 0 &&
                    ((uintptr_t)C % 16) == 0,
@@ -346,7 +351,7 @@ extern "C" int fv_gemm_bf16(int64_t Mo, int No, int64_t K, int a_mn, const void*
     FV_REQUIRE(splits >= 1 && (splits == 1 || out_dtype == FV_F32), "fv_gemm_bf16: split-K needs fp32 output planes");
     const int BN = pick_bn2(No);
     Gemm2Args a;
-    a.Mo = (int)Mo; a.No = No;
+    a.Mo = (int)Mo; a.No = No; a.red = red ? 1 : 0;
     a.KB = (int)((K + G2_BK - 1) / G2_BK);
     FV_REQUIRE(splits <= a.KB, "fv_gemm_bf16: more splits (%d) than k-blocks (%d)", splits, a.KB);
     a.kb_per_split = (a.KB + splits - 1) / splits;
@@ -369,7 +374,7 @@ extern "C" int fv_gemm_bf16(int64_t Mo, int No, int64_t K, int a_mn, const void*
     } else {
         if (int rc = get_tmap(&tmB, B, 2, K, No, 0, ldb, 64, BN)) return rc;
     }
-    if (int rc = get_tmap(&tmC, C, es_c, No, Mo, splits, ldc, out_dtype == FV_F32 ? 32 : 64, G2_BM)) return rc;
+    if (int rc = get_tmap(&tmC, C, es_c, No, Mo, red ? 1 : splits, ldc, out_dtype == FV_F32 ? 32 : 64, G2_BM)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int of = out_dtype == FV_F32 ? 1 : 0;
     if (BN == 256) return dispatch_gemm2<256>(a_mn ? 1 : 0, b_mn ? 1 : 0, of, tmA, tmB, tmC, a, smem, st);

@@ -87,6 +87,12 @@ __device__ __forceinline__ void gt_tma_store_3d(const CUtensorMap* tm, const voi
                  "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
+// TMA reduction store: global[tile] += shared tile (element type and op from the instruction / tensor map: fp32 add)
+__device__ __forceinline__ void gt_tma_red_add_3d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tm),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 __device__ __forceinline__ void gt_epi_barrier() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 // cuTensorMapEncodeTiled fetched at run time (libcuda is not linked: the library must load on machines without a driver)

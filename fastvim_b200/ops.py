@@ -23,6 +23,10 @@ Tensor = torch.Tensor
 GATE_BWD_STREAM = os.environ.get("FASTVIM_GATE_BWD_STREAM", "0") == "1"
 # short pooled sequences (Lp <= 16): fv_scan_bwd_short (two states per thread, dt_proj by GEMM); "0" = previous kernel
 SCAN_BWD_SHORT = os.environ.get("FASTVIM_SCAN_BWD_SHORT", "1") != "0"
+# split-K wgrad GEMMs: "1" = the K splits add into one fp32 output with TMA reduction stores (no workspace planes, no
+# fv_reduce_planes pass; summation order over the splits not fixed), "0" = deterministic planes + reduction
+WGRAD_ACC = os.environ.get("FASTVIM_WGRAD_ACC", "1") != "0"
+WGRAD_ACC_MAX_SPLITS = 4
 
 
 @dataclass(frozen=True)
@@ -380,6 +384,14 @@ def gemm_bf16(a: Tensor, b: Tensor, a_mn: bool = False, b_mn: bool = False, out_
     if splits == 1:
         _lib.call("fv_gemm_bf16", Mo, No, K, int(a_mn), _p(a), a.stride(0), int(b_mn), _p(b), b.stride(0), FV_F32, _p(c), No, 1,
                   _stream(a))
+        return c
+    # Few splits (FastVim-B: 2 / 4): every split adds into the one zeroed output with a TMA reduction store -- no planes, no
+    # second pass (33.2 -> 32.6 ms per training step).  Many splits onto a small output (FastVim-T: 24 / 37 splits onto
+    # <= 590 KB) contend in L2 and measured slower (11.1 vs 10.8 ms), so those keep the deterministic planes.
+    if WGRAD_ACC and splits <= WGRAD_ACC_MAX_SPLITS:
+        c.zero_()
+        _lib.call("fv_gemm_bf16", Mo, No, K, int(a_mn), _p(a), a.stride(0), int(b_mn), _p(b), b.stride(0), 2, _p(c), No,
+                  splits, _stream(a))
         return c
     ws = torch.empty((splits, Mo, No), device=a.device, dtype=torch.float32)
     _lib.call("fv_gemm_bf16", Mo, No, K, int(a_mn), _p(a), a.stride(0), int(b_mn), _p(b), b.stride(0), FV_F32, _p(ws), No,

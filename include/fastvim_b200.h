@@ -30,6 +30,9 @@ extern "C" {
 #endif
 
 typedef enum { FV_F32 = 0, FV_BF16 = 1 } fv_dtype;
+/* fv_gemm_bf16 only: fp32 output that is ADDED to (C += A.B, every K split adds its partial sum with a TMA reduction store;
+ * the caller provides the initial value, e.g. zeros; summation order over the splits is not fixed) */
+#define FV_F32_ACC 2
 typedef enum { FV_POOL_MEAN = 0, FV_POOL_MAX = 1 } fv_pool_mode;
 
 /* Sequence geometry of one mixer call.  The L tokens of an image are viewed as
@@ -250,7 +253,8 @@ int fv_gemm_out_norm_flow(int64_t M, int N, int K, const void* A, int64_t lda, c
  *   a_mn = 0: A stored (Mo x K) row-major;  a_mn = 1: A stored (K x Mo) row-major (used transposed, not copied)
  *   b_mn = 0: B stored (No x K) row-major;  b_mn = 1: B stored (K x No) row-major
  *   out_dtype FV_BF16: C (Mo x No) bf16, splits = 1;  FV_F32: C = `splits` fp32 planes of (Mo x ldc), plane s holding
- *   the partial sum over its own K range (add them with fv_reduce_planes; splits = 1 writes the result itself).
+ *   the partial sum over its own K range (add them with fv_reduce_planes; splits = 1 writes the result itself);
+ *   FV_F32_ACC: one fp32 plane that every split adds into (no workspace, no second pass; not bit-reproducible for > 2 splits).
  * Replaces the cuBLAS calls of the reference's backward (selective_scan_interface.py:698-737 and autograd through
  * in_proj / out_proj): dgrad dX = dY . W (a_mn 0, b_mn 1), wgrad dW = dY^T . X (a_mn 1, b_mn 1, fp32 planes), and the
  * x_proj GEMM with N = dt_rank + 2 d_state (mamba_simple_faster.py:321-323).  Sizes need no padding: TMA zero-fills

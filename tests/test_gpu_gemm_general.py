@@ -54,10 +54,14 @@ def test_gemm_general_vs_fp64(Mo, No, K, a_mn, b_mn, out_f32):
         assert torch.all((padc == 7.0) | (padc == 0.0))
 
 
-def test_gemm_general_split_counts_agree():
-    """Every split count gives the same fp32 result up to summation order."""
+@pytest.mark.parametrize("acc", [True, False])
+def test_gemm_general_split_counts_agree(acc, monkeypatch):
+    """Every split count gives the same fp32 result up to summation order, in both split-K forms: partial planes +
+    fv_reduce_planes (deterministic) and TMA reduction stores into one zeroed plane (FV_F32_ACC)."""
     from fastvim_b200 import ops
 
+    monkeypatch.setattr(ops, "WGRAD_ACC", acc)
+    monkeypatch.setattr(ops, "WGRAD_ACC_MAX_SPLITS", 64)
     torch.manual_seed(3)
     dy, x = _mk(4096, 256, 0.5), _mk(4096, 192, 0.1)
     want = dy.double().t() @ x.double()
