@@ -626,7 +626,10 @@ def run_infer(a, ctx: Ctx, workload: str, main: bool):
                     "traffic": load_traffic(workload, "fv_block_fwd" if top == "fv_block_fwd_signal" else top),
                     "alg_bytes_per_launch": k["alg_bytes"], "avg_us": k["avg_us"], "peak_source": peak_src,
                     "share_of_step": round(k["ms_per_step"] / max(ms_step, (ktot or {}).get("sum_ms") or 0.0), 4),
-                    "timing": "inside the replayed graph step (CUPTI)" if prof is not None else "eager CUDA events"}
+                    "timing": ("CUPTI, replay of the same step captured with programmatic dependent launch off (serialised: the "
+                               "kernel's own duration; in the timed graph it overlaps its neighbours)"
+                               if (prof is not None and pdl_was) else
+                               "inside the replayed graph step (CUPTI)" if prof is not None else "eager CUDA events")}
 
     # ---- sharded 2048^2: the bench's own logits against the CPU oracle ----
     parity = None

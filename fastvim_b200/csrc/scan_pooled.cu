@@ -17,6 +17,8 @@
 // Arithmetic per (b, d, j, dir): delta = softplus(bias + W_dt[d,:] . dt[j,:]);
 //   h[n] = exp2(delta * A[d,n] * log2e) * h[n] + delta * B[j,n] * u[j,d];  y = sum_n h[n] C[j,n]
 // (same exp2 formulation as fwd_kernel.cuh:169-171, 216).  MUFU-bound: N+2 SFU ops per pooled element.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fv {
@@ -82,27 +84,52 @@ scan_fwd_kernel(Geom g, const T* __restrict__ u, const T* __restrict__ xdbl, int
     float* sb = s + dir * plane + (int64_t)b * g.Lp * g.D + dd;
     const int step = dir == 0 ? 1 : -1;
 
+    // The [dt | B | C] rows and the u values of chunk cc + 1 are fetched into registers BEFORE chunk cc is scanned and go to
+    // shared memory after it: with the loads issued right before their use every chunk exposed a full global-memory round
+    // trip (7 chunks on every CTA at FastChannelVim-S: 75 -> 73 us).  Measured dead ends at that shape (49 k chains of 112
+    // steps, 10 warps per SM): splitting a chain's 16 states over 2 / 4 lanes (2x / 4x the warps, shared dt_proj dot product,
+    // butterfly sums) ran 96 / 94 us, the two-pass chunk-parallel kernel below 151 us.
+    constexpr int TPT = (SCAN_LC * WROW + SCAN_THREADS - 1) / SCAN_THREADS;   // tile elements per thread and chunk
+    float tpre[TPT], upre[SCAN_LC];
+    auto fetch = [&](int cc_) {
+        const int chunk_ = dir == 0 ? cc_ : nchunks - 1 - cc_;
+        const int rlo_ = chunk_ * SCAN_LC, rows_ = min(SCAN_LC, g.Lp - rlo_);
+#pragma unroll
+        for (int k = 0; k < TPT; ++k) {
+            const int i = threadIdx.x + k * SCAN_THREADS;
+            const int r = i / WROW, c = i - r * WROW;
+            float v = 0.f;
+            if (i < rows_ * WROW) {
+                if (c < RT) {
+                    if (c < R) v = ld1(xd + (int64_t)(rlo_ + r) * ldxd + c);
+                } else {
+                    v = ld1(xd + (int64_t)(rlo_ + r) * ldxd + R + (c - RT));
+                }
+            }
+            tpre[k] = v;
+        }
+        const int r0_ = dir == 0 ? rlo_ : rlo_ + rows_ - 1;
+#pragma unroll
+        for (int rr = 0; rr < SCAN_LC; ++rr)
+            upre[rr] = (rr < rows_ && live) ? ld1(ub + (int64_t)(r0_ + rr * step) * g.D) : 0.f;
+    };
+    fetch(0);
 #pragma unroll 1
     for (int cc = 0; cc < nchunks; ++cc) {
         const int chunk = dir == 0 ? cc : nchunks - 1 - cc;
         const int r_lo = chunk * SCAN_LC;
         const int rows = min(SCAN_LC, g.Lp - r_lo);
         float(*tl)[WROW] = tile[cc & 1];
-        for (int i = threadIdx.x; i < rows * WROW; i += SCAN_THREADS) {
-            const int r = i / WROW, c = i - r * WROW;
-            float v = 0.f;
-            if (c < RT) {
-                if (c < R) v = ld1(xd + (int64_t)(r_lo + r) * ldxd + c);
-            } else {
-                v = ld1(xd + (int64_t)(r_lo + r) * ldxd + R + (c - RT));
-            }
-            tl[r][c] = v;
+#pragma unroll
+        for (int k = 0; k < TPT; ++k) {
+            const int i = threadIdx.x + k * SCAN_THREADS;
+            if (i < SCAN_LC * WROW) (&tl[0][0])[i] = tpre[k];
         }
         const int r0 = dir == 0 ? r_lo : r_lo + rows - 1;
         float uu[SCAN_LC];
 #pragma unroll
-        for (int rr = 0; rr < SCAN_LC; ++rr)
-            uu[rr] = (rr < rows && live) ? ld1(ub + (int64_t)(r0 + rr * step) * g.D) : 0.f;
+        for (int rr = 0; rr < SCAN_LC; ++rr) uu[rr] = upre[rr];
+        if (cc + 1 < nchunks) fetch(cc + 1);
         __syncthreads();  // one barrier per chunk: tile[] is double-buffered
 #pragma unroll
         for (int rr = 0; rr < SCAN_LC; ++rr) {
@@ -280,7 +307,6 @@ scan_fwd_chunked_kernel(Geom g, int nch, const T* __restrict__ u, const T* __res
 
 int check_geom(const fv_geom* g, const char* who);
 int sm_count();
-
 template <typename T, int N>
 static int launch_scan_chunked(const Geom& g, const T* u, const T* xdbl, int64_t ldxd, int R, const float* dtw,
                                const float* dtb, const float* A, int a_is_log, float* s, cudaStream_t st, bool* done) {
