@@ -45,6 +45,7 @@ SIGNATURES = {
     "fv_gemm_bf16_tn": [_L, _I, _I, _P, _L, _P, _L, _P, _P, _L, _P],
     "fv_gemm_supported": [_L, _I, _I],
     "fv_set_pdl": [_I],
+    "fv_set_pdl_all": [_I],
     "fv_conv_pool_w_supported": [_G, _I],
     "fv_conv_pool_w_fwd": [_G, _I, _P, _L, _L, _P, _P, _F, _I, _P, _P, _P, _P],
     "fv_gate_w_fwd": [_G, _I, _P, _P, _L, _L, _P, _P, _P, _F, _P, _L, _L, _P],
@@ -150,3 +151,19 @@ def launch_count() -> int:
 
 def reset_launch_count() -> None:
     lib().fv_reset_launch_count()
+
+
+class pdl_all:
+    """``with pdl_all():`` -- programmatic dependent launch for every kernel of the library inside the block (process-wide
+    switch, restored on exit).  ``FASTVIM_TRAIN_PDL=1`` makes the training path (``fastvim_b200.autograd``) use it."""
+
+    def __init__(self, on: bool = True):
+        self.on = on
+
+    def __enter__(self):
+        self.prev = int(lib().fv_set_pdl_all(1 if self.on else 0))
+        return self
+
+    def __exit__(self, *exc):
+        lib().fv_set_pdl_all(self.prev)
+        return False

@@ -16,7 +16,7 @@ import torch.nn.functional as F
 
 import os
 
-from . import ops
+from . import _lib, ops
 
 # streaming gate backward from the saved pre-norm value (csrc/gate_bwd_v.cu); "0" = round-1 recomputing kernel
 GATE_BWD_V = os.environ.get("FASTVIM_GATE_BWD_V", "1") != "0"
@@ -24,6 +24,9 @@ GATE_BWD_V = os.environ.get("FASTVIM_GATE_BWD_V", "1") != "0"
 # allow.  Parity-green, but eight tiny launches per block (one 128-row tile wide, a few k-blocks deep) measured SLOWER than
 # the four cuBLAS bmm calls they replace (FastVim-B step 34.4 vs 33.1 ms), so they are opt-in ("1").
 TC_SMALL_GEMM = os.environ.get("FASTVIM_TC_SMALL_GEMM", "0") == "1"
+# programmatic dependent launch for every kernel of the training forward / backward: measured between -0.6 % and +3.6 % on
+# the FastVim-B / -T step, i.e. inside the run-to-run spread of the training line (+-2 %); opt-in until it is measured at N > 1
+TRAIN_PDL = os.environ.get("FASTVIM_TRAIN_PDL", "0") == "1"
 
 
 def _mm_f32(a, b):
@@ -51,6 +54,22 @@ def _tc():
     return _mixer.TC_GEMM
 
 
+def _train_pdl(fn):
+    """With ``FASTVIM_TRAIN_PDL=1`` the training forward / backward bodies run with programmatic dependent launch on for
+    every kernel (``_lib.pdl_all``): the ~145 launches of a step overlap their prologues with the previous kernel's tail.
+    CUDA tensors only (CPU stand-in tests never load the library)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(ctx, *args):
+        t = next((a for a in args if isinstance(a, torch.Tensor)), None)
+        if TRAIN_PDL and t is not None and t.is_cuda:
+            with _lib.pdl_all():
+                return fn(ctx, *args)
+        return fn(ctx, *args)
+    return wrapped
+
+
 def _dgrad(dy2, w):
     """dX (M, K') = dY (M, N') @ W (N', K'): tcgen05 GEMM with W read as an MN-major operand (no transpose copy)."""
     if _tc() and ops.gemm_bf16_ok(dy2, w):
@@ -67,6 +86,7 @@ def _wgrad(dy2, x2):
 
 class MixerFn(torch.autograd.Function):
     @staticmethod
+    @_train_pdl
     def forward(ctx, h, in_w, in_b, conv_w, conv_b, x_w, dt_w, dt_b, A_log, Dk, ln_w, ln_b, out_w, out_b,
                 geom, scale, eps, d_state, dt_rank):
         """h (B, L, dm) act dtype; in_w (2D, dm), out_w (dm, D), x_w (2, R+2N, D): MASTER weights (fp32 under autocast) --
@@ -106,6 +126,7 @@ class MixerFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_train_pdl
     def backward(ctx, dout):
         (h, in_w, conv_w, conv_b, x_w, dt_w, dt_b, A_log, Dk, ln_w, ln_b, out_w, xz, u, xdbl, s, y, v, pre) = ctx.saved_tensors
         geom, scale, eps, N, R, has_in_b, has_out_b, w_dtypes = ctx.meta
@@ -197,6 +218,7 @@ def mixer_forward_train(mixer, hidden_states, geom, act_dtype):
 
 class AddNormFn(torch.autograd.Function):
     @staticmethod
+    @_train_pdl
     def forward(ctx, x, weight, bias, residual, eps, prenorm, is_rms):
         w = weight.float()
         b = None if bias is None else bias.float()
@@ -210,6 +232,7 @@ class AddNormFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_train_pdl
     def backward(ctx, dy, *rest):
         res_out, w = ctx.saved_tensors
         eps, is_rms, has_bias, x_dtype, has_res, prenorm, res_dtype, w_dtype = ctx.meta

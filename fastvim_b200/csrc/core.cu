@@ -80,6 +80,11 @@ int check_geom(const fv_geom* g, const char* who) {
 }  // namespace fv
 
 extern "C" const char* fv_last_error(void) { return fv::g_err; }
+extern "C" int fv_set_pdl_all(int on) {
+    const int prev = fv::g_pdl_all > 0 ? 1 : 0;
+    fv::g_pdl_all = on ? 1 : 0;
+    return prev;
+}
 extern "C" int fv_set_pdl(int on) {
     const int prev = fv::pdl_enabled() ? 1 : 0;
     fv::g_pdl = on ? 1 : 0;

@@ -59,6 +59,10 @@ int fv_version(void);
  * captures a second, serialised graph with it off to read per-kernel durations that do not include the wait for the
  * predecessor. */
 int fv_set_pdl(int on);
+/* The same attribute for every other kernel of the library (default off: FASTVIM_PDL_ALL=1 or this call; returns the previous
+ * setting).  Measured: -1..2 % on FastVim-S/B inference, +0.7 % at 2048^2, within the run-to-run spread on the training step
+ * (FASTVIM_TRAIN_PDL=1 switches it on around the Python training path's forward and backward). */
+int fv_set_pdl_all(int on);
 int64_t fv_launch_count(void);
 void fv_reset_launch_count(void);
 
