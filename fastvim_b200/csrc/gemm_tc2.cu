@@ -32,6 +32,7 @@ constexpr uint32_t G2_C_BYTES = 128 * 128;          // staged store: 128 rows x 
 
 struct Gemm2Args {
     int Mo, No, KB, kb_per_split, ntm, ntn, ntiles, nstage, ncstage;
+    int nbatch, splits;   // tile = (batch, split, row tile, column block); operands and C carry `nbatch` planes
     int red;   // fp32 output: every split adds its partial sum into the ONE output plane (TMA reduction store) instead of writing its own
 };
 
@@ -93,7 +94,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             int st = 0;
             uint32_t ph = 0;
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-                const int split = tile / per_split, rem = tile - split * per_split;
+                const int bs = tile / per_split, batch = bs / a.splits, split = bs - batch * a.splits, rem = tile - bs * per_split;
                 const int m0 = (rem / a.ntn) * G2_BM, n0 = (rem % a.ntn) * BN;
                 const int kb0 = split * a.kb_per_split, kb1 = min(a.KB, kb0 + a.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -103,16 +104,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                     const int k0 = kb * G2_BK;
                     if (A_MN) {
 #pragma unroll
-                        for (int i = 0; i < G2_BM / 64; ++i) gt_tma_2d(stg + i * 8192, &tmA, m0 + 64 * i, k0, &full[st]);
+                        for (int i = 0; i < G2_BM / 64; ++i) gt_tma_3d(stg + i * 8192, &tmA, m0 + 64 * i, k0, batch, &full[st]);
                     } else {
-                        gt_tma_2d(stg, &tmA, k0, m0, &full[st]);
+                        gt_tma_3d(stg, &tmA, k0, m0, batch, &full[st]);
                     }
                     if (B_MN) {
 #pragma unroll
                         for (int j = 0; j < BN / 64; ++j)
-                            gt_tma_2d(stg + G2_A_BYTES + j * 8192, &tmB, n0 + 64 * j, k0, &full[st]);
+                            gt_tma_3d(stg + G2_A_BYTES + j * 8192, &tmB, n0 + 64 * j, k0, batch, &full[st]);
                     } else {
-                        gt_tma_2d(stg + G2_A_BYTES, &tmB, k0, n0, &full[st]);
+                        gt_tma_3d(stg + G2_A_BYTES, &tmB, k0, n0, batch, &full[st]);
                     }
                     if (++st == NS) { st = 0; ph ^= 1u; }
                 }
@@ -129,7 +130,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             uint32_t ph = 0, aph = 0;
             const uint32_t s_u = smem_u32(sAB);
             for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-                const int split = tile / per_split;
+                const int split = (tile / per_split) % a.splits;
                 const int kb0 = split * a.kb_per_split, kb1 = min(a.KB, kb0 + a.kb_per_split);
                 gt_mbar_wait(&acc_empty[as], aph ^ 1u);
                 tc_fence_after();
@@ -162,7 +163,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         int as = 0, cs = 0;
         uint32_t aph = 0;
         for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
-            const int split = tile / per_split, rem = tile - split * per_split;
+            const int bs = tile / per_split, rem = tile - bs * per_split;   // bs = batch * splits + split = output plane
             const int m0 = (rem / a.ntn) * G2_BM, n0 = (rem % a.ntn) * BN;
             gt_mbar_wait(&acc_full[as], aph);
             tc_fence_after();
@@ -205,8 +206,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 gt_epi_barrier();
                 if (issuer) {
-                    if (OUT_F32 && a.red) gt_tma_red_add_3d(&tmC, stage, n0 + c * CH, m0, 0);
-                    else gt_tma_store_3d(&tmC, stage, n0 + c * CH, m0, split);
+                    if (OUT_F32 && a.red) gt_tma_red_add_3d(&tmC, stage, n0 + c * CH, m0, bs / a.splits);
+                    else gt_tma_store_3d(&tmC, stage, n0 + c * CH, m0, bs);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 if (++cs == NC) cs = 0;
@@ -229,20 +230,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 // ---- host ------------------------------------------------------------------------------------------------------
 struct Tm2Key {
     const void* base;
-    int64_t d0, d1, d2, ld;
+    int64_t d0, d1, d2, ld, ps;
     int b0, b1, es;
     bool operator==(const Tm2Key& o) const {
-        return base == o.base && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && ld == o.ld && b0 == o.b0 && b1 == o.b1 && es == o.es;
+        return base == o.base && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && ld == o.ld && ps == o.ps && b0 == o.b0 && b1 == o.b1 &&
+               es == o.es;
     }
 };
 // Tensor map over a row-major matrix (d1 rows x d0 columns, row pitch ld elements of es bytes) with d2 planes of d1 * ld
 // elements; box = (b0 columns x b1 rows x 1 plane), 128-byte swizzle, out-of-range elements read as zero / are not written.
-int get_tmap(CUtensorMap* out, const void* base, int es, int64_t d0, int64_t d1, int64_t d2, int64_t ld, int b0, int b1) {
+int get_tmap(CUtensorMap* out, const void* base, int es, int64_t d0, int64_t d1, int64_t d2, int64_t ld, int b0, int b1,
+             int64_t plane_stride) {
+    if (plane_stride <= 0) plane_stride = d1 * ld;
     constexpr int NCACHE = 192;
     static thread_local Tm2Key keys[NCACHE];
     static thread_local CUtensorMap maps[NCACHE];
     static thread_local int used = 0, next = 0;
-    const Tm2Key k{base, d0, d1, d2, ld, b0, b1, es};
+    const Tm2Key k{base, d0, d1, d2, ld, plane_stride, b0, b1, es};
     for (int i = 0; i < used; ++i)
         if (keys[i] == k) {
             *out = maps[i];
@@ -252,7 +256,7 @@ int get_tmap(CUtensorMap* out, const void* base, int es, int64_t d0, int64_t d1,
     if (!encode) return 1;
     const bool three = d2 > 0;
     cuuint64_t dims[3] = {(cuuint64_t)d0, (cuuint64_t)d1, (cuuint64_t)(three ? d2 : 1)};
-    cuuint64_t strides[2] = {(cuuint64_t)(ld * es), (cuuint64_t)(d1 * ld * es)};
+    cuuint64_t strides[2] = {(cuuint64_t)(ld * es), (cuuint64_t)(plane_stride * es)};
     cuuint32_t box[3] = {(cuuint32_t)b0, (cuuint32_t)b1, 1u};
     cuuint32_t estr[3] = {1u, 1u, 1u};
     CUtensorMap m;
@@ -332,9 +336,29 @@ extern "C" int fv_gemm_bf16_splits(int64_t Mo, int No, int64_t K) {
     return (int)s;
 }
 
+namespace fv {
+static int gemm2_impl(int nbatch, int64_t Mo, int No, int64_t K, int a_mn, const void* A, int64_t lda, int64_t a_bs, int b_mn,
+                      const void* B, int64_t ldb, int64_t b_bs, int out_dtype, void* C, int64_t ldc, int64_t c_bs, int splits,
+                      void* stream);
+}
 extern "C" int fv_gemm_bf16(int64_t Mo, int No, int64_t K, int a_mn, const void* A, int64_t lda, int b_mn, const void* B,
                             int64_t ldb, int out_dtype, void* C, int64_t ldc, int splits, void* stream) {
-    using namespace fv;
+    return fv::gemm2_impl(1, Mo, No, K, a_mn, A, lda, 0, b_mn, B, ldb, 0, out_dtype, C, ldc, 0, splits, stream);
+}
+// `nbatch` independent products in one launch: operand / result b starts a_bs / b_bs / c_bs ELEMENTS after b - 1 (multiples of
+// 8); no split-K.  Used for the two directions of x_proj (mamba_simple_faster.py:321-323, 377-379).
+extern "C" int fv_gemm_bf16_batched(int nbatch, int64_t Mo, int No, int64_t K, int a_mn, const void* A, int64_t lda, int64_t a_bs,
+                                    int b_mn, const void* B, int64_t ldb, int64_t b_bs, int out_dtype, void* C, int64_t ldc,
+                                    int64_t c_bs, void* stream) {
+    FV_REQUIRE(nbatch >= 1 && nbatch <= 65535 && a_bs % 8 == 0 && b_bs % 8 == 0 && c_bs % 8 == 0 && a_bs > 0 && b_bs > 0 && c_bs > 0,
+               "fv_gemm_bf16_batched: batch count / strides (multiples of 8 elements) invalid");
+    FV_REQUIRE(out_dtype == FV_BF16 || out_dtype == FV_F32, "fv_gemm_bf16_batched: out_dtype must be FV_BF16 or FV_F32");
+    return fv::gemm2_impl(nbatch, Mo, No, K, a_mn, A, lda, a_bs, b_mn, B, ldb, b_bs, out_dtype, C, ldc, c_bs, 1, stream);
+}
+namespace fv {
+static int gemm2_impl(int nbatch, int64_t Mo, int No, int64_t K, int a_mn, const void* A, int64_t lda, int64_t a_bs, int b_mn,
+                      const void* B, int64_t ldb, int64_t b_bs, int out_dtype, void* C, int64_t ldc, int64_t c_bs, int splits,
+                      void* stream) {
     FV_REQUIRE(A && B && C, "fv_gemm_bf16: null pointer");
     FV_REQUIRE(Mo > 0 && No > 0 && K > 0 && Mo < (1ll << 31) && K < (1ll << 31), "fv_gemm_bf16: bad sizes (%lld x %d x %lld)",
                (long long)Mo, No, (long long)K);
@@ -351,30 +375,32 @@ extern "C" int fv_gemm_bf16(int64_t Mo, int No, int64_t K, int a_mn, const void*
     FV_REQUIRE(splits >= 1 && (splits == 1 || out_dtype == FV_F32), "fv_gemm_bf16: split-K needs fp32 output planes");
     const int BN = pick_bn2(No);
     Gemm2Args a;
-    a.Mo = (int)Mo; a.No = No; a.red = red ? 1 : 0;
+    a.Mo = (int)Mo; a.No = No; a.red = red ? 1 : 0; a.nbatch = nbatch; a.splits = splits;
     a.KB = (int)((K + G2_BK - 1) / G2_BK);
     FV_REQUIRE(splits <= a.KB, "fv_gemm_bf16: more splits (%d) than k-blocks (%d)", splits, a.KB);
     a.kb_per_split = (a.KB + splits - 1) / splits;
     FV_REQUIRE((int64_t)a.kb_per_split * (splits - 1) < a.KB, "fv_gemm_bf16: split count %d leaves an empty split (use fv_gemm_bf16_splits)", splits);
     a.ntm = (int)((Mo + G2_BM - 1) / G2_BM);
     a.ntn = (No + BN - 1) / BN;
-    const int64_t nt = (int64_t)a.ntm * a.ntn * splits;
+    const int64_t nt = (int64_t)a.ntm * a.ntn * splits * nbatch;
     FV_REQUIRE(nt < (1ll << 31), "fv_gemm_bf16: too many tiles");
     a.ntiles = (int)nt;
     size_t smem = 0;
     FV_REQUIRE(plan_smem2(BN, &a.nstage, &a.ncstage, &smem), "fv_gemm_bf16: no shared-memory plan for BN = %d", BN);
     CUtensorMap tmA, tmB, tmC;
     if (a_mn) {
-        if (int rc = get_tmap(&tmA, A, 2, Mo, K, 0, lda, 64, 64)) return rc;
+        if (int rc = get_tmap(&tmA, A, 2, Mo, K, nbatch, lda, 64, 64, a_bs)) return rc;
     } else {
-        if (int rc = get_tmap(&tmA, A, 2, K, Mo, 0, lda, 64, G2_BM)) return rc;
+        if (int rc = get_tmap(&tmA, A, 2, K, Mo, nbatch, lda, 64, G2_BM, a_bs)) return rc;
     }
     if (b_mn) {
-        if (int rc = get_tmap(&tmB, B, 2, No, K, 0, ldb, 64, 64)) return rc;
+        if (int rc = get_tmap(&tmB, B, 2, No, K, nbatch, ldb, 64, 64, b_bs)) return rc;
     } else {
-        if (int rc = get_tmap(&tmB, B, 2, K, No, 0, ldb, 64, BN)) return rc;
+        if (int rc = get_tmap(&tmB, B, 2, K, No, nbatch, ldb, 64, BN, b_bs)) return rc;
     }
-    if (int rc = get_tmap(&tmC, C, es_c, No, Mo, red ? 1 : splits, ldc, out_dtype == FV_F32 ? 32 : 64, G2_BM)) return rc;
+    if (int rc = get_tmap(&tmC, C, es_c, No, Mo, nbatch * (red ? 1 : splits), ldc, out_dtype == FV_F32 ? 32 : 64, G2_BM,
+                          nbatch > 1 ? c_bs : 0))
+        return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int of = out_dtype == FV_F32 ? 1 : 0;
     if (BN == 256) return dispatch_gemm2<256>(a_mn ? 1 : 0, b_mn ? 1 : 0, of, tmA, tmB, tmC, a, smem, st);
@@ -382,3 +408,4 @@ extern "C" int fv_gemm_bf16(int64_t Mo, int No, int64_t K, int a_mn, const void*
     if (BN == 128) return dispatch_gemm2<128>(a_mn ? 1 : 0, b_mn ? 1 : 0, of, tmA, tmB, tmC, a, smem, st);
     return dispatch_gemm2<64>(a_mn ? 1 : 0, b_mn ? 1 : 0, of, tmA, tmB, tmC, a, smem, st);
 }
+}  // namespace fv

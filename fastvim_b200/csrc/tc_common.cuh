@@ -26,6 +26,12 @@ __device__ __forceinline__ void gt_tma_2d(void* dst, const CUtensorMap* tm, int 
         ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void gt_tma_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -102,6 +108,7 @@ typedef CUresult (*TmEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, vo
 TmEncodeFn tm_encode_fn();
 // gemm_tc2.cu: cached tensor map over a row-major (d1 rows x d0 columns [x d2 planes]) matrix of es-byte elements, row pitch
 // ld elements, box (b0 columns x b1 rows), 128-byte swizzle; d2 = 0 -> 2-D map
-int get_tmap(CUtensorMap* out, const void* base, int es, int64_t d0, int64_t d1, int64_t d2, int64_t ld, int b0, int b1);  // gemm_tc.cu; null (with the error text set) when the driver entry point is missing
+int get_tmap(CUtensorMap* out, const void* base, int es, int64_t d0, int64_t d1, int64_t d2, int64_t ld, int b0, int b1,
+             int64_t plane_stride = 0 /* elements; 0 = d1 * ld */);  // gemm_tc.cu; null (with the error text set) when the driver entry point is missing
 
 }  // namespace fv

@@ -445,7 +445,7 @@ def gemm_out_norm(a: Tensor, w: Tensor, residual: Tensor, norm_w: Tensor, eps: f
 
 def x_proj(u: Tensor, x_w: Tensor, use_tc: bool = True) -> Tensor:
     """[dt | B | C] = u W_x^T per direction (``mamba_simple_faster.py:321-323, 377-379``).
-    u (2, B, Lp, D), x_w (2, R+2N, D) -> xdbl (2, B*Lp, R+2N).  bf16 on the GPU: two launches of the general tcgen05 GEMM
+    u (2, B, Lp, D), x_w (2, R+2N, D) -> xdbl (2, B*Lp, R+2N).  bf16 on the GPU: one batched launch of the general tcgen05 GEMM
     (ragged N = 44 / 56 / 80) writing into a buffer whose row pitch is rounded up to 16 bytes (the result is a view of it;
     the scan kernels take the pitch).  Otherwise ``torch.bmm``."""
     _, B, Lp, D = u.shape
@@ -454,8 +454,8 @@ def x_proj(u: Tensor, x_w: Tensor, use_tc: bool = True) -> Tensor:
             and u.is_contiguous() and x_w.is_contiguous():
         ld = (ncols + 7) // 8 * 8
         buf = torch.empty((2, M, ld), device=u.device, dtype=u.dtype)
-        for d in range(2):
-            gemm_bf16(u[d].view(M, D), x_w[d], out=buf[d][:, :ncols])
+        _lib.call("fv_gemm_bf16_batched", 2, M, ncols, D, 0, _p(u), D, M * D, 0, _p(x_w), D, ncols * D, FV_BF16, _p(buf), ld,
+                  M * ld, _stream(u))     # both directions in one launch
         return buf[..., :ncols]
     return torch.bmm(u.reshape(2, M, D), x_w.transpose(1, 2))
 

@@ -147,3 +147,22 @@ def test_block_to_out_proj_dataflow_is_bit_identical(batch, monkeypatch):
         outs[flow] = o
     assert torch.isfinite(outs[True]).all()
     assert torch.equal(outs[True], outs[False])
+
+
+@pytest.mark.parametrize("Bt,Lp,D,ncols", [(2, 14, 384, 44), (1, 128, 384, 44), (3, 112, 768, 56), (256, 14, 1536, 80)])
+def test_x_proj_batched_gemm_vs_fp64(Bt, Lp, D, ncols):
+    """Both directions of x_proj in ONE launch of the general tcgen05 GEMM (fv_gemm_bf16_batched, ragged N, padded row
+    pitch) against fp64 (mamba_simple_faster.py:321-323, 377-379)."""
+    from fastvim_b200 import _lib, ops
+
+    torch.manual_seed(Bt + Lp)
+    u = (torch.randn(2, Bt, Lp, D) * 0.5).bfloat16().cuda()
+    xw = (torch.randn(2, ncols, D) * D ** -0.5).bfloat16().cuda()
+    _lib.reset_launch_count()
+    xdbl = ops.x_proj(u, xw)
+    assert _lib.launch_count() == 1
+    want = torch.bmm(u.view(2, Bt * Lp, D).double(), xw.double().transpose(1, 2))
+    assert xdbl.shape == (2, Bt * Lp, ncols)
+    err = (xdbl.double() - want).abs().max().item() / want.abs().max().item()
+    assert err < 4e-3, err
+    assert torch.equal(xdbl, ops.x_proj(u, xw))          # deterministic

@@ -487,8 +487,8 @@ def test_mixer_bf16_fused_and_four_launch_agree_with_oracle(fused, monkeypatch):
         _lib.reset_launch_count()
         out = m(h.cuda())
     # in_proj and out_proj run on the library's tcgen05 GEMM (2 launches); the interior is 1 fused launch, or
-    # conv+pool, x_proj (general tcgen05 GEMM, one launch per direction), scan, gate = 5
-    assert _lib.launch_count() == (3 if fused else 7)
+    # conv+pool, x_proj (general tcgen05 GEMM, both directions in one batched launch), scan, gate = 4
+    assert _lib.launch_count() == (3 if fused else 6)
     assert_close(out, O.mixer_oracle(h, p, (14, 14)), TOL[torch.bfloat16], "mixer bf16")
 
 
