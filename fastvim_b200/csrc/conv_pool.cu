@@ -16,6 +16,8 @@
 // HBM-bound by design: algorithmic bytes = B*L*D*s read + 2*B*Lp*D*s written.
 #include <cooperative_groups.h>
 
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace fv {
@@ -349,8 +351,11 @@ static int launch_conv_pool(const Geom& g, const T* x, int64_t ldx, int64_t xbs,
     if (g.inner == 1 && g.D <= 4096) {
         // long pooled groups, too few (image, pooled position) pairs to fill the GPU: one cluster per position
         if (g.pool >= 32 && (int64_t)g.Lp * g.B < 2 * sm_count() && g.B <= 65535) {
+            // cluster size: enough CTAs to fill the GPU, but one wave (5 CTAs / SM by registers).  2048^2 (128 pooled rows of
+            // 128 tokens), measured: 8 CTAs per row (1024 CTAs, 1.4 waves) 19.8 us, 4 (512) 14.4 us, 2 (256) 18.3 us
             int NS = 8;
-            while (NS > 2 && g.pool / NS < 8) NS >>= 1;
+            while (NS > 2 && (g.pool / NS < 8 || (int64_t)g.Lp * g.B * NS > 5ll * sm_count())) NS >>= 1;
+            if (const char* e = getenv("FASTVIM_CONV_CLUSTER_NS")) NS = atoi(e) == 4 ? 4 : (atoi(e) == 2 ? 2 : 8);   // A/B timing
             return launch_conv_pool_cluster<T>(g, NS, x, ldx, xbs, cw, cb, scale, pool_mode, u, st, Dskip, wout);
         }
         return launch_conv_pool_staged<T>(g, x, ldx, xbs, cw, cb, scale, pool_mode, u, st, Dskip, wout);
