@@ -171,11 +171,10 @@ scan_fwd_kernel(Geom g, const T* __restrict__ u, const T* __restrict__ xdbl, int
 //   pass 2  the chunk is scanned again from the true start state, producing y.
 // Critical path 2*CL + NCH steps instead of Lp, and NCH times more warps to hide latency.  delta is computed once
 // (pass 1) and kept in registers for pass 2.
-constexpr int SCK_CH = 32;   // channels per CTA
 constexpr int SCK_CL = 16;   // steps per chunk
 
-template <typename T, int RT, int N>
-__global__ void __launch_bounds__(SCK_CH * 16)
+template <typename T, int RT, int N, int CH>
+__global__ void __launch_bounds__(CH * 16)
 scan_fwd_chunked_kernel(Geom g, int nch, const T* __restrict__ u, const T* __restrict__ xdbl, int64_t ldxd, int R,
                         const float* __restrict__ dtw, const float* __restrict__ dtb,
                         const float* __restrict__ A, int a_is_log, float* __restrict__ s) {
@@ -184,11 +183,11 @@ scan_fwd_chunked_kernel(Geom g, int nch, const T* __restrict__ u, const T* __res
     constexpr int WROW = RT + 2 * N;
     extern __shared__ __align__(16) float sck_smem[];
     float* tile = sck_smem;                                    // [Lp][WROW]   dt | B | C rows of this image / direction
-    float* carry = tile + (size_t)g.Lp * WROW;                 // [nch][SCK_CH][N]  local end states
-    float* sumd = carry + (size_t)nch * SCK_CH * N;            // [nch][SCK_CH]     sum of delta per chunk
+    float* carry = tile + (size_t)g.Lp * WROW;                 // [nch][CH][N]  local end states
+    float* sumd = carry + (size_t)nch * CH * N;            // [nch][CH]     sum of delta per chunk
     const int dir = blockIdx.z, b = blockIdx.y;
-    const int c = threadIdx.x & (SCK_CH - 1), k = threadIdx.x / SCK_CH;   // channel in CTA, chunk
-    const int d = blockIdx.x * SCK_CH + c;
+    const int c = threadIdx.x & (CH - 1), k = threadIdx.x / CH;   // channel in CTA, chunk
+    const int d = blockIdx.x * CH + c;
     const bool live = d < g.D;
     const int dd = live ? d : 0;
     const int64_t plane = (int64_t)g.B * g.Lp * g.D;
@@ -287,18 +286,18 @@ scan_fwd_chunked_kernel(Geom g, int nch, const T* __restrict__ u, const T* __res
         }
     }
     {
-        float* cp = carry + ((size_t)k * SCK_CH + c) * N;
+        float* cp = carry + ((size_t)k * CH + c) * N;
 #pragma unroll
         for (int n = 0; n < N; n += 4) *reinterpret_cast<float4*>(cp + n) = make_float4(h[n], h[n + 1], h[n + 2], h[n + 3]);
-        sumd[k * SCK_CH + c] = sd;
+        sumd[k * CH + c] = sd;
     }
     __syncthreads();
     // ---- combine: start state of chunk k = fold of chunks 0..k-1 (in scan order)
 #pragma unroll
     for (int n = 0; n < N; ++n) h[n] = 0.f;
     for (int kk = 0; kk < k; ++kk) {
-        const float sdk = sumd[kk * SCK_CH + c];
-        const float* cp = carry + ((size_t)kk * SCK_CH + c) * N;
+        const float sdk = sumd[kk * CH + c];
+        const float* cp = carry + ((size_t)kk * CH + c) * N;
 #pragma unroll
         for (int n = 0; n < N; n += 4) {
             const float4 Sq = *reinterpret_cast<const float4*>(cp + n);
@@ -339,20 +338,32 @@ static int launch_scan_chunked(const Geom& g, const T* u, const T* xdbl, int64_t
     const int nch = ceil_div(g.Lp, SCK_CL);
     if (R > 24 || nch < 2 || nch > 16) return 0;   // <= 512 threads (128 registers each)
     const int RT = R <= 8 ? 8 : (R <= 12 ? 12 : (R <= 16 ? 16 : 24));
-    const size_t smem = ((size_t)g.Lp * (RT + 2 * N) + (size_t)nch * SCK_CH * N + (size_t)nch * SCK_CH) * sizeof(float);
+    // channels per CTA.  Fewer channels per CTA put more SMs to work (2048^2, 384 channels x 2 directions: 32 channels = 24
+    // CTAs, 16 = 48, 8 = 96) but measured 15.8 / 16.0 / 19.2 us: the kernel is bound by each CTA's dependent chain (stage ->
+    // pass 1 -> fold -> pass 2), not by the number of SMs, so 32 stays.
+    int CH = 32;
+    if (const char* e = getenv("FASTVIM_SCAN_CHUNK_CH")) CH = atoi(e) == 8 ? 8 : (atoi(e) == 16 ? 16 : 32);   // A/B timing
+    const size_t smem = ((size_t)g.Lp * (RT + 2 * N) + (size_t)nch * CH * N + (size_t)nch * CH) * sizeof(float);
     if (smem > 200 * 1024) return 0;
-    dim3 grid(ceil_div(g.D, SCK_CH), g.B, 2), block(SCK_CH * nch);
-#define FV_SCK_CASE(RT_)                                                                                              \
-    if (RT == RT_) {                                                                                                  \
+    dim3 grid(ceil_div(g.D, CH), g.B, 2), block(CH * nch);
+#define FV_SCK_LAUNCH(RT_, CH_)                                                                                       \
+    {                                                                                                                 \
+        auto kern = scan_fwd_chunked_kernel<T, RT_, N, CH_>;                                                          \
         if (smem > 48 * 1024) {                                                                                       \
-            cudaError_t e = cudaFuncSetAttribute(scan_fwd_chunked_kernel<T, RT_, N>,                                  \
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);             \
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
             FV_REQUIRE(e == cudaSuccess, "fv_scan_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));             \
         }                                                                                                             \
-        FV_LAUNCH_PDL((scan_fwd_chunked_kernel<T, RT_, N>), grid, block, smem, st, g, nch, u, xdbl, ldxd, R, dtw, dtb, A, a_is_log, s); \
+        FV_LAUNCH_PDL((kern), grid, block, smem, st, g, nch, u, xdbl, ldxd, R, dtw, dtb, A, a_is_log, s);             \
+    }
+#define FV_SCK_CASE(RT_)                         \
+    if (RT == RT_) {                             \
+        if (CH == 32) FV_SCK_LAUNCH(RT_, 32)     \
+        else if (CH == 16) FV_SCK_LAUNCH(RT_, 16) \
+        else FV_SCK_LAUNCH(RT_, 8)               \
     }
     FV_SCK_CASE(8) FV_SCK_CASE(12) FV_SCK_CASE(16) FV_SCK_CASE(24)
 #undef FV_SCK_CASE
+#undef FV_SCK_LAUNCH
     *done = true;
     return finish_launch("scan_fwd_chunked");
 }
