@@ -44,6 +44,16 @@ __device__ __forceinline__ float softplus_fast(float x) {
     return x <= 20.f ? sp : x;
 }
 
+// raw element -> fp32.  Prefetches keep the RAW loaded values in registers and convert at the point of use: with ld1()
+// (load + convert) the compiler placed each convert right behind its load and re-used one register for successive loads, so
+// the "independent" prefetch loads were issued one memory round trip apart (ncu SASS view: every SHF.L after an LDG.U16
+// stalled on the long scoreboard, 47 % of all stall samples of scan_fwd at FastChannelVim-S).
+__device__ __forceinline__ float raw2f(float v) { return v; }
+__device__ __forceinline__ float raw2f(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T raw_zero();
+template <> __device__ __forceinline__ float raw_zero<float>() { return 0.f; }
+template <> __device__ __forceinline__ bf16 raw_zero<bf16>() { return __ushort_as_bfloat16((unsigned short)0); }
+
 constexpr int SCAN_THREADS = 128;
 constexpr int SCAN_LC = 16;  // pooled rows per chunk
 
@@ -90,7 +100,7 @@ scan_fwd_kernel(Geom g, const T* __restrict__ u, const T* __restrict__ xdbl, int
     // steps, 10 warps per SM): splitting a chain's 16 states over 2 / 4 lanes (2x / 4x the warps, shared dt_proj dot product,
     // butterfly sums) ran 96 / 94 us, the two-pass chunk-parallel kernel below 151 us.
     constexpr int TPT = (SCAN_LC * WROW + SCAN_THREADS - 1) / SCAN_THREADS;   // tile elements per thread and chunk
-    float tpre[TPT], upre[SCAN_LC];
+    T tpre[TPT], upre[SCAN_LC];
     auto fetch = [&](int cc_) {
         const int chunk_ = dir == 0 ? cc_ : nchunks - 1 - cc_;
         const int rlo_ = chunk_ * SCAN_LC, rows_ = min(SCAN_LC, g.Lp - rlo_);
@@ -98,12 +108,12 @@ scan_fwd_kernel(Geom g, const T* __restrict__ u, const T* __restrict__ xdbl, int
         for (int k = 0; k < TPT; ++k) {
             const int i = threadIdx.x + k * SCAN_THREADS;
             const int r = i / WROW, c = i - r * WROW;
-            float v = 0.f;
+            T v = raw_zero<T>();
             if (i < rows_ * WROW) {
                 if (c < RT) {
-                    if (c < R) v = ld1(xd + (int64_t)(rlo_ + r) * ldxd + c);
+                    if (c < R) v = __ldg(xd + (int64_t)(rlo_ + r) * ldxd + c);
                 } else {
-                    v = ld1(xd + (int64_t)(rlo_ + r) * ldxd + R + (c - RT));
+                    v = __ldg(xd + (int64_t)(rlo_ + r) * ldxd + R + (c - RT));
                 }
             }
             tpre[k] = v;
@@ -111,7 +121,7 @@ scan_fwd_kernel(Geom g, const T* __restrict__ u, const T* __restrict__ xdbl, int
         const int r0_ = dir == 0 ? rlo_ : rlo_ + rows_ - 1;
 #pragma unroll
         for (int rr = 0; rr < SCAN_LC; ++rr)
-            upre[rr] = (rr < rows_ && live) ? ld1(ub + (int64_t)(r0_ + rr * step) * g.D) : 0.f;
+            upre[rr] = (rr < rows_ && live) ? __ldg(ub + (int64_t)(r0_ + rr * step) * g.D) : raw_zero<T>();
     };
     fetch(0);
 #pragma unroll 1
@@ -123,12 +133,12 @@ scan_fwd_kernel(Geom g, const T* __restrict__ u, const T* __restrict__ xdbl, int
 #pragma unroll
         for (int k = 0; k < TPT; ++k) {
             const int i = threadIdx.x + k * SCAN_THREADS;
-            if (i < SCAN_LC * WROW) (&tl[0][0])[i] = tpre[k];
+            if (i < SCAN_LC * WROW) (&tl[0][0])[i] = raw2f(tpre[k]);
         }
         const int r0 = dir == 0 ? r_lo : r_lo + rows - 1;
         float uu[SCAN_LC];
 #pragma unroll
-        for (int rr = 0; rr < SCAN_LC; ++rr) uu[rr] = upre[rr];
+        for (int rr = 0; rr < SCAN_LC; ++rr) uu[rr] = raw2f(upre[rr]);
         if (cc + 1 < nchunks) fetch(cc + 1);
         __syncthreads();  // one barrier per chunk: tile[] is double-buffered
 #pragma unroll
@@ -250,10 +260,15 @@ scan_fwd_chunked_kernel(Geom g, int nch, const T* __restrict__ u, const T* __res
     // scan position p = k*CL + i  <->  pooled row j = dir ? Lp-1-p : p
     const int p0 = k * SCK_CL, steps = max(0, min(SCK_CL, Lp - p0));
     float uu[SCK_CL], dl[SCK_CL];
+    {
+        T uraw[SCK_CL];   // all loads first, conversions after (see raw2f)
 #pragma unroll
-    for (int i = 0; i < SCK_CL; ++i) {
-        const int p = p0 + i, j = dir ? Lp - 1 - p : p;
-        uu[i] = (i < steps && live) ? ld1(ub + (int64_t)j * g.D) : 0.f;
+        for (int i = 0; i < SCK_CL; ++i) {
+            const int p = p0 + i, j = dir ? Lp - 1 - p : p;
+            uraw[i] = (i < steps && live) ? __ldg(ub + (int64_t)j * g.D) : raw_zero<T>();
+        }
+#pragma unroll
+        for (int i = 0; i < SCK_CL; ++i) uu[i] = raw2f(uraw[i]);
     }
     __syncthreads();
     // ---- pass 1: local scan from zero
