@@ -508,35 +508,61 @@ scan_bwd_short_body(const Geom& g, int nplanes_ds, const T* __restrict__ u, cons
     constexpr float LOG2E = 1.4426950408889634f;
     const float2 araw = *reinterpret_cast<const float2*>(A + ((int64_t)dir * g.D + dd) * N + 2 * p);   // latency hidden below
 
-    // ---- B / C of the image's pooled rows
+    // ---- B / C of the image's pooled rows and the row records.  Every global load of the prologue is issued BEFORE the first
+    // conversion / store (raw values in registers): written as load -> convert -> store per item, each of the ~4 items of
+    // a thread cost a full memory round trip and the prologue was half of the kernel (ncu SASS view: 31 % of all stall
+    // samples on the converts / adds right behind these loads).
     const T* xd = xdbl + ((int64_t)dir * g.B + b) * Lp * ldxd + R;
-    for (int i = tid; i < Lp * 8; i += S2_THREADS) {
-        const int r = i >> 3, pp = i & 7;
-        const T* row = xd + (int64_t)r * ldxd;
-        s_bc[r * 8 + pp] = make_float4(ld1(row + 2 * pp), ld1(row + 2 * pp + 1), ld1(row + N + 2 * pp), ld1(row + N + 2 * pp + 1));
+    constexpr int NIT = (S2_LP * S2_CH + S2_THREADS - 1) / S2_THREADS;   // (row, channel) items per thread: 2
+    T bcraw[4];
+    const bool bc_live = tid < Lp * 8;
+    {
+        const int r = tid >> 3, pp = tid & 7;
+        const T* row = xd + (int64_t)(bc_live ? r : 0) * ldxd;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) bcraw[q] = __ldg(row + (q >> 1) * N + 2 * pp + (q & 1));
     }
-    // row records: (row, channel) pairs spread over the CTA with the channel fastest -- 128-byte coalesced row segments
-    for (int i = tid; i < Lp * S2_CH; i += S2_THREADS) {
+    float pvr[NIT], dsr[NIT][4];
+    T ur[NIT];
+    int64_t off[NIT];
+    bool it_live[NIT];
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) {
+        const int i = tid + k * S2_THREADS;
         const int r = i >> 5, cc = i & 31;
         const int dch = blockIdx.x * S2_CH + cc;
-        float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
-        float pv = 0.f;
-        if (dch < g.D) {
-            const int64_t o = ((int64_t)b * Lp + r) * g.D + dch;
-            pv = pre[dir * plane + o];
-            const float uv = ld1(u + dir * plane + o);
-            float dyv = 0.f;
-            for (int q0 = 0; q0 < nplanes_ds; q0 += 4) {   // the planes' loads are independent: issue four at a time
-                float v[4];
+        it_live[k] = i < Lp * S2_CH && dch < g.D;
+        off[k] = it_live[k] ? ((int64_t)b * Lp + r) * g.D + dch : 0;
+        pvr[k] = it_live[k] ? __ldg(pre + dir * plane + off[k]) : 0.f;
+        ur[k] = __ldg(u + dir * plane + off[k]);
 #pragma unroll
-                for (int q = 0; q < 4; ++q) v[q] = q0 + q < nplanes_ds ? ds[(q0 + q) * plane + o] : 0.f;
-                dyv += (v[0] + v[1]) + (v[2] + v[3]);
+        for (int q = 0; q < 4; ++q) dsr[k][q] = (it_live[k] && q < nplanes_ds) ? __ldg(ds + q * plane + off[k]) : 0.f;
+    }
+    if (bc_live)
+        s_bc[tid] = make_float4(ld1(&bcraw[0]), ld1(&bcraw[1]), ld1(&bcraw[2]), ld1(&bcraw[3]));
+#pragma unroll
+    for (int k = 0; k < NIT; ++k) {
+        const int i = tid + k * S2_THREADS;
+        if (i < Lp * S2_CH) {
+            const int r = i >> 5, cc = i & 31;
+            float4 rec = make_float4(0.f, 0.f, 0.f, 0.f);
+            float pv = 0.f;
+            if (it_live[k]) {
+                pv = pvr[k];
+                const float uv = ld1(&ur[k]);
+                float dyv = (dsr[k][0] + dsr[k][1]) + (dsr[k][2] + dsr[k][3]);
+                for (int q0 = 4; q0 < nplanes_ds; q0 += 4) {   // more than four planes: not the training path's case
+                    float v[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) v[q] = q0 + q < nplanes_ds ? ds[(q0 + q) * plane + off[k]] : 0.f;
+                    dyv += (v[0] + v[1]) + (v[2] + v[3]);
+                }
+                const float delta = s2_softplus(pv);
+                rec = make_float4(delta, delta * uv, dyv, uv);
             }
-            const float delta = s2_softplus(pv);
-            rec = make_float4(delta, delta * uv, dyv, uv);
+            s_rowd[cc * Lp + r] = rec;
+            s_prer[cc * Lp + r] = pv;
         }
-        s_rowd[cc * Lp + r] = rec;
-        s_prer[cc * Lp + r] = pv;
     }
     const float2 Anat = a_is_log ? make_float2(-expf(araw.x), -expf(araw.y)) : araw;
     const float2 A2 = make_float2(Anat.x * LOG2E, Anat.y * LOG2E);
