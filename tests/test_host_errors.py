@@ -115,3 +115,72 @@ def test_random_masking_properties_cpu():
     # odd-layer id rotation: rotating a 4 x 6 grid twice (with swapped sizes) is the identity
     r1, r2 = Block_masked.compute_rotate_indices(4, 6), Block_masked.compute_rotate_indices(6, 4)
     assert torch.equal(r2[r1], torch.arange(24))
+
+
+def test_round2_entry_points_validate_arguments_without_launching():
+    """The round-2 entry points (general tcgen05 GEMM, out_proj + norm epilogue, dataflow pair, streaming K1 / K2b) reject bad
+    arguments with a status code and a message before anything touches the device (runs without a GPU)."""
+    l = _lib.lib()
+    null = None
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    # general GEMM
+    assert l.fv_gemm_bf16(128, 64, 64, 0, null, 64, 0, null, 64, _lib.FV_BF16, null, 64, 1, null) != 0
+    assert b"null pointer" in l.fv_last_error()
+    assert l.fv_gemm_bf16(128, 64, 64, 0, p, 60, 0, p, 64, _lib.FV_BF16, p, 64, 1, null) != 0      # lda % 8
+    assert b"16-byte" in l.fv_last_error()
+    assert l.fv_gemm_bf16(128, 64, 64, 0, p, 64, 0, p, 64, _lib.FV_BF16, p, 64, 2, null) != 0      # split-K needs fp32 planes
+    assert b"split-K" in l.fv_last_error()
+    assert l.fv_gemm_bf16(128, 64, 64, 0, p, 64, 0, p, 64, 7, p, 64, 1, null) != 0                 # unknown output type
+    assert l.fv_gemm_bf16(128, 64, 128, 0, p, 128, 0, p, 128, _lib.FV_F32, p, 64, 3, null) != 0    # 3 splits > 2 k-blocks
+    assert b"splits" in l.fv_last_error()
+    assert l.fv_gemm_bf16_batched(0, 128, 64, 64, 0, p, 64, 8192, 0, p, 64, 4096, _lib.FV_BF16, p, 64, 8192, null) != 0
+    assert l.fv_gemm_bf16_batched(2, 128, 64, 64, 0, p, 64, 8191, 0, p, 64, 4096, _lib.FV_BF16, p, 64, 8192, null) != 0
+    # split heuristic: fills the SMs, never leaves an empty split
+    for Mo, No, K in [(768, 192, 50176), (3072, 768, 25088), (44, 1536, 1792), (128, 64, 64)]:
+        s = l.fv_gemm_bf16_splits(Mo, No, K)
+        kb = (K + 63) // 64
+        assert 1 <= s <= 64 and ((kb + s - 1) // s) * (s - 1) < kb
+    # out_proj + add + RMSNorm epilogue: the row must fit one accumulator
+    assert l.fv_gemm_out_norm_supported(50176, 192, 384) == 1
+    assert l.fv_gemm_out_norm_supported(50176, 384, 768) == 0
+    assert l.fv_gemm_out_norm_supported(50176, 192, 100) == 0
+    assert l.fv_gemm_out_norm(128, 192, 384, null, 384, null, 384, null, 192, null, null, 1e-5, null, 192, null) != 0
+    assert b"null pointer" in l.fv_last_error()
+    assert l.fv_gemm_out_norm_flow(392, 192, 384, p, 384, p, 384, p, 192, null, p, 1e-5, p, 192, null, 196, 0, null) != 0
+    assert b"sync" in l.fv_last_error()
+    # dataflow form of the block kernel: one-CTA-per-image configurations only, flags + positive epoch required
+    g_t = _lib.fv_geom(4, 384, 14, 14, 1, 14, 1, 0)
+    g_b = _lib.fv_geom(4, 1536, 14, 14, 1, 14, 1, 0)
+    assert l.fv_block_fwd_signal_supported(ctypes.byref(g_t), _lib.FV_BF16, 12, 16) == 1
+    assert l.fv_block_fwd_signal_supported(ctypes.byref(g_b), _lib.FV_BF16, 48, 16) == 0          # cluster kernel: no flags
+    assert l.fv_block_fwd_signal(ctypes.byref(g_t), _lib.FV_BF16, p, p, 768, 150528, p, null, p, null, p, p, p, 0, 12, 16, p,
+                                 null, null, 1e-5, 1.0, p, 384, 75264, null, 1, null) != 0
+    assert b"done_flags" in l.fv_last_error()
+    # streaming K1 / K2b: bf16; channel layouts need their inner slots to fit
+    g_ch = _lib.fv_geom(2, 768, 14, 14, 8, 112, 8, 1)
+    assert l.fv_conv_pool_w_supported(ctypes.byref(g_ch), _lib.FV_BF16) == 1
+    assert l.fv_conv_pool_w_supported(ctypes.byref(g_ch), _lib.FV_F32) == 0
+    assert l.fv_conv_pool_w_supported(ctypes.byref(g_t), _lib.FV_BF16) == 1                       # plain geometry: staged kernels
+    g_wide = _lib.fv_geom(2, 4096, 14, 14, 8, 112, 8, 1)
+    assert l.fv_conv_pool_w_supported(ctypes.byref(g_wide), _lib.FV_BF16) == 0
+    assert l.fv_conv_pool_w_fwd(ctypes.byref(g_ch), _lib.FV_BF16, p, 768, 1204224, p, null, 1.0, 0, null, p, p, null) != 0
+    assert b"Dskip" in l.fv_last_error()
+    assert l.fv_gate_w_fwd(ctypes.byref(g_ch), _lib.FV_F32, p, p, 1536, 2408448, p, null, null, 1e-5, p, 768, 1204224, null) != 0
+    assert b"bf16" in l.fv_last_error()
+    # PDL switches return the previous setting
+    prev = l.fv_set_pdl(0)
+    assert l.fv_set_pdl(prev) == 0
+    assert l.fv_set_pdl_all(1) in (0, 1) and l.fv_set_pdl_all(0) == 1
+
+
+def test_x_proj_and_gemm_helpers_fall_back_on_cpu():
+    """Host logic of the round-2 wrappers that must not touch the library for CPU tensors (stand-in based tests rely on it)."""
+    from fastvim_b200 import ops
+
+    u = torch.randn(2, 3, 5, 16)
+    xw = torch.randn(2, 7, 16)
+    got = ops.x_proj(u, xw)
+    assert torch.allclose(got, torch.bmm(u.view(2, 15, 16), xw.transpose(1, 2)))
+    assert not ops.gemm_bf16_ok(torch.zeros(4, 8, dtype=torch.bfloat16))            # CPU tensor
+    assert not ops.conv_pool_w_supported(Geometry(4, 6, 3, 18, 3, 1), 2, 64, torch.float32)
