@@ -57,7 +57,7 @@ SIGNATURES = {
     "fv_gemm_out_norm": [_L, _I, _I, _P, _L, _P, _L, _P, _L, _P, _P, _F, _P, _L, _P],
     "fv_gemm_bf16": [_L, _I, _L, _I, _P, _L, _I, _P, _L, _I, _P, _L, _I, _P],
     "fv_gemm_bf16_splits": [_L, _I, _L],
-    "fv_gemm_bf16_batched": [_I, _L, _I, _L, _I, _P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _L, _P],
+    "fv_gemm_bf16_batched": [_I, _L, _I, _L, _I, _P, _L, _L, _I, _P, _L, _L, _I, _P, _L, _L, _I, _P],
     "fv_ln_gate_fwd": [_I, _L, _I, _P, _L, _P, _L, _P, _P, _F, _P, _L, _P],
     "fv_peer_header_bytes": [],
     "fv_peer_sum_f32": [_I, _I, _P, _L, _L, _P, _P, _P],

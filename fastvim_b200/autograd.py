@@ -20,10 +20,12 @@ from . import _lib, ops
 
 # streaming gate backward from the saved pre-norm value (csrc/gate_bwd_v.cu); "0" = round-1 recomputing kernel
 GATE_BWD_V = os.environ.get("FASTVIM_GATE_BWD_V", "1") != "0"
-# x_proj / dt_proj backward GEMMs (N or K = dt_rank, dt_rank + 2 d_state) on the general tcgen05 GEMM where row pitches
-# allow.  Parity-green, but eight tiny launches per block (one 128-row tile wide, a few k-blocks deep) measured SLOWER than
-# the four cuBLAS bmm calls they replace (FastVim-B step 34.4 vs 33.1 ms), so they are opt-in ("1").
-TC_SMALL_GEMM = os.environ.get("FASTVIM_TC_SMALL_GEMM", "0") == "1"
+# x_proj / dt_proj backward GEMMs (N or K = dt_rank, dt_rank + 2 d_state) on the general tcgen05 GEMM where every row pitch is a
+# multiple of 16 bytes (FastVim-S/B: dt_rank 24 / 48; FastVim-T's dt_rank 12 keeps cuBLAS bmm): four batched launches (both
+# directions each), the two wgrad ones accumulating their K splits with TMA reduction stores.  Step time equals the four
+# cuBLAS bmm calls (FastVim-B: 32.08 vs 32.09 ms); the first form -- eight single launches + plane reductions -- was 1.25 ms
+# slower.  "0" = cuBLAS.
+TC_SMALL_GEMM = os.environ.get("FASTVIM_TC_SMALL_GEMM", "1") != "0"
 # programmatic dependent launch for every kernel of the training forward / backward: measured between -0.6 % and +3.6 % on
 # the FastVim-B / -T step, i.e. inside the run-to-run spread of the training line (+-2 %); opt-in until it is measured at N > 1
 TRAIN_PDL = os.environ.get("FASTVIM_TRAIN_PDL", "0") == "1"
@@ -155,19 +157,16 @@ class MixerFn(torch.autograd.Function):
         u2 = u.view(2, B * Lp, D)
         ncols = R + 2 * N
         dt_w_a = dt_w.to(dt)
-        if (TC_SMALL_GEMM and _tc() and R % 8 == 0 and ops.gemm_bf16_ok(ddelta2[0], u2[0], xdbl[0], x_w[0], dt_w_a[0])):
+        if (TC_SMALL_GEMM and _tc() and R % 8 == 0 and xdbl.stride(0) % 8 == 0
+                and ops.gemm_bf16_ok(ddelta2[0], u2[0], xdbl[0], x_w[0], dt_w_a[0])):
             # x_proj / dt_proj backward on the general tcgen05 GEMM (FastVim-S/B: every row pitch is a multiple of 16 bytes)
+            # four batched launches (both directions each); the wgrad ones accumulate their K splits with TMA reduction stores
             dxdbl = torch.empty((2, B * Lp, ncols), device=u.device, dtype=dt)
             dxdbl[..., R:] = dbc
-            d_dt_w = torch.empty((2, D, R), device=u.device, dtype=torch.float32)
-            d_x_w = torch.empty((2, ncols, D), device=u.device, dtype=torch.float32)
-            du_total = torch.empty((2, B * Lp, D), device=u.device, dtype=dt)
-            for d in range(2):
-                ops.gemm_bf16(ddelta2[d], dt_w_a[d], b_mn=True, out=dxdbl[d][:, :R])                          # ddt
-                ops.gemm_bf16(ddelta2[d], xdbl[d][:, :R], a_mn=True, b_mn=True, out_f32=True, out=d_dt_w[d])
-                ops.gemm_bf16(dxdbl[d], u2[d], a_mn=True, b_mn=True, out_f32=True, out=d_x_w[d])
-                ops.gemm_bf16(dxdbl[d], x_w[d], b_mn=True, out=du_total[d])
-            d_x_w = d_x_w.to(x_w_dt)
+            ops.gemm_bf16_batched(ddelta2, dt_w_a, b_mn=True, out=dxdbl[..., :R])                               # ddt
+            d_dt_w = ops.gemm_bf16_batched(ddelta2, xdbl[..., :R], a_mn=True, b_mn=True, out_f32=True)          # (2, D, R)
+            d_x_w = ops.gemm_bf16_batched(dxdbl, u2, a_mn=True, b_mn=True, out_f32=True).to(x_w_dt)             # (2, R+2N, D)
+            du_total = ops.gemm_bf16_batched(dxdbl, x_w, b_mn=True)                                             # (2, B*Lp, D)
             du_total = du_total.add_(du.view(2, B * Lp, D)).view(2, B, Lp, D)
         else:
             ddt = torch.bmm(ddelta2, dt_w_a)                                        # (2, B*Lp, R)

@@ -349,11 +349,14 @@ extern "C" int fv_gemm_bf16(int64_t Mo, int No, int64_t K, int a_mn, const void*
 // 8); no split-K.  Used for the two directions of x_proj (mamba_simple_faster.py:321-323, 377-379).
 extern "C" int fv_gemm_bf16_batched(int nbatch, int64_t Mo, int No, int64_t K, int a_mn, const void* A, int64_t lda, int64_t a_bs,
                                     int b_mn, const void* B, int64_t ldb, int64_t b_bs, int out_dtype, void* C, int64_t ldc,
-                                    int64_t c_bs, void* stream) {
-    FV_REQUIRE(nbatch >= 1 && nbatch <= 65535 && a_bs % 8 == 0 && b_bs % 8 == 0 && c_bs % 8 == 0 && a_bs > 0 && b_bs > 0 && c_bs > 0,
-               "fv_gemm_bf16_batched: batch count / strides (multiples of 8 elements) invalid");
-    FV_REQUIRE(out_dtype == FV_BF16 || out_dtype == FV_F32, "fv_gemm_bf16_batched: out_dtype must be FV_BF16 or FV_F32");
-    return fv::gemm2_impl(nbatch, Mo, No, K, a_mn, A, lda, a_bs, b_mn, B, ldb, b_bs, out_dtype, C, ldc, c_bs, 1, stream);
+                                    int64_t c_bs, int splits, void* stream) {
+    FV_REQUIRE(nbatch >= 1 && nbatch <= 65535 && a_bs % 8 == 0 && b_bs % 8 == 0 && a_bs > 0 && b_bs > 0 && c_bs > 0 &&
+                   (c_bs * (out_dtype == FV_BF16 ? 2 : 4)) % 16 == 0,
+               "fv_gemm_bf16_batched: batch count / strides (16-byte multiples) invalid");
+    FV_REQUIRE(out_dtype == FV_BF16 || out_dtype == FV_F32 || out_dtype == FV_F32_ACC,
+               "fv_gemm_bf16_batched: out_dtype must be FV_BF16, FV_F32 or FV_F32_ACC");
+    FV_REQUIRE(splits == 1 || out_dtype == FV_F32_ACC, "fv_gemm_bf16_batched: split-K only with FV_F32_ACC (one plane per batch)");
+    return fv::gemm2_impl(nbatch, Mo, No, K, a_mn, A, lda, a_bs, b_mn, B, ldb, b_bs, out_dtype, C, ldc, c_bs, splits, stream);
 }
 namespace fv {
 static int gemm2_impl(int nbatch, int64_t Mo, int No, int64_t K, int a_mn, const void* A, int64_t lda, int64_t a_bs, int b_mn,

@@ -400,6 +400,34 @@ def gemm_bf16(a: Tensor, b: Tensor, a_mn: bool = False, b_mn: bool = False, out_
     return c
 
 
+def gemm_bf16_batched(a: Tensor, b: Tensor, a_mn: bool = False, b_mn: bool = False, out: Optional[Tensor] = None,
+                      out_f32: bool = False) -> Tensor:
+    """``nbatch`` independent products ``op(a[i]) @ op(b[i]).T`` in one launch (``fv_gemm_bf16_batched``).  a, b: 3-D bf16 with
+    unit inner stride (views with padded row / batch pitches allowed).  bf16 result, or fp32 (``out_f32``) accumulated over
+    K splits into a zeroed buffer with TMA reduction stores."""
+    _check_cuda(a, b)
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16 and a.dim() == 3 and b.dim() == 3
+    assert a.stride(2) == 1 and b.stride(2) == 1 and a.shape[0] == b.shape[0]
+    nb = a.shape[0]
+    K, Mo = (a.shape[1], a.shape[2]) if a_mn else (a.shape[2], a.shape[1])
+    Kb, No = (b.shape[1], b.shape[2]) if b_mn else (b.shape[2], b.shape[1])
+    assert K == Kb
+    if out_f32:
+        c = out if out is not None else torch.empty((nb, Mo, No), device=a.device, dtype=torch.float32)
+        assert c.dtype == torch.float32 and c.stride(2) == 1
+        c.zero_()
+        splits = int(_lib.lib().fv_gemm_bf16_splits(Mo, No, K))
+        splits = max(1, min(splits, max(1, int(_lib.lib().fv_gemm_bf16_splits(Mo * nb, No, K)))))   # nb batches share the SMs
+        _lib.call("fv_gemm_bf16_batched", nb, Mo, No, K, int(a_mn), _p(a), a.stride(1), a.stride(0), int(b_mn), _p(b), b.stride(1),
+                  b.stride(0), 2, _p(c), c.stride(1), c.stride(0), splits, _stream(a))
+        return c
+    c = out if out is not None else torch.empty((nb, Mo, No), device=a.device, dtype=torch.bfloat16)
+    assert c.dtype == torch.bfloat16 and c.stride(2) == 1
+    _lib.call("fv_gemm_bf16_batched", nb, Mo, No, K, int(a_mn), _p(a), a.stride(1), a.stride(0), int(b_mn), _p(b), b.stride(1),
+              b.stride(0), FV_BF16, _p(c), c.stride(1), c.stride(0), 1, _stream(a))
+    return c
+
+
 def gemm_bf16_ok(*ts: Tensor) -> bool:
     """Operands the general tcgen05 GEMM accepts: CUDA bf16 2-D, unit inner stride, 16-byte aligned rows."""
     for t in ts:
@@ -455,7 +483,7 @@ def x_proj(u: Tensor, x_w: Tensor, use_tc: bool = True) -> Tensor:
         ld = (ncols + 7) // 8 * 8
         buf = torch.empty((2, M, ld), device=u.device, dtype=u.dtype)
         _lib.call("fv_gemm_bf16_batched", 2, M, ncols, D, 0, _p(u), D, M * D, 0, _p(x_w), D, ncols * D, FV_BF16, _p(buf), ld,
-                  M * ld, _stream(u))     # both directions in one launch
+                  M * ld, 1, _stream(u))     # both directions in one launch
         return buf[..., :ncols]
     return torch.bmm(u.reshape(2, M, D), x_w.transpose(1, 2))
 

@@ -267,11 +267,11 @@ int fv_gemm_out_norm_flow(int64_t M, int N, int K, const void* A, int64_t lda, c
 int fv_gemm_bf16_splits(int64_t Mo, int No, int64_t K);
 int fv_gemm_bf16(int64_t Mo, int No, int64_t K, int a_mn, const void* A, int64_t lda, int b_mn, const void* B,
                  int64_t ldb, int out_dtype, void* C, int64_t ldc, int splits, void* stream);
-/* nbatch independent products in one launch (operand / result planes a_bs / b_bs / c_bs elements apart, multiples of 8; no
- * split-K): the two directions of x_proj. */
+/* nbatch independent products in one launch (operand / result planes a_bs / b_bs / c_bs elements apart, 16-byte multiples;
+ * split-K only with FV_F32_ACC): the two directions of x_proj and of the x_proj / dt_proj backward. */
 int fv_gemm_bf16_batched(int nbatch, int64_t Mo, int No, int64_t K, int a_mn, const void* A, int64_t lda, int64_t a_bs,
                          int b_mn, const void* B, int64_t ldb, int64_t b_bs, int out_dtype, void* C, int64_t ldc,
-                         int64_t c_bs, void* stream);
+                         int64_t c_bs, int splits, void* stream);
 /* ---- operator API helpers on (batch, dim, L), L contiguous ---------------------------------
  * The reference's fused autograd functions (selective_scan_interface.py:208-330, 452-605) call, on
  * (B, D, L) tensors: causal_conv1d_cuda.causal_conv1d_fwd(x, w, bias, None, True) (:496-498; third-party

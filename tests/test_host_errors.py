@@ -134,8 +134,9 @@ def test_round2_entry_points_validate_arguments_without_launching():
     assert l.fv_gemm_bf16(128, 64, 64, 0, p, 64, 0, p, 64, 7, p, 64, 1, null) != 0                 # unknown output type
     assert l.fv_gemm_bf16(128, 64, 128, 0, p, 128, 0, p, 128, _lib.FV_F32, p, 64, 3, null) != 0    # 3 splits > 2 k-blocks
     assert b"splits" in l.fv_last_error()
-    assert l.fv_gemm_bf16_batched(0, 128, 64, 64, 0, p, 64, 8192, 0, p, 64, 4096, _lib.FV_BF16, p, 64, 8192, null) != 0
-    assert l.fv_gemm_bf16_batched(2, 128, 64, 64, 0, p, 64, 8191, 0, p, 64, 4096, _lib.FV_BF16, p, 64, 8192, null) != 0
+    assert l.fv_gemm_bf16_batched(0, 128, 64, 64, 0, p, 64, 8192, 0, p, 64, 4096, _lib.FV_BF16, p, 64, 8192, 1, null) != 0
+    assert l.fv_gemm_bf16_batched(2, 128, 64, 64, 0, p, 64, 8191, 0, p, 64, 4096, _lib.FV_BF16, p, 64, 8192, 1, null) != 0
+    assert l.fv_gemm_bf16_batched(2, 128, 64, 128, 0, p, 128, 16384, 0, p, 128, 8192, _lib.FV_F32, p, 64, 8192, 2, null) != 0   # split-K: ACC only
     # split heuristic: fills the SMs, never leaves an empty split
     for Mo, No, K in [(768, 192, 50176), (3072, 768, 25088), (44, 1536, 1792), (128, 64, 64)]:
         s = l.fv_gemm_bf16_splits(Mo, No, K)
