@@ -21,11 +21,11 @@ from . import _lib, ops
 # streaming gate backward from the saved pre-norm value (csrc/gate_bwd_v.cu); "0" = round-1 recomputing kernel
 GATE_BWD_V = os.environ.get("FASTVIM_GATE_BWD_V", "1") != "0"
 # x_proj / dt_proj backward GEMMs (N or K = dt_rank, dt_rank + 2 d_state) on the general tcgen05 GEMM where every row pitch is a
-# multiple of 16 bytes (FastVim-S/B: dt_rank 24 / 48; FastVim-T's dt_rank 12 keeps cuBLAS bmm): four batched launches (both
-# directions each), the two wgrad ones accumulating their K splits with TMA reduction stores.  Step time equals the four
-# cuBLAS bmm calls (FastVim-B: 32.08 vs 32.09 ms); the first form -- eight single launches + plane reductions -- was 1.25 ms
-# slower.  "0" = cuBLAS.
-TC_SMALL_GEMM = os.environ.get("FASTVIM_TC_SMALL_GEMM", "1") != "0"
+# multiple of 16 bytes (FastVim-S/B: dt_rank 24 / 48): four batched launches (both directions each), the two wgrad ones
+# accumulating their K splits with TMA reduction stores.  Parity-tested; measured 0.43 ms per FastVim-B step SLOWER than the four
+# cuBLAS bmm calls (32.61 vs 32.17 ms, three alternating pairs on one box; eight single launches + plane reductions: +1.25 ms):
+# one 128-row tile wide and a few k-blocks deep, these products are latency-bound in a persistent tensor-core kernel.  Opt-in ("1").
+TC_SMALL_GEMM = os.environ.get("FASTVIM_TC_SMALL_GEMM", "0") == "1"
 # programmatic dependent launch for every kernel of the training forward / backward: measured between -0.6 % and +3.6 % on
 # the FastVim-B / -T step, i.e. inside the run-to-run spread of the training line (+-2 %); opt-in until it is measured at N > 1
 TRAIN_PDL = os.environ.get("FASTVIM_TRAIN_PDL", "0") == "1"
