@@ -11,6 +11,8 @@
 //                       * silu(z), y -- a pure streaming pass (w, z in; y out).
 // Reference semantics: x.flip / causal_conv1d / reshape.mean (:258-289), repeat_interleave + D skip (:325-340),
 // (out + out_b.flip) / 2, LayerNorm, * silu(z) (:400-420) -- same arithmetic as block_fwd.cu (w is rounded to bf16 there too).
+#include <cstdlib>
+
 #include "block_common.cuh"
 
 namespace fv {
@@ -22,8 +24,8 @@ int conv_pool_plain_w(const Geom& g, const bf16* x, int64_t ldx, int64_t xbs, co
 
 constexpr int CG_MAX_NI = 4;  // inner slots per thread (inner / IH): pool accumulators stay in registers
 
-template <bool MAXPOOL, int NIT>
-__global__ void __launch_bounds__(512)
+template <bool MAXPOOL, int NIT, int IHT>
+__global__ void __launch_bounds__(IHT > 0 ? 384 : 512)   // sliding form: window + taps + accumulators need > 128 registers
 conv_pool_group_kernel(Geom g, int IH, int TP, const bf16* __restrict__ x, int64_t ldx, int64_t xbs,
                        const float* __restrict__ cw, const float* __restrict__ cb, float scale,
                        const float* __restrict__ Dskip, bf16* __restrict__ u, bf16* __restrict__ wout) {
@@ -74,7 +76,43 @@ conv_pool_group_kernel(Geom g, int IH, int TP, const bf16* __restrict__ x, int64
             cp_async_wait<0>();
         }
         __syncthreads();
-        if (live) {
+        if (live && IHT > 0) {
+            // IH known at compile time: the thread's inner slots of one pooled step are IHT rows apart, so their 7-row windows
+            // overlap -- slide one window (7 - IHT rows carried in registers, IHT new rows unpacked per token) instead of
+            // fetching and unpacking seven rows per token (ncu: the ALU pipe, bf16 unpacks, was this kernel's busiest)
+            const bf16* cur = xs + (size_t)(c & 1) * bufrows * D + d0;
+            for (int p = 0; p < np; ++p) {
+                const int lt0 = p * inner + ih;                   // first slot's token; buffer rows lt0 .. lt0 + 6
+                const bf16* xp = cur + (size_t)lt0 * D;
+                float4 win[7];
+#pragma unroll
+                for (int r = 0; r < 7; ++r) win[r] = ld4(xp + (size_t)r * D);
+#pragma unroll
+                for (int k = 0; k < NIT; ++k) {
+                    if (k < NI) {
+                        if (k > 0) {
+#pragma unroll
+                            for (int r = 0; r < 7; ++r)
+                                win[r] = r + IHT < 7 ? win[(r + IHT) % 7] : ld4(xp + (size_t)(k * IHT + r) * D);
+                        }
+                        float4 af = tf.b, ab = tb.b;
+#pragma unroll
+                        for (int r = 0; r < 7; ++r) {
+                            if (r <= 3) af = fma4(tf.w[r], win[r], af);
+                            if (r >= 3) ab = fma4(tb.w[6 - r], win[r], ab);
+                        }
+                        const float4 xf = silu4_pre<true>(af), xr_ = silu4_pre<true>(ab);
+                        accf[k] = MAXPOOL ? max4(accf[k], xf) : accf[k] + xf;
+                        accb[k] = MAXPOOL ? max4(accb[k], xr_) : accb[k] + xr_;
+                        if (wb_) {
+                            const float4 wv = make_float4(fmaf(Db.x, xr_.x, Df.x * xf.x), fmaf(Db.y, xr_.y, Df.y * xf.y),
+                                                          fmaf(Db.z, xr_.z, Df.z * xf.z), fmaf(Db.w, xr_.w, Df.w * xf.w));
+                            st4(wb_ + (int64_t)rowtab[p_lo * inner + lt0 + k * IHT + 3] * D + d0, wv);
+                        }
+                    }
+                }
+            }
+        } else if (live) {
             const bf16* cur = xs + (size_t)(c & 1) * bufrows * D + d0;
 #pragma unroll
             for (int k = 0; k < NIT; ++k) {
@@ -304,9 +342,13 @@ extern "C" int fv_conv_pool_w_fwd(const fv_geom* g_, int dtype, const void* x, i
     const int NI = g.inner / p.IH;
     const bool mx = pool_mode == FV_POOL_MAX;
     void (*kern)(Geom, int, int, const bf16*, int64_t, int64_t, const float*, const float*, float, const float*, bf16*, bf16*);
-    if (NI <= 1) kern = mx ? conv_pool_group_kernel<true, 1> : conv_pool_group_kernel<false, 1>;
-    else if (NI <= 2) kern = mx ? conv_pool_group_kernel<true, 2> : conv_pool_group_kernel<false, 2>;
-    else kern = mx ? conv_pool_group_kernel<true, 4> : conv_pool_group_kernel<false, 4>;
+    const bool slide = p.threads <= 384 && (getenv("FASTVIM_CONV_GROUP_SLIDE") == nullptr || getenv("FASTVIM_CONV_GROUP_SLIDE")[0] != '0');
+#define FV_CG_PICK(NI_, IH_) (mx ? conv_pool_group_kernel<true, NI_, IH_> : conv_pool_group_kernel<false, NI_, IH_>)
+    if (NI <= 1) kern = FV_CG_PICK(1, 0);                                   // one slot per thread: nothing to slide over
+    else if (NI <= 2) kern = slide && p.IH == 1 ? FV_CG_PICK(2, 1) : slide && p.IH == 2 ? FV_CG_PICK(2, 2)
+                             : slide && p.IH == 4 ? FV_CG_PICK(2, 4) : FV_CG_PICK(2, 0);
+    else kern = slide && p.IH == 1 ? FV_CG_PICK(4, 1) : slide && p.IH == 2 ? FV_CG_PICK(4, 2) : FV_CG_PICK(4, 0);
+#undef FV_CG_PICK
     if (p.smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
         FV_REQUIRE(e == cudaSuccess, "fv_conv_pool_w_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
