@@ -30,7 +30,7 @@ int sm_count();
 constexpr int ON_BM = 128, ON_BK = 64, ON_THREADS = 224;
 constexpr uint32_t ON_A_BYTES = ON_BM * ON_BK * 2;  // 16 KB
 constexpr uint32_t ON_T_BYTES = 128 * 128;          // one staged / residual tile: 128 rows x 128 B
-constexpr int ON_RS = 3;                            // residual chunk ring
+constexpr int ON_RS = 4;                            // residual chunk ring (3 -> 4: the epilogue's largest stall was the wait for a chunk)
 constexpr int ON_CS = 2;                            // output staging tiles
 constexpr int ON_TQ = 4;                            // tile queue depth (flow mode)
 
@@ -101,6 +101,8 @@ gemm_out_norm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
     tq.empty = tq.full + ON_TQ;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tq.empty + ON_TQ);
     tq.slots = reinterpret_cast<int*>(tmem_ptr + 2);
+    float* sNw = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tq.slots + ON_TQ) + 15) & ~(uintptr_t)15);   // [BN] norm weights
+    for (int i = threadIdx.x; i < BN; i += ON_THREADS) sNw[i] = a.norm_w[i];
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < NS; ++i) {
@@ -291,10 +293,10 @@ gemm_out_norm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
                     uint32_t r[32];
                     tc_ld32(t0 + c * 64 + h * 32, r);
                     tc_wait_ld();
-                    const float4* wp = reinterpret_cast<const float4*>(a.norm_w + c * 64 + h * 32);
+                    const float4* wp = reinterpret_cast<const float4*>(sNw + c * 64 + h * 32);
 #pragma unroll
                     for (int v = 0; v < 8; ++v) {
-                        const float4 wq = __ldg(wp + v);
+                        const float4 wq = wp[v];
                         r[4 * v] = __float_as_uint(__uint_as_float(r[4 * v]) * rstd * wq.x);
                         r[4 * v + 1] = __float_as_uint(__uint_as_float(r[4 * v + 1]) * rstd * wq.y);
                         r[4 * v + 2] = __float_as_uint(__uint_as_float(r[4 * v + 2]) * rstd * wq.z);
@@ -332,7 +334,7 @@ gemm_out_norm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_const
 }
 
 static bool plan_out_norm(int BN, int* ns, size_t* bytes) {
-    const size_t stage = ON_A_BYTES + (size_t)BN * ON_BK * 2, fixed = 48 * 8 + 64 + 1024, cap = 227 * 1024;
+    const size_t stage = ON_A_BYTES + (size_t)BN * ON_BK * 2, fixed = 48 * 8 + 64 + 1024 + 1024, cap = 227 * 1024;
     for (int n = 4; n >= 2; --n) {
         const size_t tot = (size_t)n * stage + (size_t)(ON_RS + ON_CS) * ON_T_BYTES + fixed;
         if (tot <= cap) {
