@@ -286,7 +286,7 @@ static int pick_bn(int N) {
 // Stream mode (large K, e.g. FastVim-B and the patch embedding, K = 768 / 1536): ring of (A + W k-block) stages.
 static bool plan_smem(int KB, int BN, int* ns, int* nc, int* stream, size_t* bytes) {
     const size_t wblk = (size_t)BN * GT_BK * 2, fixed = (size_t)(KB + 16) * 8 + 16 + 1024, cap = 227 * 1024;
-    const int opts[5][2] = {{4, 2}, {3, 2}, {4, 1}, {3, 1}, {2, 1}};
+    const int opts[7][2] = {{6, 2}, {5, 2}, {4, 2}, {3, 2}, {4, 1}, {3, 1}, {2, 1}};   // deepest A ring that fits: more bytes in flight
     for (auto& o : opts) {
         const size_t tot = (size_t)KB * wblk + (size_t)o[0] * GT_A_STAGE_BYTES + (size_t)o[1] * GT_C_STAGE_BYTES + fixed;
         if (tot <= cap && o[0] >= 3) {
