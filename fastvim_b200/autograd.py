@@ -215,6 +215,43 @@ def mixer_forward_train(mixer, hidden_states, geom, act_dtype):
                          m.dt_rank)
 
 
+# patch embedding under autograd on the library's kernels; "0" = eager unfold + cuBLAS F.linear
+NATIVE_PATCH_TRAIN = os.environ.get("FASTVIM_NATIVE_PATCH_TRAIN", "1") != "0"
+
+
+class PatchEmbedFn(torch.autograd.Function):
+    """Training form of the patch embedding (reference models/fastvim.py:67-103, an ``nn.Conv2d`` with kernel = stride =
+    patch under autocast): ``fv_patchify`` (one pass image -> bf16 patches) + the tcgen05 GEMM with the bias added in its
+    epilogue.  Backward: ``dW = dY.T @ patches`` on the general tcgen05 GEMM (both operands MN-major, split-K over the
+    tokens, fp32), ``db`` = column sums of ``dY``.  The images get no gradient (callers with ``x.requires_grad`` stay on
+    the eager path).  ``w`` (E, C, p, p) / ``b`` (E) are the MASTER parameters: they are cast here, outside autograd, on
+    every call (a CUDA-graph-replayed optimizer step never bumps ``_version``, so nothing is cached)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, patch, per_channel=False):
+        # (B*gh*gw, C*p*p) bf16; per channel (FastChannelVim's shared projection): (B*C*gh*gw, p*p)
+        cols = ops.patchify(x, patch, per_channel=per_channel)
+        wmat = w.reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
+        # the reference's autocast conv adds the bias rounded to bf16; keep that rounding, in an fp32 container
+        b32 = None if b is None else b.to(torch.bfloat16).float().contiguous()
+        out = ops.gemm_bf16_tn(cols, wmat, bias=b32)
+        ctx.save_for_backward(cols)
+        ctx.meta = (tuple(w.shape), w.dtype, None if b is None else b.dtype)
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        (cols,) = ctx.saved_tensors
+        wshape, wdt, bdt = ctx.meta
+        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        dw = db = None
+        if ctx.needs_input_grad[1]:
+            dw = _wgrad(dy2, cols).reshape(wshape).to(wdt)
+        if bdt is not None and ctx.needs_input_grad[2]:
+            db = dy2.sum(dim=0, dtype=torch.float32).to(bdt)
+        return None, dw, db, None, None
+
+
 class AddNormFn(torch.autograd.Function):
     @staticmethod
     @_train_pdl

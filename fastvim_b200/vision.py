@@ -22,6 +22,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch import Tensor
 
+from . import autograd as fv_autograd
 from . import ops
 from .mixer import Mamba
 from .mixer import linear as _linear
@@ -117,6 +118,12 @@ class PatchEmbed(nn.Module):
             else:
                 wmat, bias32 = self._folded_plain()
             out = ops.gemm_bf16_tn(cols, wmat, bias=bias32)
+        elif (not no_grad and fv_autograd.NATIVE_PATCH_TRAIN and not x.requires_grad and act_dtype == torch.bfloat16
+              and p0 == p1 and x.is_cuda and x.dtype in (torch.float32, torch.bfloat16)
+              and ops.patchify_supported(x.contiguous(), p0) and ops.gemm_supported(B * gh * gw, w.shape[0], C * p0 * p1)
+              and C * p0 * p1 % 8 == 0 and w.shape[0] % 8 == 0):
+            # training: same two kernels under autograd, weight gradient on the general tcgen05 GEMM
+            out = fv_autograd.PatchEmbedFn.apply(x.contiguous(), w, self.proj.bias, p0)
         else:
             if x.dtype == torch.uint8:
                 x = self._uint8_to_float(x)

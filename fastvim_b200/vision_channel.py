@@ -24,6 +24,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 from torch import Tensor
 
+from . import autograd as fv_autograd
 from . import ops
 from .mixer import linear as _linear
 from .mixer_channel import Mamba
@@ -74,17 +75,23 @@ class PatchEmbedPerChannel(nn.Module):
         autocast = torch.is_autocast_enabled("cuda")
         act_dtype = torch.get_autocast_dtype("cuda") if autocast else x.dtype
         no_grad = not (torch.is_grad_enabled() and (wt.requires_grad or x.requires_grad))
-        if (no_grad and act_dtype == torch.bfloat16 and p0 == p1 and x.is_cuda and x.dtype in (torch.float32, torch.bfloat16)
-                and ops.patchify_supported(x.contiguous(), p0)):
-            cols = ops.patchify(x.contiguous(), p0, per_channel=True)     # one pass image -> bf16 patches (fv_patchify)
+        native_in = (act_dtype == torch.bfloat16 and p0 == p1 and x.is_cuda and x.dtype in (torch.float32, torch.bfloat16)
+                     and ops.patchify_supported(x.contiguous(), p0))
+        if (native_in and not no_grad and fv_autograd.NATIVE_PATCH_TRAIN and not x.requires_grad
+                and ops.gemm_supported(B * num_channels * gh * gw, wt.shape[0], p0 * p1) and wt.shape[0] % 8 == 0):
+            # training: fv_patchify + tcgen05 GEMM under autograd, weight gradient on the general tcgen05 GEMM
+            out = fv_autograd.PatchEmbedFn.apply(x.contiguous(), wt, self.proj.bias, p0, True)
         else:
-            cols = x.reshape(B, num_channels, gh, p0, gw, p1).permute(0, 1, 2, 4, 3, 5).reshape(-1, p0 * p1).to(act_dtype)
-        wmat = wt.reshape(wt.shape[0], -1).to(cols.dtype)
-        bias = None if self.proj.bias is None else self.proj.bias.to(cols.dtype)
-        if cols.is_cuda and no_grad:
-            out = _linear(cols, wmat, bias)
-        else:
-            out = F.linear(cols, wmat, bias)
+            if native_in and no_grad:
+                cols = ops.patchify(x.contiguous(), p0, per_channel=True)     # one pass image -> bf16 patches (fv_patchify)
+            else:
+                cols = x.reshape(B, num_channels, gh, p0, gw, p1).permute(0, 1, 2, 4, 3, 5).reshape(-1, p0 * p1).to(act_dtype)
+            wmat = wt.reshape(wt.shape[0], -1).to(cols.dtype)
+            bias = None if self.proj.bias is None else self.proj.bias.to(cols.dtype)
+            if cols.is_cuda and no_grad:
+                out = _linear(cols, wmat, bias)
+            else:
+                out = F.linear(cols, wmat, bias)
         out = out.reshape(B, num_channels, gh, gw, -1)                            # (B, C, H/ps, W/ps, E)
         out = out + channel_embed.to(out.dtype)[:, :, None, None, :]              # channel-specific offsets (:184)
         if self.scanpath_type == "colwise":

@@ -166,3 +166,95 @@ def test_x_proj_batched_gemm_vs_fp64(Bt, Lp, D, ncols):
     err = (xdbl.double() - want).abs().max().item() / want.abs().max().item()
     assert err < 4e-3, err
     assert torch.equal(xdbl, ops.x_proj(u, xw))          # deterministic
+
+
+@pytest.mark.parametrize("embed,batch,xdt", [(192, 8, torch.float32), (768, 3, torch.float32), (192, 5, torch.bfloat16)])
+def test_patch_embed_training_on_library_kernels(embed, batch, xdt, monkeypatch):
+    """PatchEmbed under autograd (reference models/fastvim.py:67-103, an nn.Conv2d under autocast): fv_patchify + tcgen05
+    GEMM forward, weight gradient on the general tcgen05 GEMM -- against an fp64 convolution of the same bf16-rounded
+    operands, and against the eager unfold + F.linear path it replaces."""
+    import torch.nn.functional as F
+
+    from fastvim_b200 import _lib
+    from fastvim_b200 import autograd as fv_autograd
+    from fastvim_b200.vision import PatchEmbed
+
+    torch.manual_seed(embed + batch)
+    pe = PatchEmbed(img_size=224, patch_size=16, in_chans=3, embed_dim=embed).cuda()
+    x = torch.randn(batch, 3, 224, 224, device="cuda").to(xdt)
+    g = torch.randn(batch, 196, embed, device="cuda")
+
+    names = []
+    real = _lib.call
+    monkeypatch.setattr(_lib, "call", lambda name, *a: (names.append(name), real(name, *a))[1])
+
+    def run():
+        pe.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = pe(x)
+        (out.float() * g).sum().backward()
+        return out.detach(), pe.proj.weight.grad.clone(), pe.proj.bias.grad.clone()
+
+    out, dw, db = run()
+    assert "fv_patchify" in names and "fv_gemm_bf16_tn" in names and "fv_gemm_bf16" in names, names
+    assert out.dtype == torch.bfloat16 and dw.dtype == torch.float32 and dw.shape == pe.proj.weight.shape
+
+    xd = x.bfloat16().double()
+    wd = pe.proj.weight.detach().bfloat16().double().requires_grad_()
+    bd = pe.proj.bias.detach().bfloat16().double().requires_grad_()
+    want = F.conv2d(xd, wd, bd, stride=16).flatten(2).transpose(1, 2)
+    assert (out.double() - want).abs().max() <= 2 ** -7 * want.abs().max()          # one bf16 rounding of the output
+    (want * g.bfloat16().double()).sum().backward()                                  # the upstream gradient arrives in bf16
+    assert (dw.double() - wd.grad).abs().max() <= 1e-4 * wd.grad.abs().max()
+    assert (db.double() - bd.grad).abs().max() <= 1e-4 * bd.grad.abs().max()
+
+    monkeypatch.setattr(fv_autograd, "NATIVE_PATCH_TRAIN", False)
+    names.clear()
+    out_e, dw_e, db_e = run()
+    assert "fv_patchify" not in names
+    assert (out.float() - out_e.float()).abs().max() <= 2 ** -7 * out_e.float().abs().max()
+    assert (dw - dw_e).abs().max() <= 2e-2 * dw_e.abs().max()      # the eager path rounds dW through bf16 (autocast F.linear)
+    assert (db - db_e).abs().max() <= 2e-2 * db_e.abs().max()
+
+
+def test_patch_embed_per_channel_training_on_library_kernels(monkeypatch):
+    """FastChannelVim's shared per-channel projection under autograd (reference channelvim PatchEmbedPerChannel, an
+    nn.Conv3d with a (1, p, p) kernel): native path vs the eager unfold + F.linear path on the same inputs, and vs fp64."""
+    from fastvim_b200 import _lib
+    from fastvim_b200 import autograd as fv_autograd
+    from fastvim_b200.vision_channel import PatchEmbedPerChannel
+
+    torch.manual_seed(5)
+    pe = PatchEmbedPerChannel(img_size=224, patch_size=16, stride=16, in_chans=5, embed_dim=384, hcs=False).cuda()
+    x = torch.randn(2, 5, 224, 224, device="cuda")
+    names = []
+    real = _lib.call
+    monkeypatch.setattr(_lib, "call", lambda name, *a: (names.append(name), real(name, *a))[1])
+
+    def run():
+        pe.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = pe(x)[0]
+        g = torch.linspace(-1, 1, out.numel(), device="cuda").reshape(out.shape)
+        (out.float() * g).sum().backward()
+        return out.detach(), pe.proj.weight.grad.clone(), pe.proj.bias.grad.clone(), pe.channel_embed.weight.grad.clone(), g
+
+    out, dw, db, dce, g = run()
+    assert "fv_patchify" in names and "fv_gemm_bf16_tn" in names and "fv_gemm_bf16" in names, names
+    assert dw.shape == pe.proj.weight.shape and dw.dtype == torch.float32
+
+    # fp64 statement of the projection gradient: tokens are (b, gh, gw, c) in Channel-First order
+    cols = x.bfloat16().double().reshape(2, 5, 14, 16, 14, 16).permute(0, 2, 4, 1, 3, 5).reshape(-1, 256)
+    want_dw = g.bfloat16().double().reshape(-1, 384).t() @ cols
+    assert (dw.double().reshape(384, 256) - want_dw).abs().max() <= 1e-4 * want_dw.abs().max()
+    want_db = g.bfloat16().double().reshape(-1, 384).sum(0)
+    assert (db.double() - want_db).abs().max() <= 1e-4 * want_db.abs().max()
+
+    monkeypatch.setattr(fv_autograd, "NATIVE_PATCH_TRAIN", False)
+    names.clear()
+    out_e, dw_e, db_e, dce_e, _ = run()
+    assert "fv_patchify" not in names
+    assert (out.float() - out_e.float()).abs().max() <= 2 ** -6 * out_e.float().abs().max()
+    assert (dw - dw_e).abs().max() <= 2e-2 * dw_e.abs().max()
+    assert (db - db_e).abs().max() <= 2e-2 * db_e.abs().max()
+    assert (dce - dce_e).abs().max() <= 2e-2 * dce_e.abs().max()
