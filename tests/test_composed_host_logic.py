@@ -154,3 +154,60 @@ def test_mamba_inner_fn_autograd_host_logic(has_z, monkeypatch):
         for i, (a, b) in enumerate(zip(gg, gw)):
             assert a is not None and a.shape == b.shape, i
             assert_close(a, b, 5e-5, f"grad {i}")
+
+
+@pytest.mark.parametrize("per_channel", [False, True])
+def test_patch_embed_fn_host_logic(per_channel, monkeypatch):
+    """autograd.PatchEmbedFn with the two kernel wrappers replaced by torch stand-ins of the same contract (bf16 patches;
+    fp32-accumulated GEMM with the fp32 bias added before the bf16 rounding): output, weight and bias gradients against
+    autograd through the reference's own statement, an nn.Conv2d / shared-filter Conv3d over bf16-rounded operands
+    (models/fastvim.py:67-103, channelvim PatchEmbedPerChannel)."""
+    import torch.nn.functional as F
+
+    from fastvim_b200 import autograd as A
+    from fastvim_b200 import ops
+
+    def patchify(img, patch, per_channel=False):
+        B, C, H, W = img.shape
+        gh, gw = H // patch, W // patch
+        t = img.reshape(B, C, gh, patch, gw, patch)
+        t = t.permute(0, 1, 2, 4, 3, 5).reshape(-1, patch * patch) if per_channel else \
+            t.permute(0, 2, 4, 1, 3, 5).reshape(B * gh * gw, C * patch * patch)
+        return t.to(torch.bfloat16)
+
+    def gemm_bf16_tn(a, w, out=None, bias=None):
+        assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and (bias is None or bias.dtype == torch.float32)
+        acc = a.float() @ w.float().t()
+        return (acc if bias is None else acc + bias).to(torch.bfloat16)
+
+    monkeypatch.setattr(ops, "patchify", patchify)
+    monkeypatch.setattr(ops, "gemm_bf16_tn", gemm_bf16_tn)
+    torch.manual_seed(3)
+    B, C, p, E = 2, 3, 4, 16
+    x = torch.randn(B, C, 8, 12)
+    w = (torch.randn(E, 1 if per_channel else C, p, p) * 0.2).requires_grad_()
+    b = torch.randn(E).requires_grad_()
+    out = A.PatchEmbedFn.apply(x, w, b, p, per_channel)
+    ntok = B * (C if per_channel else 1) * 2 * 3
+    assert out.shape == (ntok, E) and out.dtype == torch.bfloat16
+    g = torch.randn(ntok, E).to(torch.bfloat16)
+    out.backward(g)
+    assert w.grad.shape == w.shape and w.grad.dtype == torch.float32 and b.grad.dtype == torch.float32
+
+    xr = x.to(torch.bfloat16).double()
+    wr = w.detach().to(torch.bfloat16).double().requires_grad_()
+    br = b.detach().to(torch.bfloat16).double().requires_grad_()
+    if per_channel:   # the same filter on every channel; tokens in (b, c, gh, gw) order
+        want = F.conv2d(xr.reshape(B * C, 1, 8, 12), wr, br, stride=p).flatten(2).transpose(1, 2).reshape(ntok, E)
+    else:
+        want = F.conv2d(xr, wr, br, stride=p).flatten(2).transpose(1, 2).reshape(ntok, E)
+    assert (out.double() - want).abs().max() <= 2 ** -8 * want.abs().max() + 1e-6
+    want.backward(g.double())
+    # on CPU tensors _wgrad falls back to a bf16 matmul whose RESULT is rounded to bf16 (the tcgen05 / cuBLAS forms write the
+    # fp32 accumulator; tests/test_gpu_gemm_general.py holds them to 1e-4)
+    assert (w.grad.double() - wr.grad).abs().max() <= 2 ** -7 * wr.grad.abs().max()
+    assert_close(b.grad, br.grad.float(), 1e-5, "db")
+    # no bias; frozen projection
+    w2 = w.detach().clone().requires_grad_()
+    A.PatchEmbedFn.apply(x, w2, None, p, per_channel).backward(g)
+    assert torch.equal(w2.grad, w.grad)
